@@ -1,0 +1,230 @@
+// oracle/ref_wrap.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Thin C-ABI wrapper that lets the tests / the cpu_baseline leg of bench.py call the
+// UNMODIFIED reference encoder (compiled where it lies under /root/reference by
+// oracle/Makefile into oracle/_ref/libmptc_ref.so).  Nothing under mptc_b200/ may
+// link, import or execute this.
+//
+// The reference's only frame entry point loads a PNG (dxt_image.cpp:385).  A raw-RGB
+// constructor `DXTImage(int,int,uint8_t*)` is declared (dxt_image.h:52) but never
+// defined, so this TU textually includes dxt_image.cpp (to reach its file-static
+// helpers CompressRGB / PhysicalToLogicalBlocks) and supplies that missing
+// definition: it performs exactly the steps of the PNG constructor after stbi_load
+// (dxt_image.cpp:403-434).  mptc_ref_selfcheck_png() proves both constructors agree.
+#include "dxt_image.cpp"   // reference TU, unmodified (found via -I<ref>/codec)
+
+#include "codec.h"
+#include "arithmetic_codec.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <unistd.h>
+
+namespace MPTC {
+// The declared-but-undefined raw constructor (dxt_image.h:52).
+DXTImage::DXTImage(int width, int height, uint8_t *rgb) {
+  _width = width;
+  _height = height;
+  _is_intra = true;
+  _search_area = 0;
+  _blocks_width = (_width + 3) >> 2;
+  _blocks_height = (_height + 3) >> 2;
+  const int num_blocks = _blocks_width * _blocks_height;
+  _num_blocks = num_blocks;
+  _found_at.resize(num_blocks);
+  _found.resize(num_blocks);
+  std::fill(_found.begin(), _found.end(), 0);
+  _index_mask.resize(num_blocks);
+  _src_img.assign(rgb, rgb + (size_t)_width * _height * 3);
+  _physical_blocks.resize(num_blocks);
+  for (int physical_idx = 0; physical_idx < num_blocks; ++physical_idx) {
+    int i = physical_idx % _blocks_width;
+    int j = physical_idx / _blocks_width;
+    const unsigned char *offset_data = _src_img.data() + ((size_t)j * 4 * _width + i * 4) * 3;
+    _physical_blocks[physical_idx].dxt_block = CompressRGB(offset_data, _width);
+  }
+  _logical_blocks = std::move(PhysicalToLogicalBlocks(_physical_blocks));
+  MakeDict();
+}
+}  // namespace MPTC
+
+using MPTC::DXTImage;
+
+struct RefFrame {
+  std::unique_ptr<DXTImage> img;
+  double t_fit_s = 0, t_search_s = 0, t_entropy_s = 0;
+};
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static void decode_stream(const uint8_t *src, uint32_t nbytes, size_t nsym, uint8_t *dst) {
+  // The reference's own arithmetic decoder (arithmetic_codec.cpp:391) turns a stream
+  // back into the symbol plane the encoder consumed.
+  std::vector<uint8_t> buf(src, src + nbytes);
+  buf.resize(nbytes + 16, 0);
+  entropy::Arithmetic_Codec dec((unsigned)buf.size(), buf.data());
+  entropy::Adaptive_Data_Model model(257);
+  dec.start_decoder();
+  for (size_t i = 0; i < nsym; ++i) dst[i] = (uint8_t)dec.decode(model);
+  dec.stop_decoder();
+}
+
+extern "C" {
+
+void mptc_ref_quiet(void) {
+  // The reference prints per-frame chatter on std::cout (codec.cpp:846-848 etc).
+  std::cout.setstate(std::ios_base::failbit);
+}
+
+void *mptc_ref_frame_new(int w, int h, const uint8_t *rgb, int is_intra, int search_area,
+                         int err_threshold) {
+  RefFrame *f = new RefFrame;
+  double t0 = now_s();
+  f->img.reset(new DXTImage(w, h, const_cast<uint8_t *>(rgb)));
+  f->t_fit_s = now_s() - t0;
+  f->img->_is_intra = is_intra != 0;
+  f->img->_search_area = search_area;
+  DXTImage::_err_threshold = err_threshold;  // what the PNG ctor does (dxt_image.cpp:393-394)
+  vErrThreshold = err_threshold;
+  return f;
+}
+
+void mptc_ref_frame_free(void *p) { delete static_cast<RefFrame *>(p); }
+
+int mptc_ref_num_blocks(void *p) { return static_cast<RefFrame *>(p)->img->_num_blocks; }
+
+void mptc_ref_get_blocks(void *p, uint64_t *out) {
+  auto &v = static_cast<RefFrame *>(p)->img->_physical_blocks;
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].dxt_block;
+}
+
+// Reencode(prev, -1) exactly as CompressMultiUnique calls it (codec.cpp:1394).
+void mptc_ref_reencode(void *p, void *prev) {
+  RefFrame *f = static_cast<RefFrame *>(p);
+  std::unique_ptr<DXTImage> null_ref;
+  double t0 = now_s();
+  if (prev) f->img->Reencode(static_cast<RefFrame *>(prev)->img, -1);
+  else f->img->Reencode(null_ref, -1);
+  f->t_search_s = now_s() - t0;
+}
+
+void mptc_ref_get_motion(void *p, uint8_t *out /* 2*nb */) {
+  auto &v = static_cast<RefFrame *>(p)->img->_motion_indices;
+  for (size_t i = 0; i < v.size(); ++i) {
+    out[2 * i] = std::get<0>(v[i]);
+    out[2 * i + 1] = std::get<1>(v[i]);
+  }
+}
+
+int mptc_ref_num_unique(void *p) {
+  return (int)static_cast<RefFrame *>(p)->img->_unique_palette.size();
+}
+
+void mptc_ref_get_unique(void *p, uint32_t *out) {
+  auto &v = static_cast<RefFrame *>(p)->img->_unique_palette;
+  memcpy(out, v.data(), v.size() * 4);
+}
+
+// Encoder-internal PSNR (logical blocks; dxt_image.cpp:363).
+double mptc_ref_psnr_logical(void *p) { return static_cast<RefFrame *>(p)->img->PSNR(); }
+
+// PSNR of what a decoder reconstructs: rebuild logical blocks from the emitted
+// physical blocks with the reference's own PhysicalToLogical, then its own PSNR().
+double mptc_ref_psnr_physical(void *p) {
+  RefFrame *f = static_cast<RefFrame *>(p);
+  std::vector<LogicalDXTBlock> keep = f->img->_logical_blocks;
+  f->img->SetLogicalBlocks();
+  double r = f->img->PSNR();
+  f->img->_logical_blocks = keep;
+  return r;
+}
+
+// Runs the reference's per-frame EntropyEncode (codec.cpp:1115 -> CompressEndpoint :804)
+// and returns the payload bytes it appends.  Only defined by the reference when the
+// endpoint planes are multiples of 64 blocks (image_processing.h:293-294).
+int mptc_ref_entropy_encode(void *p, uint8_t *out, int out_cap) {
+  RefFrame *f = static_cast<RefFrame *>(p);
+  std::vector<uint8_t> bytes;
+  double t0 = now_s();
+  MPTC::EntropyEncode(f->img, bytes);
+  f->t_entropy_s = now_s() - t0;
+  if ((int)bytes.size() > out_cap) return -(int)bytes.size();
+  memcpy(out, bytes.data(), bytes.size());
+  return (int)bytes.size();
+}
+
+// Splits a frame payload produced above into its five streams and decodes the four
+// endpoint streams back to symbol planes with the reference's decoder:
+// planes = ep1_Y(nb) | ep1_Co(nb) | ep1_Cg(nb) | ep2_Y | ep2_Co | ep2_Cg.
+// sizes[5] = compressed bytes of motion, Y1, C1, Y2, C2.
+int mptc_ref_payload_planes(const uint8_t *payload, int nbytes, int nb, uint8_t *planes,
+                            uint8_t *motion /* 2*nb */, uint32_t *sizes) {
+  const uint8_t *q = payload;
+  uint32_t n_unique, msz;
+  memcpy(&n_unique, q, 4); q += 4;
+  memcpy(&msz, q, 4); q += 4;
+  sizes[0] = msz;
+  decode_stream(q, msz, (size_t)2 * nb, motion);
+  q += msz;
+  uint8_t *dst = planes;
+  for (int s = 0; s < 4; ++s) {
+    uint32_t sz;
+    memcpy(&sz, q, 4); q += 4;
+    sizes[1 + s] = sz;
+    size_t nsym = (s & 1) ? (size_t)2 * nb : (size_t)nb;
+    decode_stream(q, sz, nsym, dst);
+    dst += nsym;
+    q += sz;
+  }
+  return (int)(q - payload) == nbytes ? (int)n_unique : -1;
+}
+
+void mptc_ref_get_times(void *p, double *out3) {
+  RefFrame *f = static_cast<RefFrame *>(p);
+  out3[0] = f->t_fit_s; out3[1] = f->t_search_s; out3[2] = f->t_entropy_s;
+}
+
+// Encode an arbitrary byte vector the way the palette / plane streams are encoded
+// (codec.cpp:186-197: Adaptive_Data_Model(257), start..stop).  Used to pin the host coder.
+int mptc_ref_arith_encode(const uint8_t *sym, int n, uint8_t *out, int out_cap) {
+  std::vector<uint8_t> tmp((size_t)n * 2 + 1024, 0);
+  entropy::Arithmetic_Codec enc((unsigned)tmp.size(), tmp.data());
+  entropy::Adaptive_Data_Model model(257);
+  enc.start_encoder();
+  for (int i = 0; i < n; ++i) enc.encode(sym[i], model);
+  unsigned nb = enc.stop_encoder();
+  if ((int)nb > out_cap) return -(int)nb;
+  memcpy(out, tmp.data(), nb);
+  return (int)nb;
+}
+
+// Whole-sequence encode through the reference's own driver (codec.cpp:1307), from a
+// directory of PNGs to a stream file.
+void mptc_ref_compress_multi_unique(const char *dir, const char *out_file, unsigned search_area,
+                                    int thr, unsigned intra_interval, unsigned unique_interval) {
+  MPTC::CompressMultiUnique(dir, out_file, search_area, thr, intra_interval, unique_interval, "");
+}
+
+// Proves the supplied raw constructor == the reference's PNG constructor
+// (dxt_image.cpp:385): writes the frame as PNG with the reference's bundled
+// stb_image_write, loads it through the real constructor, compares every block.
+int mptc_ref_selfcheck_png(int w, int h, const uint8_t *rgb) {
+  char path[64];
+  snprintf(path, sizeof path, "/tmp/mptc_ref_selfcheck_%d.png", (int)getpid());
+  if (!stbi_write_png(path, w, h, 3, rgb, 3 * w)) return -1;
+  DXTImage a(std::string(path), true, 4, 50);
+  DXTImage b(w, h, const_cast<uint8_t *>(rgb));
+  unlink(path);
+  if (a._physical_blocks.size() != b._physical_blocks.size()) return -2;
+  int bad = 0;
+  for (size_t i = 0; i < a._physical_blocks.size(); ++i)
+    bad += a._physical_blocks[i].dxt_block != b._physical_blocks[i].dxt_block;
+  return bad;
+}
+
+}  // extern "C"
