@@ -1,0 +1,109 @@
+"""ctypes binding of oracle/libmptc_oracle.so (the plain-C restatement, mptc_oracle.c).
+TEST INFRASTRUCTURE: only tests/, bench.py's cpu_baseline / --impl reference legs and
+__graft_entry__.smoke() may import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmptc_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mptc_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "port"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, ci = C.c_void_p, C.c_int
+        L.mptc_oracle_dxt1_fit.argtypes = [vp, ci, ci, vp]
+        L.mptc_oracle_reencode.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp]
+        L.mptc_oracle_eval_candidate.argtypes = [vp, C.c_uint64, C.c_uint32, vp, vp]
+        L.mptc_oracle_endpoint_planes.argtypes = [vp, ci, ci, vp]
+        L.mptc_oracle_arith_encode.argtypes = [vp, ci, vp, ci]
+        L.mptc_oracle_psnr.restype = C.c_double
+        L.mptc_oracle_psnr.argtypes = [vp, ci, ci, vp]
+        L.mptc_oracle_tables.argtypes = [vp, vp]
+        L.mptc_oracle_encode_gops.restype = C.c_double
+        L.mptc_oracle_encode_gops.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
+        _lib = L
+    return _lib
+
+
+def dxt1_fit(rgb: np.ndarray) -> np.ndarray:
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w = rgb.shape[:2]
+    out = np.empty((h // 4) * (w // 4), dtype=np.uint64)
+    lib().mptc_oracle_dxt1_fit(rgb.ctypes.data, w, h, out.ctypes.data)
+    return out
+
+
+def reencode(rgb, is_intra, search_area, err_threshold, init_blocks, prev_blocks=None):
+    """-> (final_blocks u64[nb], motion u8[2nb], unique u32[n])."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w = rgb.shape[:2]
+    blocks = np.array(init_blocks, dtype=np.uint64, copy=True)
+    nb = blocks.size
+    motion = np.empty(2 * nb, dtype=np.uint8)
+    unique = np.empty(nb, dtype=np.uint32)
+    pp = None
+    if prev_blocks is not None:
+        prev_blocks = np.ascontiguousarray(prev_blocks, dtype=np.uint64)
+        pp = prev_blocks.ctypes.data
+    n = lib().mptc_oracle_reencode(rgb.ctypes.data, w, h, int(is_intra), search_area, err_threshold,
+                                   blocks.ctypes.data, pp, motion.ctypes.data, unique.ctypes.data)
+    return blocks, motion, unique[:n].copy()
+
+
+def endpoint_planes(blocks, bw, bh) -> np.ndarray:
+    """-> uint8 [6, pbh, pbw] with pbw/pbh = bw/bh rounded up to multiples of 64."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint64)
+    pbw, pbh = (bw + 63) // 64 * 64, (bh + 63) // 64 * 64
+    out = np.empty((6, pbh, pbw), dtype=np.uint8)
+    lib().mptc_oracle_endpoint_planes(blocks.ctypes.data, bw, bh, out.ctypes.data)
+    return out
+
+
+def arith_encode(sym) -> bytes:
+    sym = np.ascontiguousarray(sym, dtype=np.uint8)
+    cap = 2 * sym.size + 1024
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib().mptc_oracle_arith_encode(sym.ctypes.data, sym.size, out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].tobytes()
+
+
+def psnr(rgb, blocks) -> float:
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint64)
+    return lib().mptc_oracle_psnr(rgb.ctypes.data, rgb.shape[1], rgb.shape[0], blocks.ctypes.data)
+
+
+def tables():
+    a = np.empty((256, 2), dtype=np.uint8)
+    b = np.empty((256, 2), dtype=np.uint8)
+    lib().mptc_oracle_tables(a.ctypes.data, b.ctypes.data)
+    return a, b
+
+
+def encode_gops(frames, gop, search_area, err_threshold, threads, want_outputs=True):
+    """CPU baseline: -> (seconds, blocks[n, nb] or None, motion[n, 2nb] or None)."""
+    frames = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, h, w = frames.shape[:3]
+    nb = (h // 4) * (w // 4)
+    ob = np.empty((n, nb), dtype=np.uint64) if want_outputs else None
+    om = np.empty((n, 2 * nb), dtype=np.uint8) if want_outputs else None
+    t = lib().mptc_oracle_encode_gops(frames.ctypes.data, n, w, h, gop, search_area, err_threshold, threads,
+                                      ob.ctypes.data if want_outputs else None,
+                                      om.ctypes.data if want_outputs else None)
+    return t, ob, om
