@@ -1,0 +1,54 @@
+"""Builds libmptc_b200.so (the CUDA kernels + the C-ABI of include/mptc_gpu.h) in-tree with
+nvcc for sm_100a.  No torch extension machinery: the library has a plain C ABI."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmptc_b200.so")
+
+SOURCES = ["mptc_kernels.cu", "mptc_capi.cu", "mptc_host.cpp"]
+HEADERS = ["mptc_kernels.h", "mptc_device.cuh", "mptc_host.h", os.path.join("..", "..", "include", "mptc_gpu.h"),
+           os.path.join("..", "..", "include", "mptc_codec.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",            # belt and braces: every reference FP32 op is individually rounded
+    "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-pthread",
+    "-shared", "-lcudart",
+]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+    return exe
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,233 @@
+"""ctypes binding of libmptc_b200.so -- the C-ABI declared in include/mptc_gpu.h.
+
+There is no CPU fallback: loading fails loudly when the CUDA library has not been built,
+and every compute call fails loudly when no GPU is present."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MPTC_OK = 0
+STAGES = {"total": 0, "fit": 1, "inter": 2, "intra": 3, "compact": 4, "planes": 5}
+
+# every symbol include/mptc_gpu.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "mptc_gpu_create", "mptc_gpu_destroy", "mptc_gpu_last_error", "mptc_gpu_launch_count",
+    "mptc_gpu_dxt1_fit", "mptc_gpu_reencode", "mptc_gpu_endpoint_planes",
+    "mptc_gpu_seq_reserve", "mptc_gpu_seq_upload", "mptc_gpu_seq_encode", "mptc_gpu_seq_download",
+    "mptc_gpu_sync", "mptc_gpu_last_encode_ms", "mptc_gpu_encode_sequence",
+    "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("search_area", C.c_int), ("err_threshold", C.c_int), ("gop", C.c_int)]
+
+
+class MptcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Loads libmptc_b200.so; raises if it is missing (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        raise MptcError(f"{_build.LIB} is missing: run `python -m mptc_b200.build` (needs nvcc). "
+                        "There is no CPU fallback for the encoder hot path.")
+    L = C.CDLL(_build.LIB)
+    vp, ci = C.c_void_p, C.c_int
+    L.mptc_gpu_create.argtypes = [ci, C.POINTER(vp)]
+    L.mptc_gpu_destroy.argtypes = [vp]
+    L.mptc_gpu_last_error.restype = C.c_char_p
+    L.mptc_gpu_last_error.argtypes = [vp]
+    L.mptc_gpu_launch_count.restype = C.c_uint64
+    L.mptc_gpu_launch_count.argtypes = [vp]
+    L.mptc_gpu_dxt1_fit.argtypes = [vp, vp, ci, ci, vp]
+    L.mptc_gpu_reencode.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+    L.mptc_gpu_endpoint_planes.argtypes = [vp, vp, ci, ci, vp]
+    L.mptc_gpu_seq_reserve.argtypes = [vp, ci, ci, ci]
+    L.mptc_gpu_seq_upload.argtypes = [vp, vp, ci, ci]
+    L.mptc_gpu_seq_encode.argtypes = [vp, ci, ci, C.POINTER(Params)]
+    L.mptc_gpu_seq_download.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp]
+    L.mptc_gpu_sync.argtypes = [vp]
+    L.mptc_gpu_last_encode_ms.argtypes = [vp, ci, C.POINTER(C.c_float)]
+    L.mptc_gpu_encode_sequence.argtypes = [vp, vp, ci, ci, ci, C.POINTER(Params), vp, vp, vp, vp, vp]
+    L.mptc_gpu_host_alloc.restype = vp
+    L.mptc_gpu_host_alloc.argtypes = [C.c_size_t]
+    L.mptc_gpu_host_free.argtypes = [vp]
+    L.mptc_gpu_last_candidate_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from mptc_gpu_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._p = load().mptc_gpu_host_alloc(max(self.nbytes, 1))
+        if not self._p:
+            raise MptcError("mptc_gpu_host_alloc failed")
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            load().mptc_gpu_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One mptc_gpu_ctx: one per (host thread, GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load()
+        p = C.c_void_p()
+        r = self._L.mptc_gpu_create(device, C.byref(p))
+        if r != MPTC_OK:
+            raise MptcError(f"mptc_gpu_create(device={device}) failed with {r}: no usable CUDA device "
+                            "(the encoder hot path has no CPU fallback)")
+        self._p = p
+        self.device = device
+        self.w = self.h = self.nb = 0
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self._L.mptc_gpu_destroy(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, r):
+        if r != MPTC_OK:
+            raise MptcError(f"mptc_gpu error {r}: {self._L.mptc_gpu_last_error(self._p).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.mptc_gpu_launch_count(self._p))
+
+    # ---- single frame ------------------------------------------------------------------
+    def dxt1_fit(self, rgb: np.ndarray) -> np.ndarray:
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        h, w = rgb.shape[:2]
+        out = np.empty((h // 4) * (w // 4), dtype=np.uint64)
+        self._check(self._L.mptc_gpu_dxt1_fit(self._p, rgb.ctypes.data, w, h, out.ctypes.data))
+        return out
+
+    def reencode(self, rgb, is_intra, search_area, err_threshold, prev_blocks=None):
+        """-> dict(initial, blocks, motion, unique)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        h, w = rgb.shape[:2]
+        nb = (h // 4) * (w // 4)
+        initial = np.empty(nb, dtype=np.uint64)
+        blocks = np.empty(nb, dtype=np.uint64)
+        motion = np.empty(2 * nb, dtype=np.uint8)
+        unique = np.empty(nb, dtype=np.uint32)
+        nu = C.c_uint32(0)
+        if prev_blocks is not None:
+            prev_blocks = np.ascontiguousarray(prev_blocks, dtype=np.uint64)
+        self._check(self._L.mptc_gpu_reencode(self._p, rgb.ctypes.data, w, h, int(is_intra), search_area,
+                                              err_threshold, _ptr(prev_blocks), initial.ctypes.data,
+                                              blocks.ctypes.data, motion.ctypes.data, unique.ctypes.data,
+                                              C.addressof(nu)))
+        return {"initial": initial, "blocks": blocks, "motion": motion, "unique": unique[: nu.value].copy()}
+
+    def endpoint_planes(self, blocks, bw, bh) -> np.ndarray:
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint64)
+        pbw, pbh = (bw + 63) // 64 * 64, (bh + 63) // 64 * 64
+        out = np.empty((6, pbh, pbw), dtype=np.uint8)
+        self._check(self._L.mptc_gpu_endpoint_planes(self._p, blocks.ctypes.data, bw, bh, out.ctypes.data))
+        return out
+
+    # ---- sequences -----------------------------------------------------------------------
+    def seq_reserve(self, w, h, n_frames):
+        self._check(self._L.mptc_gpu_seq_reserve(self._p, w, h, n_frames))
+        self.w, self.h, self.nb = w, h, (w // 4) * (h // 4)
+        self.pbw, self.pbh = (w // 4 + 63) // 64 * 64, (h // 4 + 63) // 64 * 64
+
+    def seq_upload(self, frames: np.ndarray, first=0):
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+        self._check(self._L.mptc_gpu_seq_upload(self._p, frames.ctypes.data, first, frames.shape[0]))
+
+    def seq_encode(self, first, count, search_area, err_threshold, gop):
+        p = Params(search_area, err_threshold, gop)
+        self._check(self._L.mptc_gpu_seq_encode(self._p, first, count, C.byref(p)))
+
+    def seq_download(self, first, count, want=("blocks", "initial", "motion", "unique", "planes"), into=None):
+        nb = self.nb
+        out = dict(into) if into else {}
+        if "blocks" in want and "blocks" not in out:
+            out["blocks"] = np.empty((count, nb), dtype=np.uint64)
+        if "initial" in want and "initial" not in out:
+            out["initial"] = np.empty((count, nb), dtype=np.uint64)
+        if "motion" in want and "motion" not in out:
+            out["motion"] = np.empty((count, 2 * nb), dtype=np.uint8)
+        if "unique" in want and "unique" not in out:
+            out["unique"] = np.empty((count, nb), dtype=np.uint32)
+            out["n_unique"] = np.empty(count, dtype=np.uint32)
+        if "planes" in want and "planes" not in out:
+            out["planes"] = np.empty((count, 6, self.pbh, self.pbw), dtype=np.uint8)
+        self._check(self._L.mptc_gpu_seq_download(self._p, first, count, _ptr(out.get("blocks")),
+                                                  _ptr(out.get("initial")), _ptr(out.get("motion")),
+                                                  _ptr(out.get("unique")), _ptr(out.get("n_unique")),
+                                                  _ptr(out.get("planes"))))
+        return out
+
+    def sync(self):
+        self._check(self._L.mptc_gpu_sync(self._p))
+
+    def last_encode_ms(self, stage="total") -> float:
+        ms = C.c_float(0)
+        self._check(self._L.mptc_gpu_last_encode_ms(self._p, STAGES[stage], C.byref(ms)))
+        return float(ms.value)
+
+    def last_candidate_count(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.mptc_gpu_last_candidate_count(self._p, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def encode_sequence(self, frames: np.ndarray, search_area, err_threshold, gop, out=None, planes=True):
+        """End to end from host frames to host results (H2D + kernels + D2H)."""
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+        n, h, w = frames.shape[:3]
+        nb = (h // 4) * (w // 4)
+        pbw, pbh = (w // 4 + 63) // 64 * 64, (h // 4 + 63) // 64 * 64
+        if out is None:
+            out = {"blocks": np.empty((n, nb), dtype=np.uint64), "motion": np.empty((n, 2 * nb), dtype=np.uint8),
+                   "unique": np.empty((n, nb), dtype=np.uint32), "n_unique": np.empty(n, dtype=np.uint32)}
+            if planes:
+                out["planes"] = np.empty((n, 6, pbh, pbw), dtype=np.uint8)
+        p = Params(search_area, err_threshold, gop)
+        self._check(self._L.mptc_gpu_encode_sequence(self._p, frames.ctypes.data, n, w, h, C.byref(p),
+                                                     _ptr(out["blocks"]), _ptr(out["motion"]), _ptr(out["unique"]),
+                                                     _ptr(out["n_unique"]), _ptr(out.get("planes"))))
+        self.w, self.h, self.nb, self.pbw, self.pbh = w, h, nb, pbw, pbh
+        return out

@@ -1,0 +1,419 @@
+// mptc_capi.cu -- the extern "C" boundary declared in include/mptc_gpu.h.
+//
+// Owns the context (streams, events, device-resident sequence buffers) and schedules the
+// kernels of mptc_kernels.cu.  Scheduling mirrors the reference's frame loop
+// (codec/codec.cpp:1383-1509) but runs frame k of every GOP in the same launches:
+// GOPs are independent, frames inside a GOP are not.
+#include "../../include/mptc_gpu.h"
+#include "mptc_kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace mptc;
+
+namespace {
+
+struct StageEvent {
+  int stage;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct mptc_gpu_ctx {
+  int device = 0;
+  cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_uploaded = nullptr, ev_encoded = nullptr;
+  // reserved sequence
+  int w = 0, h = 0, bw = 0, bh = 0, nb = 0, pbw = 0, pbh = 0, cap_frames = 0;
+  size_t frame_bytes = 0, plane_bytes = 0;  // plane_bytes = 6*pbw*pbh
+  uint8_t *d_rgb = nullptr;
+  uint64_t *d_init = nullptr, *d_final = nullptr;
+  uint8_t *d_motion = nullptr, *d_flags = nullptr, *d_planes = nullptr;
+  uint32_t *d_unique = nullptr, *d_nunique = nullptr;
+  int *d_progress = nullptr, *d_tickets = nullptr;
+  unsigned long long *d_cand = nullptr;
+  int tickets_cap = 0;
+  int max_wave_ctas = 0;
+  bool encoded = false;
+  std::vector<StageEvent> stage_events;
+  size_t stage_events_used = 0;
+  uint64_t launches = 0;
+  char err[512] = {0};
+};
+
+namespace {
+
+int fail(mptc_gpu_ctx *c, int code, const char *fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof c->err, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(ctx, call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? MPTC_E_NOMEM : MPTC_E_CUDA,          \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// stb__PrepareOptTable (Include/stb_dxt.h:111-137): best (max,min) 5/6-bit pair whose 1/3
+// interpolant reproduces each 8-bit value, with the 3 % range penalty.
+void build_match_table(uint8_t *table, int bits) {
+  const int size = 1 << bits;
+  for (int target = 0; target < 256; ++target) {
+    int best = 256;
+    for (int lo = 0; lo < size; ++lo)
+      for (int hi = 0; hi < size; ++hi) {
+        int e_lo = bits == 5 ? ((lo << 3) | (lo >> 2)) : ((lo << 2) | (lo >> 4));
+        int e_hi = bits == 5 ? ((hi << 3) | (hi >> 2)) : ((hi << 2) | (hi >> 4));
+        int err = abs((2 * e_hi + e_lo) / 3 - target) + abs(e_hi - e_lo) * 3 / 100;
+        if (err < best) {
+          table[2 * target + 0] = (uint8_t)hi;
+          table[2 * target + 1] = (uint8_t)lo;
+          best = err;
+        }
+      }
+  }
+}
+
+void free_seq(mptc_gpu_ctx *c) {
+  cudaFree(c->d_rgb); cudaFree(c->d_init); cudaFree(c->d_final); cudaFree(c->d_motion);
+  cudaFree(c->d_flags); cudaFree(c->d_planes); cudaFree(c->d_unique); cudaFree(c->d_nunique);
+  cudaFree(c->d_progress);
+  c->d_rgb = nullptr; c->d_init = c->d_final = nullptr; c->d_motion = c->d_flags = c->d_planes = nullptr;
+  c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr;
+  c->cap_frames = 0; c->w = c->h = 0;
+  c->encoded = false;
+}
+
+SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
+  SeqView v;
+  v.rgb = c->d_rgb; v.init_blocks = c->d_init; v.final_blocks = c->d_final; v.motion = c->d_motion;
+  v.flags = c->d_flags; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.planes = c->d_planes;
+  v.progress = c->d_progress; v.frame_bytes = c->frame_bytes;
+  v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb;
+  v.first = first; v.count = count; v.gop = gop;
+  return v;
+}
+
+StageEvent &stage_begin(mptc_gpu_ctx *c, int stage) {
+  if (c->stage_events_used == c->stage_events.size()) {
+    StageEvent e;
+    e.stage = stage;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    c->stage_events.push_back(e);
+  }
+  StageEvent &e = c->stage_events[c->stage_events_used++];
+  e.stage = stage;
+  cudaEventRecord(e.a, c->s_compute);
+  return e;
+}
+
+void stage_end(mptc_gpu_ctx *c, StageEvent &e) {
+  cudaEventRecord(e.b, c->s_compute);
+  ++c->launches;
+}
+
+int check_params(mptc_gpu_ctx *c, int sa, int gop) {
+  if (sa < 1 || sa > 63) return fail(c, MPTC_E_ARG, "search_area %d outside 1..63 (uint8 motion bytes)", sa);
+  if (gop < 1) return fail(c, MPTC_E_ARG, "gop %d < 1", gop);
+  return MPTC_OK;
+}
+
+// Search + compaction + planes over frames [first, first+count) whose fit is already done.
+// If fit == true also runs K1 over the range.  k_begin lets single-frame calls start at an
+// inter frame whose predecessor's final blocks were supplied by the caller.
+int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, bool fit, int k_begin,
+               bool planes) {
+  cudaStream_t s = c->s_compute;
+  const int n_gops = (count + gop - 1) / gop;
+  if (gop > c->tickets_cap) {
+    cudaFree(c->d_tickets);
+    CU(c, cudaMalloc(&c->d_tickets, sizeof(int) * gop));
+    c->tickets_cap = gop;
+  }
+  SeqView v = view_of(c, first, count, gop);
+  c->stage_events_used = 0;
+  CU(c, cudaEventRecord(c->ev_begin, s));
+  CU(c, cudaMemsetAsync(c->d_tickets, 0, sizeof(int) * gop, s));
+  CU(c, cudaMemsetAsync(c->d_progress + (size_t)first * c->bh, 0, sizeof(int) * (size_t)count * c->bh, s));
+  CU(c, cudaMemsetAsync(c->d_flags + (size_t)first * c->nb, 0, (size_t)count * c->nb, s));
+  CU(c, cudaMemsetAsync(c->d_cand, 0, 2 * sizeof(unsigned long long), s));
+  if (fit) {
+    StageEvent &e = stage_begin(c, 1);
+    launch_dxt1_fit(v, s);
+    stage_end(c, e);
+  }
+  const int k_end = count < gop ? count : gop;
+  for (int k = k_begin; k < k_end; ++k) {
+    if (k > 0) {
+      StageEvent &e = stage_begin(c, 2);
+      launch_inter_search(v, k, n_gops, sa, thr, s);
+      stage_end(c, e);
+    }
+    StageEvent &e = stage_begin(c, 3);
+    launch_intra_wavefront(v, k, n_gops, sa, thr, c->d_tickets + k, c->max_wave_ctas, s);
+    stage_end(c, e);
+  }
+  {
+    StageEvent &e = stage_begin(c, 4);
+    launch_compact_unique(v, sa, c->d_cand, s);
+    stage_end(c, e);
+  }
+  if (planes) {
+    StageEvent &e = stage_begin(c, 5);
+    launch_endpoint_planes(v, c->pbw, c->pbh, s);
+    stage_end(c, e);
+  }
+  CU(c, cudaEventRecord(c->ev_end, s));
+  CU(c, cudaGetLastError());
+  c->encoded = true;
+  return MPTC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptc_gpu_create(int device, mptc_gpu_ctx **out) {
+  if (!out) return MPTC_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return MPTC_E_CUDA;
+  mptc_gpu_ctx *c = new mptc_gpu_ctx;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return MPTC_E_CUDA; }
+  bool ok = cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev_begin) == cudaSuccess && cudaEventCreate(&c->ev_end) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_encoded, cudaEventDisableTiming) == cudaSuccess &&
+            cudaMalloc(&c->d_cand, 2 * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) {
+    uint8_t t5[512], t6[512];
+    build_match_table(t5, 5);
+    build_match_table(t6, 6);
+    ok = upload_tables(t5, t6) == cudaSuccess;
+  }
+  if (!ok) { mptc_gpu_destroy(c); return MPTC_E_CUDA; }
+  c->max_wave_ctas = intra_wavefront_max_ctas(device);
+  *out = c;
+  return MPTC_OK;
+}
+
+void mptc_gpu_destroy(mptc_gpu_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_seq(c);
+  cudaFree(c->d_tickets);
+  cudaFree(c->d_cand);
+  for (auto &e : c->stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+  if (c->ev_end) cudaEventDestroy(c->ev_end);
+  if (c->ev_uploaded) cudaEventDestroy(c->ev_uploaded);
+  if (c->ev_encoded) cudaEventDestroy(c->ev_encoded);
+  if (c->s_compute) cudaStreamDestroy(c->s_compute);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  delete c;
+}
+
+const char *mptc_gpu_last_error(const mptc_gpu_ctx *c) { return c ? c->err : "null context"; }
+uint64_t mptc_gpu_launch_count(const mptc_gpu_ctx *c) { return c ? c->launches : 0; }
+
+int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
+  if (!c) return MPTC_E_ARG;
+  if (w < 4 || h < 4 || (w & 3) || (h & 3)) return fail(c, MPTC_E_ARG, "frame %dx%d: width/height must be multiples of 4", w, h);
+  if (n_frames < 1) return fail(c, MPTC_E_ARG, "n_frames %d < 1", n_frames);
+  CU(c, cudaSetDevice(c->device));
+  if (c->w == w && c->h == h && c->cap_frames >= n_frames) return MPTC_OK;
+  CU(c, cudaDeviceSynchronize());
+  free_seq(c);
+  c->w = w; c->h = h; c->bw = w / 4; c->bh = h / 4; c->nb = c->bw * c->bh;
+  c->pbw = (c->bw + 63) / 64 * 64; c->pbh = (c->bh + 63) / 64 * 64;
+  c->frame_bytes = (size_t)w * h * 3;
+  c->plane_bytes = (size_t)6 * c->pbw * c->pbh;
+  const size_t F = (size_t)n_frames, nb = (size_t)c->nb;
+  CU(c, cudaMalloc(&c->d_rgb, F * c->frame_bytes));
+  CU(c, cudaMalloc(&c->d_init, F * nb * 8));
+  CU(c, cudaMalloc(&c->d_final, F * nb * 8));
+  CU(c, cudaMalloc(&c->d_motion, F * nb * 2));
+  CU(c, cudaMalloc(&c->d_flags, F * nb));
+  CU(c, cudaMalloc(&c->d_unique, F * nb * 4));
+  CU(c, cudaMalloc(&c->d_nunique, F * 4));
+  CU(c, cudaMalloc(&c->d_planes, F * c->plane_bytes));
+  CU(c, cudaMalloc(&c->d_progress, F * c->bh * sizeof(int)));
+  c->cap_frames = n_frames;
+  return MPTC_OK;
+}
+
+int mptc_gpu_seq_upload(mptc_gpu_ctx *c, const uint8_t *frames, int first, int count) {
+  if (!c || !frames) return MPTC_E_ARG;
+  if (first < 0 || count < 1 || first + count > c->cap_frames) return fail(c, MPTC_E_STATE, "upload range [%d,%d) outside reserved %d frames", first, first + count, c->cap_frames);
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(c->d_rgb + c->frame_bytes * first, frames, c->frame_bytes * count, cudaMemcpyHostToDevice, c->s_compute));
+  return MPTC_OK;
+}
+
+int mptc_gpu_seq_encode(mptc_gpu_ctx *c, int first, int count, const mptc_gpu_params *p) {
+  if (!c || !p) return MPTC_E_ARG;
+  if (int r = check_params(c, p->search_area, p->gop)) return r;
+  if (first < 0 || count < 1 || first + count > c->cap_frames) return fail(c, MPTC_E_STATE, "encode range [%d,%d) outside reserved %d frames", first, first + count, c->cap_frames);
+  CU(c, cudaSetDevice(c->device));
+  return run_encode(c, first, count, p->gop, p->search_area, p->err_threshold, true, 0, true);
+}
+
+int mptc_gpu_seq_download(mptc_gpu_ctx *c, int first, int count, uint64_t *blocks, uint64_t *initial,
+                          uint8_t *motion, uint32_t *unique, uint32_t *n_unique, uint8_t *planes) {
+  if (!c) return MPTC_E_ARG;
+  if (first < 0 || count < 1 || first + count > c->cap_frames) return fail(c, MPTC_E_STATE, "download range [%d,%d) outside reserved %d frames", first, first + count, c->cap_frames);
+  CU(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->s_compute;
+  const size_t nb = (size_t)c->nb, f0 = (size_t)first, n = (size_t)count;
+  if (blocks) CU(c, cudaMemcpyAsync(blocks, c->d_final + f0 * nb, n * nb * 8, cudaMemcpyDeviceToHost, s));
+  if (initial) CU(c, cudaMemcpyAsync(initial, c->d_init + f0 * nb, n * nb * 8, cudaMemcpyDeviceToHost, s));
+  if (motion) CU(c, cudaMemcpyAsync(motion, c->d_motion + f0 * nb * 2, n * nb * 2, cudaMemcpyDeviceToHost, s));
+  if (unique) CU(c, cudaMemcpyAsync(unique, c->d_unique + f0 * nb, n * nb * 4, cudaMemcpyDeviceToHost, s));
+  if (n_unique) CU(c, cudaMemcpyAsync(n_unique, c->d_nunique + f0, n * 4, cudaMemcpyDeviceToHost, s));
+  if (planes) CU(c, cudaMemcpyAsync(planes, c->d_planes + f0 * c->plane_bytes, n * c->plane_bytes, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  return MPTC_OK;
+}
+
+int mptc_gpu_sync(mptc_gpu_ctx *c) {
+  if (!c) return MPTC_E_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->s_compute));
+  CU(c, cudaStreamSynchronize(c->s_h2d));
+  CU(c, cudaStreamSynchronize(c->s_d2h));
+  return MPTC_OK;
+}
+
+int mptc_gpu_last_encode_ms(mptc_gpu_ctx *c, int stage, float *ms) {
+  if (!c || !ms) return MPTC_E_ARG;
+  if (!c->encoded) return fail(c, MPTC_E_STATE, "no encode has run");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventSynchronize(c->ev_end));
+  if (stage == 0) {
+    CU(c, cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return MPTC_OK;
+  }
+  float total = 0.f;
+  for (size_t i = 0; i < c->stage_events_used; ++i) {
+    if (c->stage_events[i].stage != stage) continue;
+    float t = 0.f;
+    CU(c, cudaEventElapsedTime(&t, c->stage_events[i].a, c->stage_events[i].b));
+    total += t;
+  }
+  *ms = total;
+  return MPTC_OK;
+}
+
+int mptc_gpu_last_candidate_count(mptc_gpu_ctx *c, uint64_t *inter, uint64_t *intra) {
+  if (!c) return MPTC_E_ARG;
+  if (!c->encoded) return fail(c, MPTC_E_STATE, "no encode has run");
+  CU(c, cudaSetDevice(c->device));
+  unsigned long long h[2];
+  CU(c, cudaStreamSynchronize(c->s_compute));
+  CU(c, cudaMemcpy(h, c->d_cand, sizeof h, cudaMemcpyDeviceToHost));
+  if (inter) *inter = h[0];
+  if (intra) *intra = h[1];
+  return MPTC_OK;
+}
+
+int mptc_gpu_dxt1_fit(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, uint64_t *blocks_out) {
+  if (!c || !rgb || !blocks_out) return MPTC_E_ARG;
+  if (int r = mptc_gpu_seq_reserve(c, w, h, 2)) return r;
+  if (int r = mptc_gpu_seq_upload(c, rgb, 0, 1)) return r;
+  SeqView v = view_of(c, 0, 1, 1);
+  launch_dxt1_fit(v, c->s_compute);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(blocks_out, c->d_init, (size_t)c->nb * 8, cudaMemcpyDeviceToHost, c->s_compute));
+  CU(c, cudaStreamSynchronize(c->s_compute));
+  return MPTC_OK;
+}
+
+int mptc_gpu_reencode(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, int is_intra, int search_area,
+                      int err_threshold, const uint64_t *prev_blocks, uint64_t *initial_out,
+                      uint64_t *blocks_out, uint8_t *motion_out, uint32_t *unique_out, uint32_t *n_unique) {
+  if (!c || !rgb) return MPTC_E_ARG;
+  if (int r = check_params(c, search_area, 1)) return r;
+  if (!is_intra && !prev_blocks) return fail(c, MPTC_E_ARG, "inter frame needs prev_blocks (reference->_physical_blocks)");
+  if (int r = mptc_gpu_seq_reserve(c, w, h, 2)) return r;
+  // slot 0 = the reference frame (only its final blocks matter), slot 1 = this frame
+  const int slot = is_intra ? 0 : 1;
+  if (int r = mptc_gpu_seq_upload(c, rgb, slot, 1)) return r;
+  if (!is_intra)
+    CU(c, cudaMemcpyAsync(c->d_final, prev_blocks, (size_t)c->nb * 8, cudaMemcpyHostToDevice, c->s_compute));
+  {
+    SeqView v = view_of(c, slot, 1, 1);
+    launch_dxt1_fit(v, c->s_compute);
+    ++c->launches;
+  }
+  int r = is_intra ? run_encode(c, 0, 1, 1, search_area, err_threshold, false, 0, false)
+                   : run_encode(c, 0, 2, 2, search_area, err_threshold, false, 1, false);
+  if (r) return r;
+  const size_t nb = (size_t)c->nb, off = (size_t)slot * nb;
+  cudaStream_t s = c->s_compute;
+  if (initial_out) CU(c, cudaMemcpyAsync(initial_out, c->d_init + off, nb * 8, cudaMemcpyDeviceToHost, s));
+  if (blocks_out) CU(c, cudaMemcpyAsync(blocks_out, c->d_final + off, nb * 8, cudaMemcpyDeviceToHost, s));
+  if (motion_out) CU(c, cudaMemcpyAsync(motion_out, c->d_motion + off * 2, nb * 2, cudaMemcpyDeviceToHost, s));
+  uint32_t nu = 0;
+  CU(c, cudaMemcpyAsync(&nu, c->d_nunique + slot, 4, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  if (unique_out && nu) CU(c, cudaMemcpy(unique_out, c->d_unique + off, (size_t)nu * 4, cudaMemcpyDeviceToHost));
+  if (n_unique) *n_unique = nu;
+  return MPTC_OK;
+}
+
+int mptc_gpu_endpoint_planes(mptc_gpu_ctx *c, const uint64_t *blocks, int bw, int bh, uint8_t *planes_out) {
+  if (!c || !blocks || !planes_out) return MPTC_E_ARG;
+  if (bw < 1 || bh < 1) return fail(c, MPTC_E_ARG, "bad plane size %dx%d", bw, bh);
+  if (int r = mptc_gpu_seq_reserve(c, bw * 4, bh * 4, 2)) return r;
+  cudaStream_t s = c->s_compute;
+  CU(c, cudaMemcpyAsync(c->d_final, blocks, (size_t)c->nb * 8, cudaMemcpyHostToDevice, s));
+  SeqView v = view_of(c, 0, 1, 1);
+  launch_endpoint_planes(v, c->pbw, c->pbh, s);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(planes_out, c->d_planes, c->plane_bytes, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  return MPTC_OK;
+}
+
+int mptc_gpu_encode_sequence(mptc_gpu_ctx *c, const uint8_t *frames, int n_frames, int w, int h,
+                             const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion, uint32_t *unique,
+                             uint32_t *n_unique, uint8_t *planes) {
+  if (!c || !frames || !p) return MPTC_E_ARG;
+  if (int r = check_params(c, p->search_area, p->gop)) return r;
+  if (int r = mptc_gpu_seq_reserve(c, w, h, n_frames)) return r;
+  if (int r = mptc_gpu_seq_upload(c, frames, 0, n_frames)) return r;
+  if (int r = run_encode(c, 0, n_frames, p->gop, p->search_area, p->err_threshold, true, 0, planes != nullptr)) return r;
+  return mptc_gpu_seq_download(c, 0, n_frames, blocks, nullptr, motion, unique, n_unique, planes);
+}
+
+void *mptc_gpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void mptc_gpu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

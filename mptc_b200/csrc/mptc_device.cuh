@@ -1,0 +1,218 @@
+// mptc_device.cuh -- device-side building blocks shared by the sm_100a kernels.
+//
+// Bit-exactness rules: every FP32 operation of the reference is
+// individually rounded (x86-64 SSE, no FMA contraction), so all float math here goes through
+// __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn, which nvcc never contracts into FFMA.  Float->int
+// casts follow cvttss2si (NaN / out of range -> INT_MIN).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mptc {
+
+constexpr int kRejected = 0x7fffffff;  // candidate not accepted (dxt_image.cpp:753-755)
+
+// ---- RGB565 helpers (codec/dxt_image.cpp:43-69) -------------------------------------
+__device__ __forceinline__ uint32_t expand565_rgbx(uint32_t v) {
+  uint32_t r = v >> 11, g = (v >> 5) & 63u, b = v & 31u;
+  r = (r << 3) | (r >> 2);
+  g = (g << 2) | (g >> 4);
+  b = (b << 3) | (b >> 2);
+  return r | (g << 8) | (b << 16);
+}
+
+__device__ __forceinline__ uint32_t pack565_rgbx(uint32_t c) {
+  return ((c & 0xF8u) << 8) | (((c >> 8) & 0xFCu) << 3) | (((c >> 16) & 0xFFu) >> 3);
+}
+
+// per-byte (2a+b)/3 and (a+2b)/3 on packed RGBX (LerpChannels, dxt_image.cpp:34-41)
+__device__ __forceinline__ uint32_t lerp_bytes(uint32_t a, uint32_t b, int wa, int wb, int div) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int s = 0; s < 24; s += 8) {
+    int x = (int)((a >> s) & 0xFF), y = (int)((b >> s) & 0xFF);
+    out |= (uint32_t)((wa * x + wb * y) / div) << s;
+  }
+  return out;
+}
+
+// Palette of a physical block (PhysicalToLogical, dxt_image.cpp:198-214), packed RGBX.
+__device__ __forceinline__ void palette_of_block(uint64_t blk, uint32_t pal[4]) {
+  uint32_t e1 = (uint32_t)(blk & 0xFFFF), e2 = (uint32_t)((blk >> 16) & 0xFFFF);
+  pal[0] = expand565_rgbx(e1);
+  pal[1] = expand565_rgbx(e2);
+  if (e1 <= e2) {
+    pal[2] = lerp_bytes(pal[0], pal[1], 1, 1, 2);
+    pal[3] = 0;
+  } else {
+    pal[2] = lerp_bytes(pal[0], pal[1], 2, 1, 3);
+    pal[3] = lerp_bytes(pal[0], pal[1], 1, 2, 3);
+  }
+}
+
+// CompressedBlock::Error (dxt_image.cpp:258-276): sum of squared byte differences / 48.
+// px[k] are RGBX-packed pixels (X = 0), pal[v] RGBX-packed palette entries (X = 0).
+__device__ __forceinline__ int block_error(const uint32_t *px, const uint32_t pal[4], uint32_t word) {
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    uint32_t v = (word >> (2 * k)) & 3u;
+    uint32_t c = (v & 2u) ? ((v & 1u) ? pal[3] : pal[2]) : ((v & 1u) ? pal[1] : pal[0]);
+    uint32_t d = __vabsdiffu4(px[k], c);
+    sum = __dp4a(d, d, sum);
+  }
+  return (int)(sum / 48u);
+}
+
+// ToFiveBits / ToSixBits exactly as written (dxt_image.cpp:72-121): neighbours at +-4 / +-2.
+template <int KEEP, int STEP, int SHIFT>
+__device__ __forceinline__ int snap_bits(int x) {
+  int base = x & KEEP;
+  int high = (base + STEP) & 0xFF;  // base is never 255
+  int low = base == 0 ? 0 : base - STEP;
+  base |= base >> SHIFT;
+  high |= high >> SHIFT;
+  low |= low >> SHIFT;
+  int db = abs(x - base), dh = abs(x - high), dl = abs(x - low);
+  return db <= dh ? (db < dl ? base : low) : high;
+}
+
+// (int32)(p + 0.5f) then clamp to 0..255 with cvttss2si semantics (dxt_image.cpp:330-331):
+// NaN, +-inf and anything outside int32 become INT_MIN, which clamps to 0.
+__device__ __forceinline__ int quantise_endpoint(float p) {
+  float x = __fadd_rn(p, 0.5f);
+  int v = __float2int_rz(x);
+  v = min(max(v, 0), 255);
+  return (x < 2147483648.0f) ? v : 0;  // false for NaN as well
+}
+
+// CompressedBlock::RecalculateEndpoints (dxt_image.cpp:290-351) for index word `word` over
+// the 16 pixels pf[k*3+ch] (already converted to float).  Returns the snapped 8-bit
+// endpoints packed RGBX.  Summation order and rounding follow the reference exactly.
+__device__ __forceinline__ void refit_endpoints(const float *pf, uint32_t word, uint32_t &ep1, uint32_t &ep2) {
+  const float w23 = 2.0f / 3.0f, w13 = 1.0f / 3.0f;  // (3-order)/3, order/3 in FP32
+  float asq = 0.f, bsq = 0.f, ab = 0.f;
+  float ax0 = 0.f, ax1 = 0.f, ax2 = 0.f, bx0 = 0.f, bx1 = 0.f, bx2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    uint32_t v = (word >> (2 * k)) & 3u;
+    // idx_to_order = {0,3,1,2}: a = {1, 0, 2/3, 1/3}[v], b = {0, 1, 1/3, 2/3}[v]
+    float a = (v & 2u) ? ((v & 1u) ? w13 : w23) : ((v & 1u) ? 0.0f : 1.0f);
+    float b = (v & 2u) ? ((v & 1u) ? w23 : w13) : ((v & 1u) ? 1.0f : 0.0f);
+    asq = __fadd_rn(asq, __fmul_rn(a, a));
+    bsq = __fadd_rn(bsq, __fmul_rn(b, b));
+    ab = __fadd_rn(ab, __fmul_rn(a, b));
+    float p0 = pf[3 * k + 0], p1 = pf[3 * k + 1], p2 = pf[3 * k + 2];
+    ax0 = __fadd_rn(ax0, __fmul_rn(p0, a));
+    bx0 = __fadd_rn(bx0, __fmul_rn(p0, b));
+    ax1 = __fadd_rn(ax1, __fmul_rn(p1, a));
+    bx1 = __fadd_rn(bx1, __fmul_rn(p1, b));
+    ax2 = __fadd_rn(ax2, __fmul_rn(p2, a));
+    bx2 = __fadd_rn(bx2, __fmul_rn(p2, b));
+  }
+  float f = __fdiv_rn(1.0f, __fsub_rn(__fmul_rn(asq, bsq), __fmul_rn(ab, ab)));
+  int r1 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(ax0, bsq), __fmul_rn(bx0, ab))));
+  int r2 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(bx0, asq), __fmul_rn(ax0, ab))));
+  int g1 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(ax1, bsq), __fmul_rn(bx1, ab))));
+  int g2 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(bx1, asq), __fmul_rn(ax1, ab))));
+  int b1 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(ax2, bsq), __fmul_rn(bx2, ab))));
+  int b2 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(bx2, asq), __fmul_rn(ax2, ab))));
+  r1 = snap_bits<0xF8, 4, 5>(r1);  r2 = snap_bits<0xF8, 4, 5>(r2);
+  g1 = snap_bits<0xFC, 2, 6>(g1);  g2 = snap_bits<0xFC, 2, 6>(g2);
+  b1 = snap_bits<0xF8, 4, 5>(b1);  b2 = snap_bits<0xF8, 4, 5>(b2);
+  ep1 = (uint32_t)r1 | ((uint32_t)g1 << 8) | ((uint32_t)b1 << 16);
+  ep2 = (uint32_t)r2 | ((uint32_t)g2 << 8) | ((uint32_t)b2 << 16);
+}
+
+// Per-target-block context, built once per target and shared by every candidate evaluation.
+struct TargetCtx {
+  float pf[48];        // pixels as float, [k*3 + ch]      (Get4X4ColorsBlock, dxt_image.cpp:636-650)
+  uint32_t px[16];     // pixels RGBX-packed
+  uint64_t own_block;  // the block's initial stb fit
+  uint32_t own_word;
+  int orig_err;        // blk.Error() with the initial logical block (dxt_image.cpp:668, :728)
+};
+
+// One candidate evaluation (dxt_image.cpp:739-758 / :679-698).  Returns err_diff, or
+// kRejected when the refit would need an endpoint swap.
+__device__ __forceinline__ int eval_candidate(const TargetCtx &t, uint32_t word) {
+  if (word == t.own_word) return 0;  // blk == blk2: palette untouched
+  uint32_t ep1, ep2;
+  refit_endpoints(t.pf, word, ep1, ep2);
+  if (!(pack565_rgbx(ep1) > pack565_rgbx(ep2))) return kRejected;
+  uint32_t pal[4] = {ep1, ep2, lerp_bytes(ep1, ep2, 2, 1, 3), lerp_bytes(ep1, ep2, 1, 2, 3)};
+  return block_error(t.px, pal, word) - t.orig_err;
+}
+
+// The block emitted when candidate `word` wins (dxt_image.cpp:900-905 / :922-926).
+__device__ __forceinline__ uint64_t winning_block(const TargetCtx &t, uint32_t word) {
+  if (word == t.own_word) return t.own_block;
+  uint32_t ep1, ep2;
+  refit_endpoints(t.pf, word, ep1, ep2);
+  return (uint64_t)pack565_rgbx(ep1) | ((uint64_t)pack565_rgbx(ep2) << 16) | ((uint64_t)word << 32);
+}
+
+// ---- order-independent form of the reference's stateful winner scan ----
+// Scan position p = row * W + col in the reference's loop order.  Three associative
+// reductions replace the sequential loop with its inner-loop-only `break`:
+//   first  = min p over candidates with err_diff <= 0
+//   lastneg= max (row, -col) over candidates with err_diff < 0
+//   best   = min (err_diff, p) over all accepted candidates
+struct WinnerState {
+  uint32_t first;    // 0xffffffff = none
+  int lastneg;       // -1 = none; (row << 7) | (127 - col)
+  uint32_t best;     // 0xffffffff = none; (err_diff + 65536) << 14 | p
+};
+
+__device__ __forceinline__ void winner_init(WinnerState &s) {
+  s.first = 0xffffffffu; s.lastneg = -1; s.best = 0xffffffffu;
+}
+
+__device__ __forceinline__ void winner_update(WinnerState &s, int e, int row, int col, int W) {
+  if (e == kRejected) return;
+  uint32_t p = (uint32_t)(row * W + col);
+  if (e <= 0) s.first = min(s.first, p);
+  if (e < 0) s.lastneg = max(s.lastneg, (row << 7) | (127 - col));
+  s.best = min(s.best, ((uint32_t)(e + 65536) << 14) | p);
+}
+
+__device__ __forceinline__ void winner_merge(WinnerState &s, const WinnerState &o) {
+  s.first = min(s.first, o.first);
+  s.lastneg = max(s.lastneg, o.lastneg);
+  s.best = min(s.best, o.best);
+}
+
+__device__ __forceinline__ void winner_warp_reduce(WinnerState &s) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    WinnerState o;
+    o.first = __shfl_xor_sync(0xffffffffu, s.first, d);
+    o.lastneg = __shfl_xor_sync(0xffffffffu, s.lastneg, d);
+    o.best = __shfl_xor_sync(0xffffffffu, s.best, d);
+    winner_merge(s, o);
+  }
+}
+
+// Returns the search's return value (min_err) and the winning (row, col); INT_MAX if nothing
+// was accepted.
+__device__ __forceinline__ int winner_resolve(const WinnerState &s, int W, int &row, int &col) {
+  if (s.first != 0xffffffffu) {
+    row = (int)(s.first / (uint32_t)W);
+    col = (int)(s.first % (uint32_t)W);
+    if (s.lastneg >= 0 && (s.lastneg >> 7) > row) {
+      row = s.lastneg >> 7;
+      col = 127 - (s.lastneg & 127);
+    }
+    return 0;
+  }
+  if (s.best != 0xffffffffu) {
+    uint32_t p = s.best & 0x3FFFu;
+    row = (int)(p / (uint32_t)W);
+    col = (int)(p % (uint32_t)W);
+    return (int)(s.best >> 14) - 65536;
+  }
+  row = col = 0;
+  return 0x7fffffff;
+}
+
+}  // namespace mptc

@@ -1,0 +1,575 @@
+// mptc_kernels.cu -- sm_100a kernels of the MPTC encoder hot path.
+//
+//   K1 k_dxt1_fit          stb_compress_dxt_block(HIGHQUAL) per 4x4 block   (Include/stb_dxt.h:467-538)
+//   K2 k_inter_search      DXTImage::InterBlockSearch + winner apply        (codec/dxt_image.cpp:715-774, :885-908)
+//   K3 k_intra_wavefront   DXTImage::IntraSearch + winner apply, raster     (codec/dxt_image.cpp:652-713, :912-955)
+//                          dependency resolved by a row-staggered wavefront
+//   K4 k_compact_unique    _unique_palette push_backs as a prefix sum       (codec/dxt_image.cpp:953-954)
+//   K5 k_endpoint_planes   RGB565 -> YCoCg667 -> 64x64 5/3 wavelet -> u8    (codec/codec.cpp:804-839, wavelet.cpp:30-131)
+//
+// No tensor cores: nothing here is a dense contraction (integer / ordered-FP32 work).
+#include "mptc_kernels.h"
+#include "mptc_device.cuh"
+
+#include <cuda/atomic>
+
+namespace mptc {
+
+// ------------------------------------------------------------------------------------------
+// stb single-colour tables (stb__OMatch5/6, stb_dxt.h:111-137), filled by the host at
+// context creation with the same search stb__PrepareOptTable runs.
+// ------------------------------------------------------------------------------------------
+__constant__ uint8_t c_omatch5[256][2];
+__constant__ uint8_t c_omatch6[256][2];
+
+cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6) {
+  cudaError_t e = cudaMemcpyToSymbol(c_omatch5, omatch5, 512);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_omatch6, omatch6, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: DXT1 endpoint fit
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mul8bit(int a, int b) {  // stb_dxt.h:64-68
+  int t = a * b + 128;
+  return (t + (t >> 8)) >> 8;
+}
+__device__ __forceinline__ uint32_t quant565(int r, int g, int b) {  // stb__As16Bit :82-85
+  return (uint32_t)((mul8bit(r, 31) << 11) + (mul8bit(g, 63) << 5) + mul8bit(b, 31));
+}
+__device__ __forceinline__ int exp5(uint32_t v) { return (int)((v << 3) | (v >> 2)); }
+__device__ __forceinline__ int exp6(uint32_t v) { return (int)((v << 2) | (v >> 4)); }
+
+// stb__EvalColors + stb__MatchColorsBlock, non-dither branch (:139-145, :176-215)
+__device__ __forceinline__ uint32_t match_indices(const uint32_t *px, uint32_t c0, uint32_t c1) {
+  int col[4][3];
+  col[0][0] = exp5(c0 >> 11); col[0][1] = exp6((c0 >> 5) & 63u); col[0][2] = exp5(c0 & 31u);
+  col[1][0] = exp5(c1 >> 11); col[1][1] = exp6((c1 >> 5) & 63u); col[1][2] = exp5(c1 & 31u);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    col[2][k] = (2 * col[0][k] + col[1][k]) / 3;
+    col[3][k] = (2 * col[1][k] + col[0][k]) / 3;
+  }
+  int dr = col[0][0] - col[1][0], dg = col[0][1] - col[1][1], db = col[0][2] - col[1][2];
+  int stops[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) stops[i] = col[i][0] * dr + col[i][1] * dg + col[i][2] * db;
+  int c0pt = (stops[1] + stops[3]) >> 1;
+  int half = (stops[3] + stops[2]) >> 1;
+  int c3pt = (stops[2] + stops[0]) >> 1;
+  uint32_t mask = 0;
+#pragma unroll
+  for (int i = 15; i >= 0; --i) {
+    int dot = (int)(px[i] & 0xFF) * dr + (int)((px[i] >> 8) & 0xFF) * dg + (int)((px[i] >> 16) & 0xFF) * db;
+    mask <<= 2;
+    if (dot < half) mask |= (dot < c0pt) ? 1u : 3u;
+    else            mask |= (dot < c3pt) ? 2u : 0u;
+  }
+  return mask;
+}
+
+// stb__OptimizeColorsBlock (:273-375)
+__device__ __forceinline__ void pca_endpoints(const uint32_t *px, uint32_t &mx16, uint32_t &mn16) {
+  int mu[3], lo[3], hi[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    int s = 0, mn = 255, mx = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int v = (int)((px[i] >> (8 * ch)) & 0xFF);
+      s += v; mn = min(mn, v); mx = max(mx, v);
+    }
+    mu[ch] = (s + 8) >> 4; lo[ch] = mn; hi[ch] = mx;
+  }
+  int cov[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int r = (int)(px[i] & 0xFF) - mu[0], g = (int)((px[i] >> 8) & 0xFF) - mu[1], b = (int)((px[i] >> 16) & 0xFF) - mu[2];
+    cov[0] += r * r; cov[1] += r * g; cov[2] += r * b;
+    cov[3] += g * g; cov[4] += g * b; cov[5] += b * b;
+  }
+  float cf[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cf[i] = __fdiv_rn(__int2float_rn(cov[i]), 255.0f);
+  float vr = __int2float_rn(hi[0] - lo[0]), vg = __int2float_rn(hi[1] - lo[1]), vb = __int2float_rn(hi[2] - lo[2]);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {  // nIterPower = 4, each op rounded (:331-340)
+    float r = __fadd_rn(__fadd_rn(__fmul_rn(vr, cf[0]), __fmul_rn(vg, cf[1])), __fmul_rn(vb, cf[2]));
+    float g = __fadd_rn(__fadd_rn(__fmul_rn(vr, cf[1]), __fmul_rn(vg, cf[3])), __fmul_rn(vb, cf[4]));
+    float b = __fadd_rn(__fadd_rn(__fmul_rn(vr, cf[2]), __fmul_rn(vg, cf[4])), __fmul_rn(vb, cf[5]));
+    vr = r; vg = g; vb = b;
+  }
+  double magn = fabs((double)vr);  // the one FP64 spot (:342-354)
+  magn = fmax(magn, fabs((double)vg));
+  magn = fmax(magn, fabs((double)vb));
+  int ar, ag, ab;
+  if (magn < 4.0) { ar = 299; ag = 587; ab = 114; }
+  else {
+    magn = __ddiv_rn(512.0, magn);
+    ar = __double2int_rz(__dmul_rn((double)vr, magn));
+    ag = __double2int_rz(__dmul_rn((double)vg, magn));
+    ab = __double2int_rz(__dmul_rn((double)vb, magn));
+  }
+  int dmin = 0x7fffffff, dmax = -0x7fffffff;
+  uint32_t pmin = 0, pmax = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int dot = (int)(px[i] & 0xFF) * ar + (int)((px[i] >> 8) & 0xFF) * ag + (int)((px[i] >> 16) & 0xFF) * ab;
+    if (dot < dmin) { dmin = dot; pmin = px[i]; }
+    if (dot > dmax) { dmax = dot; pmax = px[i]; }
+  }
+  mx16 = quant565((int)(pmax & 0xFF), (int)((pmax >> 8) & 0xFF), (int)((pmax >> 16) & 0xFF));
+  mn16 = quant565((int)(pmin & 0xFF), (int)((pmin >> 8) & 0xFF), (int)((pmin >> 16) & 0xFF));
+}
+
+__device__ __forceinline__ int sclamp(float y, int hi) {  // stb__sclamp :377-383 (values stay tiny)
+  int x = __float2int_rz(y);
+  return min(max(x, 0), hi);
+}
+
+__device__ __forceinline__ uint32_t omatch_pair(int r, int g, int b, int which) {
+  return ((uint32_t)c_omatch5[r][which] << 11) | ((uint32_t)c_omatch6[g][which] << 5) | (uint32_t)c_omatch5[b][which];
+}
+
+// stb__RefineBlock (:388-464)
+__device__ __forceinline__ bool refine_endpoints(const uint32_t *px, uint32_t &mx16, uint32_t &mn16, uint32_t mask) {
+  uint32_t old_mx = mx16, old_mn = mn16;
+  if ((mask ^ (mask << 2)) < 4u) {
+    int r = 8, g = 8, b = 8;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { r += (int)(px[i] & 0xFF); g += (int)((px[i] >> 8) & 0xFF); b += (int)((px[i] >> 16) & 0xFF); }
+    r >>= 4; g >>= 4; b >>= 4;
+    mx16 = omatch_pair(r, g, b, 0);
+    mn16 = omatch_pair(r, g, b, 1);
+  } else {
+    int a1r = 0, a1g = 0, a1b = 0, a2r = 0, a2g = 0, a2b = 0, akku = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t step = (mask >> (2 * i)) & 3u;
+      int w1 = (step == 0) ? 3 : (step == 1 ? 0 : (step == 2 ? 2 : 1));
+      akku += (step == 0) ? 0x090000 : (step == 1 ? 0x000900 : (step == 2 ? 0x040102 : 0x010402));
+      int r = (int)(px[i] & 0xFF), g = (int)((px[i] >> 8) & 0xFF), b = (int)((px[i] >> 16) & 0xFF);
+      a1r += w1 * r; a1g += w1 * g; a1b += w1 * b;
+      a2r += r; a2g += g; a2b += b;
+    }
+    a2r = 3 * a2r - a1r; a2g = 3 * a2g - a1g; a2b = 3 * a2b - a1b;
+    int xx = akku >> 16, yy = (akku >> 8) & 0xff, xy = akku & 0xff;
+    // 3.0f*31.0f/255.0f folds to one FP32 constant in the reference build as well
+    float frb = __fdiv_rn(3.0f * 31.0f / 255.0f, __int2float_rn(xx * yy - xy * xy));
+    float fg = __fdiv_rn(__fmul_rn(frb, 63.0f), 31.0f);
+    mx16  = (uint32_t)sclamp(__fadd_rn(__fmul_rn(__int2float_rn(a1r * yy - a2r * xy), frb), 0.5f), 31) << 11;
+    mx16 |= (uint32_t)sclamp(__fadd_rn(__fmul_rn(__int2float_rn(a1g * yy - a2g * xy), fg), 0.5f), 63) << 5;
+    mx16 |= (uint32_t)sclamp(__fadd_rn(__fmul_rn(__int2float_rn(a1b * yy - a2b * xy), frb), 0.5f), 31);
+    mn16  = (uint32_t)sclamp(__fadd_rn(__fmul_rn(__int2float_rn(a2r * xx - a1r * xy), frb), 0.5f), 31) << 11;
+    mn16 |= (uint32_t)sclamp(__fadd_rn(__fmul_rn(__int2float_rn(a2g * xx - a1g * xy), fg), 0.5f), 63) << 5;
+    mn16 |= (uint32_t)sclamp(__fadd_rn(__fmul_rn(__int2float_rn(a2b * xx - a1b * xy), frb), 0.5f), 31);
+  }
+  return old_mn != mn16 || old_mx != mx16;
+}
+
+// stb__CompressColorBlock (:467-538)
+__device__ __forceinline__ uint64_t fit_block(const uint32_t *px) {
+  uint32_t mx, mn, mask;
+  bool constant = true;
+#pragma unroll
+  for (int i = 1; i < 16; ++i) constant = constant && (px[i] == px[0]);
+  if (constant) {
+    int r = (int)(px[0] & 0xFF), g = (int)((px[0] >> 8) & 0xFF), b = (int)((px[0] >> 16) & 0xFF);
+    mask = 0xAAAAAAAAu;
+    mx = omatch_pair(r, g, b, 0);
+    mn = omatch_pair(r, g, b, 1);
+  } else {
+    pca_endpoints(px, mx, mn);
+    mask = (mx != mn) ? match_indices(px, mx, mn) : 0u;
+    for (int pass = 0; pass < 2; ++pass) {  // HIGHQUAL: refinecount = 2
+      uint32_t last = mask;
+      if (refine_endpoints(px, mx, mn, mask)) {
+        if (mx != mn) mask = match_indices(px, mx, mn);
+        else { mask = 0; break; }
+      }
+      if (mask == last) break;
+    }
+  }
+  if (mx < mn) { uint32_t t = mn; mn = mx; mx = t; mask ^= 0x55555555u; }
+  return (uint64_t)mx | ((uint64_t)mn << 16) | ((uint64_t)mask << 32);
+}
+
+// Loads the 4x4 block (bx, by) of an RGB8 frame as 16 RGBX words.  Each thread reads 4 rows
+// x 12 bytes as three aligned 32-bit words; consecutive threads read consecutive 12-byte
+// runs, so a warp covers 384 contiguous bytes per row.
+__device__ __forceinline__ void load_block_rgbx(const uint8_t *frame, int w, int bx, int by, uint32_t *px) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + ((size_t)(by * 4 + j) * w + bx * 4) * 3);
+    uint32_t a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
+    px[4 * j + 0] = a & 0x00FFFFFFu;
+    px[4 * j + 1] = (a >> 24) | ((b & 0xFFFFu) << 8);
+    px[4 * j + 2] = (b >> 16) | ((c & 0xFFu) << 16);
+    px[4 * j + 3] = c >> 8;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_dxt1_fit(const uint8_t *__restrict__ rgb, size_t frame_bytes, int w, int bw,
+                                                   int nb, uint64_t *__restrict__ init_blocks,
+                                                   uint64_t *__restrict__ final_blocks) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int f = blockIdx.y;
+  if (b >= nb) return;
+  uint32_t px[16];
+  load_block_rgbx(rgb + frame_bytes * f, w, b % bw, b / bw, px);
+  uint64_t blk = fit_block(px);
+  init_blocks[(size_t)f * nb + b] = blk;
+  final_blocks[(size_t)f * nb + b] = blk;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared by K2/K3: build the per-target context in shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_target(TargetCtx &t, const uint8_t *frame, int w, int bx, int by,
+                                             uint64_t own_block) {
+  // called by one thread
+  uint32_t px[16];
+  load_block_rgbx(frame, w, bx, by, px);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    t.px[k] = px[k];
+    t.pf[3 * k + 0] = __uint2float_rn(px[k] & 0xFF);
+    t.pf[3 * k + 1] = __uint2float_rn((px[k] >> 8) & 0xFF);
+    t.pf[3 * k + 2] = __uint2float_rn((px[k] >> 16) & 0xFF);
+  }
+  t.own_block = own_block;
+  t.own_word = (uint32_t)(own_block >> 32);
+  uint32_t pal[4];
+  palette_of_block(own_block, pal);
+  t.orig_err = block_error(px, pal, t.own_word);
+}
+
+template <int NWARPS>
+__device__ __forceinline__ void winner_block_reduce(WinnerState &s, WinnerState *smem) {
+  winner_warp_reduce(s);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    WinnerState o;
+    winner_init(o);
+    if (lane < NWARPS) o = smem[lane];
+    winner_warp_reduce(o);
+    if (lane == 0) smem[0] = o;
+  }
+  __syncthreads();
+  s = smem[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: inter search.  One CTA per target block; threads stride over the (2sa)^2 window of the
+// previous frame's FINAL index words.
+// ------------------------------------------------------------------------------------------
+constexpr int kSearchThreads = 256;
+
+__global__ void __launch_bounds__(kSearchThreads)
+k_inter_search(SeqView v, int k_in_gop, int sa, int thr) {
+  __shared__ TargetCtx t;
+  __shared__ WinnerState red[kSearchThreads / 32];
+  const int b = blockIdx.x;
+  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
+  if (f >= v.first + v.count) return;
+  const int bx = b % v.bw, by = b / v.bw;
+  const uint64_t *prev = v.final_blocks + (size_t)(f - 1) * v.nb;
+  if (threadIdx.x == 0) build_target(t, v.rgb + v.frame_bytes * f, v.w, bx, by, v.init_blocks[(size_t)f * v.nb + b]);
+  __syncthreads();
+
+  const int W = 2 * sa;
+  WinnerState s;
+  winner_init(s);
+  for (int p = threadIdx.x; p < W * W; p += kSearchThreads) {
+    int row = p / W, col = p - row * W;
+    int j = by - sa + row, i = bx - sa + col;
+    if (i < 0 || j < 0 || i >= v.bw || j >= v.bh) continue;
+    uint32_t word = (uint32_t)(__ldg(prev + (size_t)j * v.bw + i) >> 32);
+    winner_update(s, eval_candidate(t, word), row, col, W);
+  }
+  winner_block_reduce<kSearchThreads / 32>(s, red);
+
+  if (threadIdx.x == 0) {
+    int row, col;
+    int min_err = winner_resolve(s, W, row, col);
+    uint8_t flag = 0;
+    if (min_err <= thr) {
+      uint32_t word = (uint32_t)(prev[(size_t)(by - sa + row) * v.bw + (bx - sa + col)] >> 32);
+      v.final_blocks[(size_t)f * v.nb + b] = winning_block(t, word);
+      v.motion[((size_t)f * v.nb + b) * 2 + 0] = (uint8_t)(col | 0x80);  // x = (i - bx) + sa
+      v.motion[((size_t)f * v.nb + b) * 2 + 1] = (uint8_t)(row | 0x80);  // y = (j - by) + sa
+      flag = 1;
+    }
+    v.flags[(size_t)f * v.nb + b] = flag;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: intra search as a row-staggered wavefront.
+//
+// Block (x, y) reads the FINAL index words of (x-sa..x-1, y) and (x-sa..x+sa-1, y-1..y-2sa+1)
+// (dxt_image.cpp:672-679), which Reencode overwrites as it goes (:926).  One CTA walks one
+// block row left to right; row y may process block x once row y-1 has finished block
+// min(x+sa, bw)-1.  progress[f][y] = number of leading blocks of row y that are final.
+// Rows are handed out in increasing order by an atomic ticket, so every CTA a waiter depends
+// on already holds a ticket and is resident: no deadlock for any grid size.
+// Blocks with flags != 0 (found by the inter search) are already final and are skipped.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  cuda::atomic_ref<int, cuda::thread_scope_device> r(*const_cast<int *>(p));
+  return r.load(cuda::memory_order_acquire);
+}
+__device__ __forceinline__ void st_release(int *p, int val) {
+  cuda::atomic_ref<int, cuda::thread_scope_device> r(*p);
+  r.store(val, cuda::memory_order_release);
+}
+
+__global__ void __launch_bounds__(kSearchThreads)
+k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__restrict__ ticket) {
+  __shared__ TargetCtx t;
+  __shared__ WinnerState red[kSearchThreads / 32];
+  __shared__ int s_item;
+  const int W = 2 * sa;
+  const int n_items = n_gops * v.bh;
+  for (;;) {
+    if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if (item >= n_items) return;
+    const int g = item % n_gops, by = item / n_gops;
+    const int f = v.first + g * v.gop + k_in_gop;
+    if (f >= v.first + v.count) continue;
+    const uint8_t *frame = v.rgb + v.frame_bytes * f;
+    uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
+    const uint8_t *flags = v.flags + (size_t)f * v.nb;
+    int *progress = v.progress + (size_t)f * v.bh;
+    int published = 0;
+
+    for (int bx = 0; bx < v.bw; ++bx) {
+      const int b = by * v.bw + bx;
+      if (flags[b]) continue;  // uniform: already final (inter search hit)
+      if (threadIdx.x == 0) {
+        if (published < bx) { st_release(progress + by, bx); published = bx; }
+        if (by > 0) {
+          const int need = min(bx + sa, v.bw);
+          while (ld_acquire(progress + by - 1) < need) __nanosleep(20);
+        }
+        build_target(t, frame, v.w, bx, by, v.init_blocks[(size_t)f * v.nb + b]);
+      }
+      __syncthreads();
+
+      WinnerState s;
+      winner_init(s);
+      for (int p = threadIdx.x; p < W * W; p += kSearchThreads) {
+        int row = p / W, col = p - row * W;          // scan order: j downwards, i downwards
+        int j = by - row, i = bx + sa - 1 - col;
+        if (i < 0 || j < 0 || i >= v.bw || (row == 0 && i >= bx)) continue;
+        uint32_t word = (uint32_t)(__ldcg(cur + (size_t)j * v.bw + i) >> 32);
+        winner_update(s, eval_candidate(t, word), row, col, W);
+      }
+      winner_block_reduce<kSearchThreads / 32>(s, red);
+
+      if (threadIdx.x == 0) {
+        int row, col;
+        int min_err = winner_resolve(s, W, row, col);
+        size_t mo = ((size_t)f * v.nb + b) * 2;
+        if (min_err <= thr) {
+          uint32_t word = (uint32_t)(__ldcg(cur + (size_t)(by - row) * v.bw + (bx + sa - 1 - col)) >> 32);
+          cur[b] = winning_block(t, word);
+          v.motion[mo + 0] = (uint8_t)(2 * sa - 1 - col);  // x = (i - bx) + sa
+          v.motion[mo + 1] = (uint8_t)(2 * sa - 1 - row);  // y = (j - by) + 2sa - 1
+        } else {
+          v.motion[mo + 0] = 255;
+          v.motion[mo + 1] = 255;
+        }
+        __threadfence();
+        published = bx + 1;
+        st_release(progress + by, published);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_release(progress + by, v.bw);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: unique-palette compaction.  One CTA per frame; ordered prefix sum over the
+// "(255,255)" motion entries; emits the interp words in raster order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_compact_unique(SeqView v, int sa, unsigned long long *__restrict__ cand_counts) {
+  __shared__ int warp_sums[32];
+  __shared__ int s_base;
+  const int f = v.first + blockIdx.x;
+  const uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
+  const uint64_t *blocks = v.final_blocks + (size_t)f * v.nb;
+  uint32_t *out = v.unique + (size_t)f * v.nb;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool intra_frame = ((f - v.first) % v.gop) == 0;
+  unsigned long long n_inter = 0, n_intra = 0;  // full-window candidate positions
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < v.nb; start += 1024) {
+    int b = start + threadIdx.x;
+    bool uniq = false;
+    if (b < v.nb) {
+      uint16_t m = reinterpret_cast<const uint16_t *>(motion)[b];
+      uniq = (m == 0xFFFFu);
+      int bx = b % v.bw, by = b / v.bw;
+      bool inter_hit = !intra_frame && (m & 0x8080u) == 0x8080u && !uniq;
+      if (!intra_frame)
+        n_inter += (unsigned long long)(min(bx + sa, v.bw) - max(bx - sa, 0)) * (min(by + sa, v.bh) - max(by - sa, 0));
+      if (!inter_hit)
+        n_intra += (unsigned long long)min(by, 2 * sa - 1) * (min(bx + sa - 1, v.bw - 1) - max(bx - sa, 0) + 1) + min(bx, sa);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, uniq);
+    int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    int base = s_base;
+    int before = 0, total = 0;
+    for (int k = 0; k < 32; ++k) {
+      int c = warp_sums[k];
+      if (k < wid) before += c;
+      total += c;
+    }
+    if (uniq) out[base + before + in_warp] = (uint32_t)(blocks[b] >> 32);
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) v.n_unique[f] = (uint32_t)s_base;
+  for (int d = 16; d > 0; d >>= 1) {
+    n_inter += __shfl_xor_sync(0xffffffffu, n_inter, d);
+    n_intra += __shfl_xor_sync(0xffffffffu, n_intra, d);
+  }
+  if (lane == 0) {
+    atomicAdd(cand_counts + 0, n_inter);
+    atomicAdd(cand_counts + 1, n_intra);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: endpoint planes.  One CTA per (64x64 tile, plane, frame).  Colour transform, six
+// in-place lifting levels (columns then rows, wavelet.cpp:110-130) and the +128 symbol
+// mapping all happen on the tile in shared memory; 4 B/block in, 6 B/block out.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mirror_hi(int i, int n) { return i < n ? i : 2 * n - 2 - i; }
+
+__global__ void __launch_bounds__(1024)
+k_endpoint_planes(SeqView v, int pbw, int pbh) {
+  __shared__ int16_t a[64][65];
+  __shared__ int16_t d[64][65];
+  const int tiles_x = pbw / 64;
+  const int tx = (blockIdx.x % tiles_x) * 64, ty = (blockIdx.x / tiles_x) * 64;
+  const int plane = blockIdx.y;            // ep*3 + ch
+  const int ep = plane / 3, ch = plane % 3;
+  const int f = v.first + blockIdx.z;
+  const uint64_t *blocks = v.final_blocks + (size_t)f * v.nb;
+  for (int e = threadIdx.x; e < 4096; e += 1024) {
+    int y = e >> 6, x = e & 63;
+    int sx = min(tx + x, v.bw - 1), sy = min(ty + y, v.bh - 1);  // edge replication (extension)
+    uint32_t c = (uint32_t)((blocks[(size_t)sy * v.bw + sx] >> (16 * ep)) & 0xFFFFu);
+    int r = (int)(c >> 11), g = (int)((c >> 5) & 63u), b = (int)(c & 31u);
+    int co = r - b, tt = r + b + (b >> 4), cg = g - tt, yy = tt + cg / 2;  // image_processing.cpp:10-27
+    a[y][x] = (int16_t)(ch == 0 ? yy : (ch == 1 ? co : cg));
+  }
+  __syncthreads();
+  for (int dim = 64; dim > 1; dim >>= 1) {
+    const int half = dim >> 1;
+    // columns: predict (odd rows) ...
+    for (int e = threadIdx.x; e < half * dim; e += 1024) {
+      int k = e / dim, c = e - k * dim, i = 2 * k + 1;
+      d[k][c] = (int16_t)(a[i][c] - (a[i - 1][c] + a[mirror_hi(i + 1, dim)][c]) / 2);
+    }
+    __syncthreads();
+    // ... update (even rows), gather low half on top
+    int16_t sv[2];
+    int cnt = 0;
+    for (int e = threadIdx.x; e < half * dim; e += 1024) {
+      int k = e / dim, c = e - k * dim;
+      int dp = k == 0 ? 0 : k - 1;            // mirror: d[-1] -> d[0]
+      sv[cnt++] = (int16_t)(a[2 * k][c] + (d[dp][c] + d[k][c] + 2) / 4);
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int e = threadIdx.x; e < half * dim; e += 1024) {
+      int k = e / dim, c = e - k * dim;
+      a[k][c] = sv[cnt++];
+      a[half + k][c] = d[k][c];
+    }
+    __syncthreads();
+    // rows: predict (odd columns)
+    for (int e = threadIdx.x; e < half * dim; e += 1024) {
+      int r = e / half, k = e - r * half, i = 2 * k + 1;
+      d[r][k] = (int16_t)(a[r][i] - (a[r][i - 1] + a[r][mirror_hi(i + 1, dim)]) / 2);
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int e = threadIdx.x; e < half * dim; e += 1024) {
+      int r = e / half, k = e - r * half;
+      int dp = k == 0 ? 0 : k - 1;
+      sv[cnt++] = (int16_t)(a[r][2 * k] + (d[r][dp] + d[r][k] + 2) / 4);
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int e = threadIdx.x; e < half * dim; e += 1024) {
+      int r = e / half, k = e - r * half;
+      a[r][k] = sv[cnt++];
+      a[r][half + k] = d[r][k];
+    }
+    __syncthreads();
+  }
+  uint8_t *out = v.planes + ((size_t)f * 6 + plane) * (size_t)pbw * pbh;
+  for (int e = threadIdx.x; e < 1024; e += 1024) {
+    int y = e >> 4, x4 = (e & 15) * 4;
+    uint32_t w = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w |= (uint32_t)((uint8_t)((int8_t)a[y][x4 + q] + 128)) << (8 * q);
+    *reinterpret_cast<uint32_t *>(out + (size_t)(ty + y) * pbw + tx + x4) = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launch wrappers
+// ------------------------------------------------------------------------------------------
+void launch_dxt1_fit(const SeqView &v, cudaStream_t s) {
+  dim3 grid((v.nb + 127) / 128, v.count);
+  k_dxt1_fit<<<grid, 128, 0, s>>>(v.rgb + v.frame_bytes * v.first, v.frame_bytes, v.w, v.bw, v.nb,
+                                  v.init_blocks + (size_t)v.first * v.nb, v.final_blocks + (size_t)v.first * v.nb);
+}
+
+void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
+  dim3 grid(v.nb, n_gops);
+  k_inter_search<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, sa, thr);
+}
+
+void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
+                            int max_ctas, cudaStream_t s) {
+  int items = n_gops * v.bh;
+  int grid = items < max_ctas ? items : max_ctas;
+  k_intra_wavefront<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
+}
+
+void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, cudaStream_t s) {
+  k_compact_unique<<<v.count, 1024, 0, s>>>(v, sa, cand_counts);
+}
+
+void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, cudaStream_t s) {
+  dim3 grid((pbw / 64) * (pbh / 64), 6, v.count);
+  k_endpoint_planes<<<grid, 1024, 0, s>>>(v, pbw, pbh);
+}
+
+int intra_wavefront_max_ctas(int device) {
+  int per_sm = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intra_wavefront, kSearchThreads, 0);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (per_sm < 1) per_sm = 1;
+  return per_sm * sms;
+}
+
+}  // namespace mptc

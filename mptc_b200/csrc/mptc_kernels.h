@@ -1,0 +1,35 @@
+// mptc_kernels.h -- launch interface between the C-ABI layer and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mptc {
+
+// Device-resident sequence: all arrays are [frame][...] over the reserved capacity.
+struct SeqView {
+  const uint8_t *rgb;      // [F][h][w][3]
+  uint64_t *init_blocks;   // [F][nb]   stb fit (DXTImage ctor result)
+  uint64_t *final_blocks;  // [F][nb]   after Reencode
+  uint8_t *motion;         // [F][nb][2]
+  uint8_t *flags;          // [F][nb]   1 = final after the inter search
+  uint32_t *unique;        // [F][nb]
+  uint32_t *n_unique;      // [F]
+  uint8_t *planes;         // [F][6][pbh][pbw]
+  int *progress;           // [F][bh]   wavefront progress counters
+  size_t frame_bytes;
+  int w, h, bw, bh, nb;
+  int first, count;        // frame range of this encode call
+  int gop;
+};
+
+cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
+void launch_dxt1_fit(const SeqView &v, cudaStream_t s);
+void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
+void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
+                            int max_ctas, cudaStream_t s);
+void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, cudaStream_t s);
+void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, cudaStream_t s);
+int intra_wavefront_max_ctas(int device);
+
+}  // namespace mptc

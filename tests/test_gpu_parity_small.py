@@ -1,0 +1,91 @@
+"""GPU parity against the oracle on small seeded inputs (bit-exact: integer/byte/index work).
+Calls go through the C-ABI (mptc_b200.capi -> libmptc_b200.so)."""
+import numpy as np
+import pytest
+
+from mptc_b200.synth import make_sequence
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_sequence(frames, sa, thr, gop):
+    prev = None
+    res = []
+    for i, rgb in enumerate(frames):
+        init = port.dxt1_fit(rgb)
+        blocks, motion, unique = port.reencode(rgb, i % gop == 0, sa, thr, init, prev)
+        res.append((init, blocks, motion, unique))
+        prev = blocks
+    return res
+
+
+@pytest.mark.parametrize("w,h", [(64, 64), (256, 256), (200, 120)])
+def test_dxt1_fit_bit_exact(ctx, w, h):
+    frames = make_sequence(w, h, 2, seed=7)
+    for rgb in frames:
+        assert np.array_equal(ctx.dxt1_fit(rgb), port.dxt1_fit(rgb))
+
+
+def test_dxt1_fit_edge_content(ctx):
+    rng = np.random.default_rng(3)
+    h, w = 64, 128
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)           # noise
+    img[:16] = 0                                                          # flat black
+    img[16:32] = 255                                                      # flat white
+    img[32:36, :, :] = rng.integers(0, 256, size=(1, w, 3), dtype=np.uint8)  # vertical stripes
+    img[36:40, :, 1:] = 0                                                 # single channel
+    img[40:44] = np.arange(w, dtype=np.uint8)[None, :, None]             # grey ramp
+    assert np.array_equal(ctx.dxt1_fit(img), port.dxt1_fit(img))
+
+
+@pytest.mark.parametrize("sa,thr,gop", [(2, 50, 2), (4, 10, 3), (8, 50, 4), (16, 50, 4), (4, 0, 2), (3, 200, 2)])
+def test_reencode_single_frame_api(ctx, sa, thr, gop):
+    frames = make_sequence(128, 96, gop, seed=11)
+    ref = oracle_sequence(frames, sa, thr, gop)
+    prev = None
+    for i, rgb in enumerate(frames):
+        got = ctx.reencode(rgb, i == 0, sa, thr, prev)
+        init, blocks, motion, unique = ref[i]
+        assert np.array_equal(got["initial"], init)
+        assert np.array_equal(got["motion"], motion), f"frame {i}"
+        assert np.array_equal(got["blocks"], blocks), f"frame {i}"
+        assert np.array_equal(got["unique"], unique), f"frame {i}"
+        prev = got["blocks"]
+
+
+@pytest.mark.parametrize("w,h,n,sa,thr,gop", [(256, 256, 8, 8, 50, 4), (256, 256, 8, 16, 50, 4), (320, 192, 6, 4, 20, 3)])
+def test_sequence_bit_exact(ctx, w, h, n, sa, thr, gop):
+    frames = make_sequence(w, h, n)
+    ref = oracle_sequence(frames, sa, thr, gop)
+    out = ctx.encode_sequence(frames, sa, thr, gop)
+    for i in range(n):
+        init, blocks, motion, unique = ref[i]
+        assert np.array_equal(out["motion"][i], motion), f"frame {i}"
+        assert np.array_equal(out["blocks"][i], blocks), f"frame {i}"
+        nu = int(out["n_unique"][i])
+        assert nu == unique.size
+        assert np.array_equal(out["unique"][i, :nu], unique)
+        planes = port.endpoint_planes(blocks, w // 4, h // 4)
+        assert np.array_equal(out["planes"][i], planes), f"planes frame {i}"
+
+
+def test_flat_content_den_zero_path(ctx):
+    """Flat frames give all-equal index words (den == 0 in RecalculateEndpoints)."""
+    frames = np.empty((2, 64, 64, 3), dtype=np.uint8)
+    frames[0] = 77
+    frames[1] = 77
+    frames[1, 8:24, 8:40] = (10, 200, 30)
+    frames[0, 40:44, 0:64, 0] = np.arange(64, dtype=np.uint8) * 3
+    ref = oracle_sequence(frames, 4, 50, 2)
+    out = ctx.encode_sequence(frames, 4, 50, 2)
+    for i in range(2):
+        assert np.array_equal(out["blocks"][i], ref[i][1])
+        assert np.array_equal(out["motion"][i], ref[i][2])
+
+
+def test_endpoint_planes_api(ctx):
+    rng = np.random.default_rng(5)
+    for bw, bh in [(64, 64), (128, 64), (100, 70)]:
+        blocks = rng.integers(0, 2**63, size=bw * bh, dtype=np.uint64)
+        assert np.array_equal(ctx.endpoint_planes(blocks, bw, bh), port.endpoint_planes(blocks, bw, bh))
