@@ -347,17 +347,22 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
     uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
     const uint8_t *flags = v.flags + (size_t)f * v.nb;
     int *progress = v.progress + (size_t)f * v.bh;
-    int published = 0;
+    int published = 0, seen_above = 0;  // thread 0 only
 
     for (int bx = 0; bx < v.bw; ++bx) {
       const int b = by * v.bw + bx;
       if (flags[b]) continue;  // uniform: already final (inter search hit)
       if (threadIdx.x == 0) {
-        if (published < bx) { st_release(progress + by, bx); published = bx; }
+        // Invariant: progress[y] = p implies progress[y-1] >= min(p-1+sa, bw), so that by
+        // induction every row of the window is final -- also when blocks are skipped.
         if (by > 0) {
           const int need = min(bx + sa, v.bw);
-          while (ld_acquire(progress + by - 1) < need) __nanosleep(20);
+          while (seen_above < need) {
+            seen_above = ld_acquire(progress + by - 1);
+            if (seen_above < need) __nanosleep(20);
+          }
         }
+        if (published < bx) { st_release(progress + by, bx); published = bx; }
         build_target(t, frame, v.w, bx, by, v.init_blocks[(size_t)f * v.nb + b]);
       }
       __syncthreads();
@@ -392,7 +397,14 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) st_release(progress + by, v.bw);
+    if (threadIdx.x == 0) {
+      if (by > 0)
+        while (seen_above < v.bw) {
+          seen_above = ld_acquire(progress + by - 1);
+          if (seen_above < v.bw) __nanosleep(20);
+        }
+      st_release(progress + by, v.bw);
+    }
   }
 }
 
