@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- MPTC encode throughput (Mpixel/s) of the B200 hot path, the driver's contract.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path (DXT1 fit + inter/intra index-reuse search + unique
+compaction + endpoint wavelet planes) over one batch: the BASELINE.json configs[1] workload,
+a 1920x1080 synthetic 60-frame sequence, search_area 16, err_threshold 50, GOP 15, per GPU.
+With N GPUs (torchrun, one rank per GPU) each rank encodes its own 60-frame shard of a
+60*N-frame sequence: GOPs are independent, so there is no data-path collective (weak scaling).
+
+Printed JSON (rank 0, one line):
+  value     whole-job Mpixel/s with the frames already resident in HBM (device time of the
+            kernels, CUDA events on the library's compute stream, max over ranks)
+  e2e       the same metric through the C-ABI call with HOST (pinned) buffers: H2D of the
+            frames + kernels + D2H of blocks/motion/unique/planes inside the timed region
+  roofline  instruction-issue roofline of the dominant kernel: achieved =
+            candidate evaluations x 360 issue slots / kernel time, peak = 148 SMs x 4
+            schedulers x 32 lanes x SM clock; plus that kernel's algorithmic HBM GB/s
+  cpu_baseline  the reference encoder (oracle/_ref, unmodified reference sources) on the
+            box's host cores over a bounded sample of the same workload
+--impl reference prints the reference arm: the reference CPU encoder alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, FRAMES, SA, THR, GOP = 1920, 1080, 60, 16, 50, 15
+ALGO_SLOTS_PER_CANDIDATE = 360
+SM_COUNT, SCHEDULERS, LANES = 148, 4, 32
+WORKLOAD = f"{W}x{H} synthetic x{FRAMES} frames/GPU, search_area={SA}, err_threshold={THR}, gop={GOP}"
+METRIC = "mptc_encode_mpixel_per_s"
+UNIT = "Mpixel/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("sm_max_mhz", 1965.0)), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.dev), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    c = [x.strip() for x in line.split(",")]
+                    if len(c) < 9:
+                        continue
+                    try:
+                        sm.append(float(c[1])); mx.append(float(c[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm), reasons=sorted(reasons))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ---------------------------------------------------------------------------------------------
+def cpu_sample_frames(cores: int):
+    """Bounded sample of the workload: per host core one 2-frame GOP (intra + inter) of a
+    512x512 crop of the 1080p sequence, each core a different crop / GOP."""
+    from mptc_b200.synth import make_frame
+    crops = []
+    for t in range(cores):
+        g = t % (FRAMES // GOP)
+        f0 = g * GOP
+        x0 = (t * 192) % (W - 512) // 4 * 4
+        y0 = (t * 128) % (H - 512) // 4 * 4
+        pair = np.stack([make_frame(W, H, f0 + k)[y0:y0 + 512, x0:x0 + 512] for k in range(2)])
+        crops.append(np.ascontiguousarray(pair))
+    return crops
+
+
+def run_cpu_sample(crops, kind: str):
+    """One GOP per thread (ThreadedCompressMultiUnique, codec.cpp:1781-1793, without its
+    5-thread cap).  Returns seconds of wall time."""
+    if kind == "reference":
+        from oracle import ref
+
+        def work(pair):
+            prev = None
+            for i in range(pair.shape[0]):
+                fr = ref.RefFrame(pair[i], i == 0, SA, THR)   # DXTImage ctor (stb fit)
+                fr.reencode(prev)                             # DXTImage::Reencode
+                prev = fr
+        ref.lib()  # load + silence before threading
+        ref.RefFrame(crops[0][0][:16, :16], True, 1, THR)     # stb table init is not thread safe
+    else:
+        from oracle import port
+
+        def work(pair):
+            port.encode_gops(pair, GOP, SA, THR, 1, want_outputs=False)
+        port.lib()
+    threads = [threading.Thread(target=work, args=(c,)) for c in crops]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def cpu_kind():
+    from oracle import ref
+    return "reference" if ref.available() else "port"
+
+
+def cpu_baseline(steps: int = 1):
+    cores = os.cpu_count() or 1
+    kind = cpu_kind()
+    crops = cpu_sample_frames(cores)
+    pix = sum(c.shape[0] * c.shape[1] * c.shape[2] for c in crops)
+    times = [run_cpu_sample(crops, kind) for _ in range(steps)]
+    t = float(np.mean(times))
+    return {"value": pix / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{cores} threads x one 2-frame GOP (intra+inter) of a 512x512 crop of the 1080p sequence, "
+                      f"stages fit+search (DXTImage ctor + Reencode), sa={SA} thr={THR}; {t:.2f} s/step"}, times
+
+
+def reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    kind = cpu_kind()
+    crops = cpu_sample_frames(cores)
+    pix = sum(c.shape[0] * c.shape[1] * c.shape[2] for c in crops)
+    for _ in range(min(args.warmup, 1)):   # CPU code has no warm-up effects worth minutes of wall time
+        run_cpu_sample(crops, kind)
+    times = [run_cpu_sample(crops, kind) for _ in range(args.steps)]
+    t = float(np.mean(times))
+    val = pix / t / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference CPU encoder; each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} threads x one 2-frame GOP of a 512x512 crop, fit+search, sa={SA} thr={THR}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def gpu_arm(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+
+    from mptc_b200 import capi
+    from mptc_b200.synth import make_frame
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the encoder hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = capi.Context(local_rank)
+    nb = (W // 4) * (H // 4)
+    # this rank's shard of the 60*world-frame sequence: frames [60*rank, 60*rank+60)
+    pin_frames = capi.PinnedArray((FRAMES, H, W, 3), np.uint8)
+    for f in range(FRAMES):
+        pin_frames.array[f] = make_frame(W, H, FRAMES * rank + f)
+    frames = pin_frames.array
+    pbw, pbh = (W // 4 + 63) // 64 * 64, (H // 4 + 63) // 64 * 64
+    pins = {"blocks": capi.PinnedArray((FRAMES, nb), np.uint64), "motion": capi.PinnedArray((FRAMES, 2 * nb), np.uint8),
+            "unique": capi.PinnedArray((FRAMES, nb), np.uint32), "n_unique": capi.PinnedArray((FRAMES,), np.uint32),
+            "planes": capi.PinnedArray((FRAMES, 6, pbh, pbw), np.uint8)}
+    out = {k: v.array for k, v in pins.items()}
+    h2d_bytes = frames.nbytes
+    d2h_bytes = sum(a.nbytes for a in out.values())
+
+    ctx.seq_reserve(W, H, FRAMES)
+    ctx.seq_upload(frames)
+    ctx.sync()
+
+    def resident_step():
+        ctx.seq_encode(0, FRAMES, SA, THR, GOP)
+
+    def e2e_step():
+        ctx.encode_sequence(frames, SA, THR, GOP, out=out)
+
+    # ---- device-resident value ------------------------------------------------------------
+    for _ in range(args.warmup):
+        resident_step()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches
+    dev_ms, stage_ms = [], {k: 0.0 for k in ("fit", "inter", "intra", "compact", "planes")}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        resident_step()
+        dev_ms.append(ctx.last_encode_ms("total"))   # synchronises on the step's end event
+        for k in stage_ms:
+            stage_ms[k] += ctx.last_encode_ms(k)
+    barrier()
+    wall_s = time.perf_counter() - t0
+    launches = ctx.launches - launches0
+    n_inter, n_intra = ctx.last_candidate_count()
+    step_ms = max_over_ranks(float(np.mean(dev_ms)))
+    wall_ms = max_over_ranks(wall_s * 1e3 / args.steps)
+
+    # ---- end to end (host buffers) ----------------------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()                                    # returns after the D2H copies completed
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    clocks = sampler.stop()
+    checksum = int(out["n_unique"].sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pixels_total = FRAMES * W * H * world
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    for k in stage_ms:
+        stage_ms[k] /= args.steps
+    dominant = max(("inter", "intra"), key=lambda k: stage_ms[k])
+    n_cand = n_inter if dominant == "inter" else n_intra
+    k_launches = (GOP - 1) if dominant == "inter" else GOP   # one launch covers frame k of every GOP
+    k_ms = stage_ms[dominant]
+    achieved = n_cand * ALGO_SLOTS_PER_CANDIDATE / (k_ms * 1e-3) / 1e12
+    clk = sm_max_mhz
+    peak = SM_COUNT * SCHEDULERS * LANES * clk * 1e6 / 1e12
+    n_gops = FRAMES // GOP
+    # algorithmic HBM bytes of the search kernels: 72 B/block in + 20 B per
+    # distinct candidate + ~14 B/block out
+    frames_k = n_gops * ((GOP - 1) if dominant == "inter" else GOP)
+    algo_bytes = frames_k * nb * (72 + 20 + 14)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(dominant)
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "k_inter_search" if dominant == "inter" else "k_intra_wavefront",
+        "bound": "issue", "achieved": achieved, "peak": peak, "unit": "Tslot/s", "frac": achieved / peak,
+        "peak_source": f"148 SMs x 4 schedulers x 32 lanes x {clk:.0f} MHz (clocks.max.sm, {peak_src}); issue-slot roofline per SURVEY.md 8(d)",
+        "units_per_launch": n_cand / max(k_launches, 1), "launches_per_step": k_launches,
+        "avg_launch_ms": k_ms / max(k_launches, 1), "algo_slots_per_unit": ALGO_SLOTS_PER_CANDIDATE,
+        "traffic": traffic,
+        "hbm": {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
+        "stage_ms_per_step": stage_ms, "candidates_per_step": {"inter": n_inter, "intra": n_intra},
+    }
+    if clocks.get("sm_mhz"):
+        roofline["frac_at_sampled_clock"] = achieved / (SM_COUNT * SCHEDULERS * LANES * clocks["sm_mhz"] * 1e6 / 1e12)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_baseline(1)
+
+    line = {
+        "metric": METRIC, "value": pixels_total / (step_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "sharding": f"gop-sharded x{world}, no collective",
+                   "l2": "inputs (373 MB RGB per step) exceed the 126 MB L2; no explicit flush"},
+        "wall_ms_per_step": wall_ms,
+        "e2e": {"value": pixels_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "checksum_n_unique": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mptc_b200", choices=["mptc_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
