@@ -394,6 +394,60 @@ int mptc_oracle_reencode(const uint8_t *rgb, int w, int h, int is_intra, int sa,
   return nu;
 }
 
+/* Decoder-side index reconstruction (ReconstructDXTData, codec/codec.cpp:441-500): rebuilds
+ * every block's interp word from the motion bytes, the unique list and the previous
+ * frame's words.  Returns the number of unique words consumed, or -1 on a bad vector. */
+int mptc_oracle_reconstruct_words(const uint8_t *motion, const uint32_t *unique, int n_unique,
+                                  const uint32_t *prev_words, int bw, int bh, int sa, uint32_t *out) {
+  int nu = 0;
+  for (int b = 0; b < bw * bh; ++b) {
+    int x = motion[2 * b], y = motion[2 * b + 1], bx = b % bw, by = b / bw;
+    if (x == 255 && y == 255) {
+      if (nu >= n_unique) return -1;
+      out[b] = unique[nu++];
+    } else if ((x & 0x80) && (y & 0x80)) {
+      int rx = bx + (x & 0x7F) - sa, ry = by + (y & 0x7F) - sa;
+      if (!prev_words || rx < 0 || ry < 0 || rx >= bw || ry >= bh) return -1;
+      out[b] = prev_words[ry * bw + rx];
+    } else {
+      int rx = bx + x - sa, ry = by + y - (2 * sa - 1);
+      if (rx < 0 || ry < 0 || rx >= bw || ry >= bh || ry * bw + rx >= b) return -1;
+      out[b] = out[ry * bw + rx];
+    }
+  }
+  return nu;
+}
+
+/* Inductive spot check for frames too large to run the whole oracle on: for each listed
+ * block, redo the reference's decision for THAT block given the final blocks of its window
+ * (cur_final for already-visited positions, prev_final for the inter window) and compare it
+ * with what `cur_final`/`motion` hold.  If every block of a frame passes, the frame equals
+ * the reference's output by induction over raster order.  Returns the number of mismatches. */
+int mptc_oracle_check_blocks(const uint8_t *rgb, int w, int h, int is_intra, int sa, int thr,
+                             const uint64_t *init_blocks, const uint64_t *cur_final,
+                             const uint64_t *prev_final, const uint8_t *motion,
+                             const int *which, int n_which) {
+  int bw = w >> 2, bh = h >> 2, bad = 0;
+  uint8_t px[16][3];
+  for (int q = 0; q < n_which; ++q) {
+    int b = which[q], bx = b % bw, by = b / bw;
+    hit ht;
+    uint64_t want_blk;
+    uint8_t want_mx, want_my;
+    load_block(rgb, w, bx, by, px);
+    if (!is_intra && prev_final &&
+        search_inter(&px[0][0], init_blocks[b], prev_final, bw, bh, bx, by, sa, &ht) <= thr) {
+      want_blk = ht.blk; want_mx = (uint8_t)(ht.x | 0x80); want_my = (uint8_t)(ht.y | 0x80);
+    } else if (search_intra(&px[0][0], init_blocks[b], cur_final, bw, bh, bx, by, sa, &ht) <= thr) {
+      want_blk = ht.blk; want_mx = (uint8_t)ht.x; want_my = (uint8_t)ht.y;
+    } else {
+      want_blk = init_blocks[b]; want_mx = 255; want_my = 255;
+    }
+    bad += (want_blk != cur_final[b]) || want_mx != motion[2 * b] || want_my != motion[2 * b + 1];
+  }
+  return bad;
+}
+
 /* ------------------------------------------------------------------------------------
  * Endpoint planes: RGB565 -> YCoCg667 -> 64x64-tiled 5/3 integer wavelet -> uint8 symbols
  * (dxt_image.cpp:496-530, image_processing.cpp:10-27, image_processing.h:292-333,

@@ -32,6 +32,17 @@ int mptc_oracle_reencode(const uint8_t *rgb, int w, int h, int is_intra, int sea
 int mptc_oracle_eval_candidate(const uint8_t *pixels48, uint64_t own_block, uint32_t cand_word,
                                int *err_diff, uint64_t *new_block);
 
+/* Decoder-side word reconstruction (ReconstructDXTData, codec.cpp:441-500); returns the
+ * number of unique words consumed or -1 if a motion vector is invalid. */
+int mptc_oracle_reconstruct_words(const uint8_t *motion, const uint32_t *unique, int n_unique,
+                                  const uint32_t *prev_words, int bw, int bh, int sa, uint32_t *out);
+
+/* Per-block inductive check of a frame's results (see mptc_oracle.c); returns #mismatches. */
+int mptc_oracle_check_blocks(const uint8_t *rgb, int w, int h, int is_intra, int sa, int thr,
+                             const uint64_t *init_blocks, const uint64_t *cur_final,
+                             const uint64_t *prev_final, const uint8_t *motion,
+                             const int *which, int n_which);
+
 /* Endpoint planes (codec.cpp:804-845 + image_processing.h:292-333 + wavelet.cpp:30-131):
  * planes_out = ep1_Y | ep1_Co | ep1_Cg | ep2_Y | ep2_Co | ep2_Cg, each pbw*pbh symbols,
  * where pbw/pbh = bw/bh rounded up to a multiple of 64.  For bw,bh multiples of 64 this is

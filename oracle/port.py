@@ -34,6 +34,8 @@ def lib():
         L.mptc_oracle_psnr.restype = C.c_double
         L.mptc_oracle_psnr.argtypes = [vp, ci, ci, vp]
         L.mptc_oracle_tables.argtypes = [vp, vp]
+        L.mptc_oracle_reconstruct_words.argtypes = [vp, vp, ci, vp, ci, ci, ci, vp]
+        L.mptc_oracle_check_blocks.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci]
         L.mptc_oracle_encode_gops.restype = C.c_double
         L.mptc_oracle_encode_gops.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
         _lib = L
@@ -107,3 +109,34 @@ def encode_gops(frames, gop, search_area, err_threshold, threads, want_outputs=T
                                       ob.ctypes.data if want_outputs else None,
                                       om.ctypes.data if want_outputs else None)
     return t, ob, om
+
+
+def reconstruct_words(motion, unique, prev_words, bw, bh, search_area):
+    """Decoder-side index reconstruction; -> (words u32[nb], n_unique_consumed)."""
+    motion = np.ascontiguousarray(motion, dtype=np.uint8)
+    unique = np.ascontiguousarray(unique, dtype=np.uint32)
+    out = np.zeros(bw * bh, dtype=np.uint32)
+    pw = None
+    if prev_words is not None:
+        prev_words = np.ascontiguousarray(prev_words, dtype=np.uint32)
+        pw = prev_words.ctypes.data
+    n = lib().mptc_oracle_reconstruct_words(motion.ctypes.data, unique.ctypes.data, unique.size, pw, bw, bh,
+                                            search_area, out.ctypes.data)
+    return out, n
+
+
+def check_blocks(rgb, is_intra, search_area, err_threshold, init_blocks, cur_final, prev_final, motion, which):
+    """Re-derives the reference's decision for the blocks in `which`; -> number of mismatches."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w = rgb.shape[:2]
+    init_blocks = np.ascontiguousarray(init_blocks, dtype=np.uint64)
+    cur_final = np.ascontiguousarray(cur_final, dtype=np.uint64)
+    motion = np.ascontiguousarray(motion, dtype=np.uint8)
+    which = np.ascontiguousarray(which, dtype=np.int32)
+    pf = None
+    if prev_final is not None:
+        prev_final = np.ascontiguousarray(prev_final, dtype=np.uint64)
+        pf = prev_final.ctypes.data
+    return lib().mptc_oracle_check_blocks(rgb.ctypes.data, w, h, int(is_intra), search_area, err_threshold,
+                                          init_blocks.ctypes.data, cur_final.ctypes.data, pf, motion.ctypes.data,
+                                          which.ctypes.data, which.size)

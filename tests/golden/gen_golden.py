@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libmptc_ref.so, built
+by `make -C oracle ref` from /root/reference).  The reference ships no golden vectors of its
+own, so these fixtures -- outputs of the reference itself, run in the build
+container -- are what pins the oracle and the CUDA path.  Re-run only where /root/reference
+exists:   python tests/golden/gen_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from mptc_b200.synth import make_sequence  # noqa: E402
+from oracle import ref  # noqa: E402
+
+# name: (w, h, n_frames, seed, search_area, err_threshold, gop, store_arrays)
+CASES = {
+    "seq_64x64_sa2": (64, 64, 3, 5, 2, 50, 3, True),
+    "seq_128x96_sa4_thr10": (128, 96, 3, 11, 4, 10, 3, True),
+    "seq_256x256_sa8": (256, 256, 2, 1234, 8, 50, 2, True),       # multiple of 256: planes + payload defined
+    "seq_256x256_sa16_hash": (256, 256, 8, 1234, 16, 50, 4, False),  # BASELINE configs[0], hashes only
+    "seq_320x192_sa4_thr0_hash": (320, 192, 6, 3, 4, 0, 3, False),
+}
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_case(w, h, n, seed, sa, thr, gop, store):
+    frames = make_sequence(w, h, n, seed=seed)
+    seq = ref.encode_sequence(frames, sa, thr, gop)
+    out = {"params": np.array([w, h, n, seed, sa, thr, gop], dtype=np.int64), "frames_sha": np.array(sha(frames))}
+    hashes = []
+    for i, fr in enumerate(seq):
+        init, fin, mo, un = fr.initial_blocks, fr.blocks(), fr.motion(), fr.unique()
+        hashes.append([sha(init), sha(fin), sha(mo), sha(un)])
+        if store:
+            out[f"init_{i}"] = init
+            out[f"final_{i}"] = fin
+            out[f"motion_{i}"] = mo
+            out[f"unique_{i}"] = un
+        out[f"psnr_physical_{i}"] = np.array(fr.psnr_physical())
+        if w % 256 == 0 and h % 256 == 0:
+            payload = fr.entropy_payload()
+            nu, planes, motion, sizes = fr.payload_planes(payload)
+            assert nu == un.size and np.array_equal(motion, mo)
+            out[f"sizes_{i}"] = sizes
+            hashes[-1] += [sha(planes), hashlib.sha256(payload).hexdigest()]
+            if store:
+                out[f"planes_{i}"] = planes
+                out[f"payload_{i}"] = np.frombuffer(payload, dtype=np.uint8)
+    out["hashes"] = np.array(hashes)
+    return out
+
+
+def main():
+    assert ref.available(), "build oracle/_ref first: make -C oracle ref"
+    assert ref.selfcheck_png(make_sequence(64, 64, 1)[0]) == 0
+    for name, cfg in CASES.items():
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(*cfg))
+        print("wrote", name)
+    # arithmetic coder known answers
+    rng = np.random.default_rng(99)
+    streams = {
+        "empty": np.zeros(0, dtype=np.uint8),
+        "one": np.array([200], dtype=np.uint8),
+        "zeros": np.zeros(3000, dtype=np.uint8),
+        "skewed": np.clip(rng.normal(128, 6, 20000), 0, 255).astype(np.uint8),
+        "uniform": rng.integers(0, 256, 5000, dtype=np.uint8),
+        "ff": np.full(700, 255, dtype=np.uint8),
+    }
+    out = {}
+    for k, s in streams.items():
+        out["sym_" + k] = s
+        out["enc_" + k] = np.frombuffer(ref.arith_encode(s), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "arith.npz"), **out)
+    print("wrote arith")
+
+
+if __name__ == "__main__":
+    main()

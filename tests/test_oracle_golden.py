@@ -1,0 +1,87 @@
+"""CPU: the oracle (oracle/mptc_oracle.c) against the golden fixtures generated from the
+unmodified reference (tests/golden/gen_golden.py).  Bit-exact."""
+import numpy as np
+import pytest
+
+from golden_util import check_sequence_against_golden, load, sequence_cases, sha
+from mptc_b200.synth import make_sequence
+from oracle import port
+
+
+@pytest.mark.parametrize("name", sequence_cases())
+def test_port_matches_reference_fixture(name):
+    g = load(name)
+    w, h, n, seed, sa, thr, gop = [int(x) for x in g["params"]]
+    frames = make_sequence(w, h, n, seed=seed)
+    assert sha(frames) == str(g["frames_sha"]), "synthetic generator drifted"
+    prev = None
+    res = []
+    for i in range(n):
+        init = port.dxt1_fit(frames[i])
+        blocks, motion, unique = port.reencode(frames[i], i % gop == 0, sa, thr, init, prev)
+        r = {"initial": init, "blocks": blocks, "motion": motion, "unique": unique}
+        if w % 256 == 0 and h % 256 == 0:
+            r["planes"] = port.endpoint_planes(blocks, w // 4, h // 4).reshape(6, -1)
+        assert abs(port.psnr(frames[i], blocks) - float(g[f"psnr_physical_{i}"])) < 1e-9
+        res.append(r)
+        prev = blocks
+    check_sequence_against_golden(g, res)
+
+
+def test_arith_coder_known_answers():
+    g = load("arith")
+    names = [k[4:] for k in g.files if k.startswith("sym_")]
+    assert len(names) >= 5
+    for k in names:
+        assert port.arith_encode(g["sym_" + k]) == g["enc_" + k].tobytes(), k
+
+
+def test_payload_sizes_from_planes():
+    """Compressed size of every per-frame stream equals the reference's (codec.cpp:1115-1158)."""
+    g = load("seq_256x256_sa8")
+    for i in range(2):
+        planes = g[f"planes_{i}"]
+        sizes = g[f"sizes_{i}"]
+        mine = [len(port.arith_encode(g[f"motion_{i}"])), len(port.arith_encode(planes[0])),
+                len(port.arith_encode(np.concatenate([planes[1], planes[2]]))), len(port.arith_encode(planes[3])),
+                len(port.arith_encode(np.concatenate([planes[4], planes[5]])))]
+        assert mine == [int(s) for s in sizes]
+
+
+def test_reconstruct_words_round_trip():
+    """Decoder-side reconstruction (codec.cpp:441-500) of the oracle's own output."""
+    w, h, n, sa, thr, gop = 128, 96, 4, 4, 20, 2
+    frames = make_sequence(w, h, n, seed=21)
+    prev = None
+    for i in range(n):
+        init = port.dxt1_fit(frames[i])
+        blocks, motion, unique = port.reencode(frames[i], i % gop == 0, sa, thr, init, prev)
+        pw = None if prev is None else (prev >> np.uint64(32)).astype(np.uint32)
+        words, used = port.reconstruct_words(motion, unique, pw, w // 4, h // 4, sa)
+        assert used == unique.size
+        assert np.array_equal(words, (blocks >> np.uint64(32)).astype(np.uint32))
+        assert port.check_blocks(frames[i], i % gop == 0, sa, thr, init, blocks, prev, motion,
+                                 np.arange(blocks.size)) == 0
+        prev = blocks
+
+
+def test_check_blocks_detects_corruption():
+    frames = make_sequence(64, 64, 1, seed=2)
+    init = port.dxt1_fit(frames[0])
+    blocks, motion, unique = port.reencode(frames[0], True, 2, 50, init, None)
+    bad = blocks.copy()
+    bad[37] ^= np.uint64(1 << 40)
+    assert port.check_blocks(frames[0], True, 2, 50, init, bad, None, motion, np.arange(blocks.size)) >= 1
+
+
+def test_endpoint_planes_padding_extension():
+    """Non-multiple-of-64 planes: edge replication up to the next multiple of 64 (extension)."""
+    rng = np.random.default_rng(1)
+    bw, bh = 100, 70
+    blocks = rng.integers(0, 2**63, size=bw * bh, dtype=np.uint64)
+    got = port.endpoint_planes(blocks, bw, bh)
+    assert got.shape == (6, 128, 128)
+    padded = np.empty((128, 128), dtype=np.uint64)
+    b2 = blocks.reshape(bh, bw)
+    padded[:] = b2[np.minimum(np.arange(128), bh - 1)[:, None], np.minimum(np.arange(128), bw - 1)[None, :]]
+    assert np.array_equal(got, port.endpoint_planes(padded.reshape(-1), 128, 128))
