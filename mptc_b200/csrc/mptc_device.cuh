@@ -124,6 +124,21 @@ __device__ __forceinline__ void refit_endpoints(const float *pf, uint32_t word, 
   ep2 = (uint32_t)r2 | ((uint32_t)g2 << 8) | ((uint32_t)b2 << 16);
 }
 
+// Loads the 4x4 block (bx, by) of an RGB8 frame as 16 RGBX words.  Each thread reads 4 rows
+// x 12 bytes as three aligned 32-bit words; consecutive threads read consecutive 12-byte
+// runs, so a warp covers 384 contiguous bytes per row.
+__device__ __forceinline__ void load_block_rgbx(const uint8_t *frame, int w, int bx, int by, uint32_t *px) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + ((size_t)(by * 4 + j) * w + bx * 4) * 3);
+    uint32_t a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
+    px[4 * j + 0] = a & 0x00FFFFFFu;
+    px[4 * j + 1] = (a >> 24) | ((b & 0xFFFFu) << 8);
+    px[4 * j + 2] = (b >> 16) | ((c & 0xFFu) << 16);
+    px[4 * j + 3] = c >> 8;
+  }
+}
+
 // Per-target-block context, built once per target and shared by every candidate evaluation.
 struct TargetCtx {
   float pf[48];        // pixels as float, [k*3 + ch]      (Get4X4ColorsBlock, dxt_image.cpp:636-650)

@@ -1,0 +1,250 @@
+// mptc_inter.cu -- K2: tiled inter search with per-tile de-duplication of index words.
+//
+// Restates DXTImage::InterBlockSearch + the winner apply in Reencode
+// (codec/dxt_image.cpp:715-774, :885-908).  The reference evaluates every window position;
+// the evaluation result depends only on (target block, 32-bit index word), and after
+// re-encoding a frame's words are overwhelmingly copies of one another (that is MPTC's
+// whole point), so a 32x32 window typically holds well under 100 distinct words.  One CTA
+// takes an 8x4 tile of targets, de-duplicates the words of the union of their windows in
+// shared memory, evaluates each DISTINCT word once per target (lane = target, word uniform
+// across the warp: mptc_uniform_eval.cuh), then every target scans its own window positions
+// through the (word id -> err_diff) table with the order-independent form of the reference's
+// stateful winner scan (WinnerState).  Results are bit-identical to the
+// position-by-position loop.
+#include "mptc_kernels.h"
+#include "mptc_uniform_eval.cuh"
+
+namespace mptc {
+
+namespace {
+
+constexpr int kTileX = 8, kTileY = 4;         // 32 targets per CTA: lane = ty*8 + tx
+constexpr int kThreads = 256, kWarps = kThreads / 32;
+constexpr int kChunk = 128;                   // distinct words evaluated per pass
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;      // hash-table empty marker (the real word
+                                              // 0xFFFFFFFF lives in the extra slot HT)
+constexpr uint16_t kNoPos = 0xFFFFu;          // window position outside the frame
+
+struct TileSmem {
+  // dynamic shared memory carve-up (all sizes depend on search_area)
+  uint32_t *win;       // [NP]   index word of each union-window position
+  uint16_t *pos_uid;   // [NP]   hash slot, then dense id of that position's word
+  uint32_t *keys;      // [HT+1] open-addressing table of words
+  uint16_t *slot_uid;  // [HT+1]
+  uint32_t *ulist;     // [NP]   dense list of distinct words
+  float4 *coef;        // [kChunk]
+  int *err;            // [kChunk][33]
+};
+
+__host__ __device__ inline int round_up_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+__host__ __device__ inline size_t tile_smem_bytes(int sa, int *np_out, int *ht_out) {
+  const int UW = 2 * sa + kTileX - 1, UH = 2 * sa + kTileY - 1;
+  const int NP = UW * UH;
+  const int HT = round_up_pow2(NP + NP / 4);
+  if (np_out) *np_out = NP;
+  if (ht_out) *ht_out = HT;
+  size_t b = 0;
+  b += (size_t)kChunk * sizeof(float4);            // coef (16-byte aligned first)
+  b += (size_t)kChunk * 33 * sizeof(int);          // err
+  b += (size_t)NP * 4;                             // win
+  b += (size_t)(HT + 1) * 4;                       // keys
+  b += (size_t)NP * 4;                             // ulist
+  b += (size_t)NP * 2;                             // pos_uid
+  b += (size_t)(HT + 1) * 2;                       // slot_uid
+  return (b + 15) & ~(size_t)15;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads)
+k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_count, s_special;
+  __shared__ int s_res_err[kTileX * kTileY], s_res_pos[kTileX * kTileY];
+
+  const int W = 2 * sa;
+  const int UW = W + kTileX - 1, UH = W + kTileY - 1;
+  int NP, HT;
+  tile_smem_bytes(sa, &NP, &HT);
+  TileSmem sm;
+  {
+    unsigned char *p = smem_raw;
+    sm.coef = reinterpret_cast<float4 *>(p);   p += (size_t)kChunk * sizeof(float4);
+    sm.err = reinterpret_cast<int *>(p);       p += (size_t)kChunk * 33 * sizeof(int);
+    sm.win = reinterpret_cast<uint32_t *>(p);  p += (size_t)NP * 4;
+    sm.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)(HT + 1) * 4;
+    sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)NP * 4;
+    sm.pos_uid = reinterpret_cast<uint16_t *>(p); p += (size_t)NP * 2;
+    sm.slot_uid = reinterpret_cast<uint16_t *>(p);
+  }
+
+  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
+  if (f >= v.first + v.count) return;
+  const int tiles_x = (v.bw + kTileX - 1) / kTileX;
+  const int tx0 = (blockIdx.x % tiles_x) * kTileX, ty0 = (blockIdx.x / tiles_x) * kTileY;
+  const int ux0 = tx0 - sa, uy0 = ty0 - sa;   // union-window origin in block coordinates
+  const uint64_t *prev = v.final_blocks + (size_t)(f - 1) * v.nb;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  // ---- phase 0: clear the hash table -------------------------------------------------------
+  for (int s = tid; s <= HT; s += kThreads) sm.keys[s] = kEmpty;
+  if (tid == 0) { s_count = 0; s_special = 0; }
+  __syncthreads();
+
+  // ---- phase 1: load the union window, insert its words -------------------------------------
+  const uint32_t hmask = (uint32_t)HT - 1u;
+  const int hshift = 32 - __ffs(HT) + 1;   // HT = 2^(ffs-1)
+  for (int p = tid; p < NP; p += kThreads) {
+    const int ur = p / UW, uc = p - ur * UW;
+    const int i = ux0 + uc, j = uy0 + ur;
+    uint16_t slot = kNoPos;
+    if (i >= 0 && j >= 0 && i < v.bw && j < v.bh) {
+      const uint32_t word = (uint32_t)(__ldg(prev + (size_t)j * v.bw + i) >> 32);
+      sm.win[p] = word;
+      if (word == kEmpty) {
+        s_special = 1;
+        slot = (uint16_t)HT;
+      } else {
+        uint32_t h = (word * 0x9E3779B1u) >> hshift;
+        for (;;) {
+          const uint32_t old = atomicCAS(&sm.keys[h], kEmpty, word);
+          if (old == kEmpty || old == word) break;
+          h = (h + 1u) & hmask;
+        }
+        slot = (uint16_t)h;
+      }
+    }
+    sm.pos_uid[p] = slot;
+  }
+
+  // this lane's target block (every warp holds the same 32 targets)
+  const int tbx = tx0 + (lane & (kTileX - 1)), tby = ty0 + (lane >> 3);
+  const bool t_valid = tbx < v.bw && tby < v.bh;
+  const int tb = tby * v.bw + tbx;
+  LaneTarget t;
+  if (t_valid) {
+    load_lane_target(t, v.rgb + v.frame_bytes * f, v.w, tbx, tby, v.init_blocks[(size_t)f * v.nb + tb]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t.px[k] = 0u;
+    t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+  }
+  __syncthreads();
+
+  // ---- phase 2: dense ids for the distinct words ----------------------------------------------
+  for (int s = tid; s <= HT; s += kThreads) {
+    const bool occ = (s < HT) ? (sm.keys[s] != kEmpty) : (s_special != 0);
+    if (occ) {
+      const int uid = atomicAdd(&s_count, 1);
+      sm.slot_uid[s] = (uint16_t)uid;
+      sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;
+    }
+  }
+  __syncthreads();
+  const int U = s_count;
+  for (int p = tid; p < NP; p += kThreads) {
+    const uint16_t slot = sm.pos_uid[p];
+    if (slot != kNoPos) sm.pos_uid[p] = sm.slot_uid[slot];
+  }
+  // (visibility of pos_uid is guaranteed by the barrier after the coefficient pass below)
+
+  // ---- phases 3-5 per chunk of distinct words ----------------------------------------------
+  WinnerState ws[kTileX * kTileY / kWarps];   // this warp scans targets wid, wid+8, wid+16, wid+24
+#pragma unroll
+  for (int q = 0; q < kTileX * kTileY / kWarps; ++q) winner_init(ws[q]);
+
+  for (int c0 = 0; c0 < U; c0 += kChunk) {
+    const int cn = min(kChunk, U - c0);
+    for (int u = tid; u < cn; u += kThreads) sm.coef[u] = word_coefs(sm.ulist[c0 + u]);
+    __syncthreads();
+
+    // evaluate: warp = one distinct word, lane = target
+    for (int u = wid; u < cn; u += kWarps) {
+      const uint32_t word = sm.ulist[c0 + u];
+      const float4 cf = sm.coef[u];
+      sm.err[u * 33 + lane] = eval_uniform(t, word, cf);
+    }
+    __syncthreads();
+
+    // scan: each target walks its own window in the reference's order (j up, i up)
+#pragma unroll
+    for (int q = 0; q < kTileX * kTileY / kWarps; ++q) {
+      const int tt = wid + q * kWarps;
+      const int ttx = tt & (kTileX - 1), tty = tt >> 3;
+      if (tx0 + ttx >= v.bw || ty0 + tty >= v.bh) continue;   // warp-uniform
+      for (int p = lane; p < W * W; p += 32) {
+        const int row = p / W, col = p - row * W;
+        const uint16_t uid = sm.pos_uid[(tty + row) * UW + ttx + col];
+        if (uid == kNoPos) continue;
+        const int u = (int)uid - c0;
+        if (u < 0 || u >= cn) continue;
+        winner_update(ws[q], sm.err[u * 33 + tt], row, col, W);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 6: resolve and apply ------------------------------------------------------------
+#pragma unroll
+  for (int q = 0; q < kTileX * kTileY / kWarps; ++q) {
+    winner_warp_reduce(ws[q]);
+    if (lane == 0) {
+      int row, col;
+      const int tt = wid + q * kWarps;
+      s_res_err[tt] = winner_resolve(ws[q], W, row, col);
+      s_res_pos[tt] = (row << 8) | col;
+    }
+  }
+  __syncthreads();
+  if (wid == 0 && t_valid) {
+    const int min_err = s_res_err[lane];
+    const int row = s_res_pos[lane] >> 8, col = s_res_pos[lane] & 0xFF;
+    uint8_t flag = 0;
+    if (min_err <= thr) {
+      const uint32_t word = sm.win[((lane >> 3) + row) * UW + (lane & (kTileX - 1)) + col];
+      uint64_t blk = t.own_block;
+      if (word != t.own_word) {
+        uint32_t ep1, ep2;
+        refit_endpoints(t.pf, word, ep1, ep2);
+        blk = (uint64_t)pack565_rgbx(ep1) | ((uint64_t)pack565_rgbx(ep2) << 16) | ((uint64_t)word << 32);
+      }
+      v.final_blocks[(size_t)f * v.nb + tb] = blk;
+      v.motion[((size_t)f * v.nb + tb) * 2 + 0] = (uint8_t)(col | 0x80);   // x = (i - bx) + sa
+      v.motion[((size_t)f * v.nb + tb) * 2 + 1] = (uint8_t)(row | 0x80);   // y = (j - by) + sa
+      flag = 1;
+    }
+    v.flags[(size_t)f * v.nb + tb] = flag;
+  }
+}
+
+// Returns false when the tile's shared memory does not fit (very large search_area): the
+// caller then uses the direct kernel.
+bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
+  static int max_optin = -1;
+  if (max_optin < 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  }
+  const size_t bytes = tile_smem_bytes(sa, nullptr, nullptr);
+  if (bytes + 1024 > (size_t)max_optin) return false;
+  static size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(k_inter_search_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return false;
+    configured = bytes;
+  }
+  const int tiles = ((v.bw + kTileX - 1) / kTileX) * ((v.bh + kTileY - 1) / kTileY);
+  dim3 grid(tiles, n_gops);
+  k_inter_search_tiled<<<grid, kThreads, bytes, s>>>(v, k_in_gop, sa, thr);
+  return true;
+}
+
+}  // namespace mptc

@@ -195,21 +195,6 @@ __device__ __forceinline__ uint64_t fit_block(const uint32_t *px) {
   return (uint64_t)mx | ((uint64_t)mn << 16) | ((uint64_t)mask << 32);
 }
 
-// Loads the 4x4 block (bx, by) of an RGB8 frame as 16 RGBX words.  Each thread reads 4 rows
-// x 12 bytes as three aligned 32-bit words; consecutive threads read consecutive 12-byte
-// runs, so a warp covers 384 contiguous bytes per row.
-__device__ __forceinline__ void load_block_rgbx(const uint8_t *frame, int w, int bx, int by, uint32_t *px) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t *row = reinterpret_cast<const uint32_t *>(frame + ((size_t)(by * 4 + j) * w + bx * 4) * 3);
-    uint32_t a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
-    px[4 * j + 0] = a & 0x00FFFFFFu;
-    px[4 * j + 1] = (a >> 24) | ((b & 0xFFFFu) << 8);
-    px[4 * j + 2] = (b >> 16) | ((c & 0xFFu) << 16);
-    px[4 * j + 3] = c >> 8;
-  }
-}
-
 __global__ void __launch_bounds__(128) k_dxt1_fit(const uint8_t *__restrict__ rgb, size_t frame_bytes, int w, int bw,
                                                    int nb, uint64_t *__restrict__ init_blocks,
                                                    uint64_t *__restrict__ final_blocks) {
@@ -556,7 +541,8 @@ void launch_dxt1_fit(const SeqView &v, cudaStream_t s) {
 }
 
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
-  dim3 grid(v.nb, n_gops);
+  if (launch_inter_search_tiled(v, k_in_gop, n_gops, sa, thr, s)) return;
+  dim3 grid(v.nb, n_gops);  // direct (one CTA per target) fallback for very large windows
   k_inter_search<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, sa, thr);
 }
 
