@@ -191,6 +191,14 @@ __device__ __forceinline__ void winner_update(WinnerState &s, int e, int row, in
   s.best = min(s.best, ((uint32_t)(e + 65536) << 14) | p);
 }
 
+// Branch-free form for the tiled kernels.  e must be a real err_diff (|e| <= 65025) or 65535
+// for "rejected"; p = row*W + col; key = (row << 7) | (127 - col).
+__device__ __forceinline__ void winner_update_fast(WinnerState &s, int e, uint32_t p, int key) {
+  s.best = min(s.best, (uint32_t)(e * 16384) + (p + (65536u << 14)));
+  s.first = min(s.first, p | ((uint32_t)(-e) & 0x80000000u));   // sign(-e) set <=> e > 0
+  s.lastneg = max(s.lastneg, key | ~(e >> 31));                   // -1 unless e < 0
+}
+
 __device__ __forceinline__ void winner_merge(WinnerState &s, const WinnerState &o) {
   s.first = min(s.first, o.first);
   s.lastneg = max(s.lastneg, o.lastneg);
@@ -211,7 +219,7 @@ __device__ __forceinline__ void winner_warp_reduce(WinnerState &s) {
 // Returns the search's return value (min_err) and the winning (row, col); INT_MAX if nothing
 // was accepted.
 __device__ __forceinline__ int winner_resolve(const WinnerState &s, int W, int &row, int &col) {
-  if (s.first != 0xffffffffu) {
+  if (s.first < 0x80000000u) {
     row = (int)(s.first / (uint32_t)W);
     col = (int)(s.first % (uint32_t)W);
     if (s.lastneg >= 0 && (s.lastneg >> 7) > row) {
@@ -220,7 +228,7 @@ __device__ __forceinline__ int winner_resolve(const WinnerState &s, int W, int &
     }
     return 0;
   }
-  if (s.best != 0xffffffffu) {
+  if ((s.best >> 14) < 131071u) {  // 131071 = rejected marker (65535 + 65536), also the init value's range
     uint32_t p = s.best & 0x3FFFu;
     row = (int)(p / (uint32_t)W);
     col = (int)(p % (uint32_t)W);

@@ -32,8 +32,9 @@ struct TileSmem {
   uint32_t *keys;      // [HT+1] open-addressing table of words
   uint16_t *slot_uid;  // [HT+1]
   uint32_t *ulist;     // [NP]   dense list of distinct words
-  float4 *coef;        // [kChunk]
-  int *err;            // [kChunk][33]
+  WordInfo *info;      // [kChunk]
+  int *err;            // [kChunk + 1][33]; row kChunk = "rejected" for every target
+  uint8_t *lut5, *lut6;  // ToFiveBits / ToSixBits tables
 };
 
 __host__ __device__ inline int round_up_pow2(int x) {
@@ -49,8 +50,9 @@ __host__ __device__ inline size_t tile_smem_bytes(int sa, int *np_out, int *ht_o
   if (np_out) *np_out = NP;
   if (ht_out) *ht_out = HT;
   size_t b = 0;
-  b += (size_t)kChunk * sizeof(float4);            // coef (16-byte aligned first)
-  b += (size_t)kChunk * 33 * sizeof(int);          // err
+  b += (size_t)kChunk * sizeof(WordInfo);          // info (16-byte aligned first)
+  b += (size_t)(kChunk + 1) * 33 * sizeof(int);    // err
+  b += 512;                                        // lut5, lut6
   b += (size_t)NP * 4;                             // win
   b += (size_t)(HT + 1) * 4;                       // keys
   b += (size_t)NP * 4;                             // ulist
@@ -61,7 +63,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int sa, int *np_out, int *ht_o
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_count, s_special;
@@ -74,8 +76,9 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   TileSmem sm;
   {
     unsigned char *p = smem_raw;
-    sm.coef = reinterpret_cast<float4 *>(p);   p += (size_t)kChunk * sizeof(float4);
-    sm.err = reinterpret_cast<int *>(p);       p += (size_t)kChunk * 33 * sizeof(int);
+    sm.info = reinterpret_cast<WordInfo *>(p); p += (size_t)kChunk * sizeof(WordInfo);
+    sm.err = reinterpret_cast<int *>(p);       p += (size_t)(kChunk + 1) * 33 * sizeof(int);
+    sm.lut5 = p; sm.lut6 = p + 256;            p += 512;
     sm.win = reinterpret_cast<uint32_t *>(p);  p += (size_t)NP * 4;
     sm.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)(HT + 1) * 4;
     sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)NP * 4;
@@ -93,6 +96,9 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
 
   // ---- phase 0: clear the hash table -------------------------------------------------------
   for (int s = tid; s <= HT; s += kThreads) sm.keys[s] = kEmpty;
+  sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
+  sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
+  if (tid < 33) sm.err[kChunk * 33 + tid] = kRejectedSmall;
   if (tid == 0) { s_count = 0; s_special = 0; }
   __syncthreads();
 
@@ -133,7 +139,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
 #pragma unroll
     for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) t.px[k] = 0u;
+    for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
     t.own_block = 0; t.own_word = 0; t.orig_err = 0;
   }
   __syncthreads();
@@ -151,7 +157,9 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   const int U = s_count;
   for (int p = tid; p < NP; p += kThreads) {
     const uint16_t slot = sm.pos_uid[p];
-    if (slot != kNoPos) sm.pos_uid[p] = sm.slot_uid[slot];
+    // out-of-frame positions: the all-rejected row when everything fits one chunk, otherwise an
+    // id no chunk contains
+    sm.pos_uid[p] = (slot != kNoPos) ? sm.slot_uid[slot] : (uint16_t)(U <= kChunk ? kChunk : kNoPos);
   }
   // (visibility of pos_uid is guaranteed by the barrier after the coefficient pass below)
 
@@ -162,30 +170,37 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
 
   for (int c0 = 0; c0 < U; c0 += kChunk) {
     const int cn = min(kChunk, U - c0);
-    for (int u = tid; u < cn; u += kThreads) sm.coef[u] = word_coefs(sm.ulist[c0 + u]);
+    for (int u = tid; u < cn; u += kThreads) sm.info[u] = word_info(sm.ulist[c0 + u]);
     __syncthreads();
 
     // evaluate: warp = one distinct word, lane = target
     for (int u = wid; u < cn; u += kWarps) {
       const uint32_t word = sm.ulist[c0 + u];
-      const float4 cf = sm.coef[u];
-      sm.err[u * 33 + lane] = eval_uniform(t, word, cf);
+      const WordInfo wi = sm.info[u];
+      sm.err[u * 33 + lane] = eval_uniform(t, word, wi, sm.lut5, sm.lut6);
     }
     __syncthreads();
 
-    // scan: each target walks its own window in the reference's order (j up, i up)
+    // scan: each target walks its own window in the reference's order (j up, i up).
+    // Positions outside the frame (and, when the words do not fit one chunk, words of other
+    // chunks) read the all-rejected row kChunk.
+    const bool single = (U <= kChunk);
 #pragma unroll
     for (int q = 0; q < kTileX * kTileY / kWarps; ++q) {
       const int tt = wid + q * kWarps;
       const int ttx = tt & (kTileX - 1), tty = tt >> 3;
       if (tx0 + ttx >= v.bw || ty0 + tty >= v.bh) continue;   // warp-uniform
-      for (int p = lane; p < W * W; p += 32) {
-        const int row = p / W, col = p - row * W;
-        const uint16_t uid = sm.pos_uid[(tty + row) * UW + ttx + col];
-        if (uid == kNoPos) continue;
-        const int u = (int)uid - c0;
-        if (u < 0 || u >= cn) continue;
-        winner_update(ws[q], sm.err[u * 33 + tt], row, col, W);
+      const int *errt = sm.err + tt;
+      for (int row = 0; row < W; ++row) {
+        const uint16_t *urow = sm.pos_uid + (tty + row) * UW + ttx;
+        for (int col = lane; col < W; col += 32) {
+          int u = urow[col];
+          if (!single) {
+            u -= c0;
+            u = ((unsigned)u < (unsigned)cn) ? u : kChunk;
+          }
+          winner_update_fast(ws[q], errt[u * 33], (uint32_t)(row * W + col), (row << 7) | (127 - col));
+        }
       }
     }
     __syncthreads();
@@ -209,13 +224,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     uint8_t flag = 0;
     if (min_err <= thr) {
       const uint32_t word = sm.win[((lane >> 3) + row) * UW + (lane & (kTileX - 1)) + col];
-      uint64_t blk = t.own_block;
-      if (word != t.own_word) {
-        uint32_t ep1, ep2;
-        refit_endpoints(t.pf, word, ep1, ep2);
-        blk = (uint64_t)pack565_rgbx(ep1) | ((uint64_t)pack565_rgbx(ep2) << 16) | ((uint64_t)word << 32);
-      }
-      v.final_blocks[(size_t)f * v.nb + tb] = blk;
+      v.final_blocks[(size_t)f * v.nb + tb] = lane_winning_block(t, word);
       v.motion[((size_t)f * v.nb + tb) * 2 + 0] = (uint8_t)(col | 0x80);   // x = (i - bx) + sa
       v.motion[((size_t)f * v.nb + tb) * 2 + 1] = (uint8_t)(row | 0x80);   // y = (j - by) + sa
       flag = 1;

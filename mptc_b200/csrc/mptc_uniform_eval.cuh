@@ -34,10 +34,34 @@ __device__ __forceinline__ float4 word_coefs(uint32_t word) {
   return make_float4(asq, bsq, ab, f);
 }
 
+// Per distinct word: everything that depends on the index word only.
+struct WordInfo {
+  float4 cf;      // asq, bsq, ab, f = 1/(asq*bsq - ab*ab)
+  uint32_t sel[4];  // per block row: PRMT selector, nibble i = 2-bit index of pixel 4*row + i
+};
+
+__device__ __forceinline__ WordInfo word_info(uint32_t word) {
+  WordInfo wi;
+  wi.cf = word_coefs(word);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    uint32_t x = (word >> (8 * r)) & 0xFFu;   // 4 x 2 bits -> 4 nibbles
+    x = (x | (x << 4)) & 0x0F0Fu;
+    x = (x | (x << 2)) & 0x3333u;
+    wi.sel[r] = x;
+  }
+  return wi;
+}
+
+// All 16 indices equal <=> the least-squares system is singular (exact determinant 0; for any
+// other word it is >= 1/9, so f <= 9 and every intermediate stays far inside int32).  Only
+// these four words can reach the x86 float->int overflow semantics of dxt_image.cpp:330-331.
+__device__ __forceinline__ bool word_is_degenerate(uint32_t word) { return (word ^ (word << 2)) < 4u; }
+
 // One lane's target block held in registers.
 struct LaneTarget {
-  float pf[48];       // [k*3 + ch]
-  uint32_t px[16];    // RGBX packed
+  float pf[48];       // pixels as float, [k*3 + ch]
+  uint32_t pl[12];    // planar bytes: pl[ch*4 + row] = channel ch of pixels 4*row .. 4*row+3
   uint64_t own_block;
   uint32_t own_word;
   int orig_err;
@@ -45,25 +69,48 @@ struct LaneTarget {
 
 __device__ __forceinline__ void load_lane_target(LaneTarget &t, const uint8_t *frame, int w, int bx, int by,
                                                  uint64_t own_block) {
-  load_block_rgbx(frame, w, bx, by, t.px);
+  uint32_t px[16];
+  load_block_rgbx(frame, w, bx, by, px);
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    t.pf[3 * k + 0] = __uint2float_rn(t.px[k] & 0xFF);
-    t.pf[3 * k + 1] = __uint2float_rn((t.px[k] >> 8) & 0xFF);
-    t.pf[3 * k + 2] = __uint2float_rn((t.px[k] >> 16) & 0xFF);
+    t.pf[3 * k + 0] = __uint2float_rn(px[k] & 0xFF);
+    t.pf[3 * k + 1] = __uint2float_rn((px[k] >> 8) & 0xFF);
+    t.pf[3 * k + 2] = __uint2float_rn((px[k] >> 16) & 0xFF);
   }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      t.pl[ch * 4 + r] = ((px[4 * r + 0] >> (8 * ch)) & 0xFFu) | (((px[4 * r + 1] >> (8 * ch)) & 0xFFu) << 8) |
+                         (((px[4 * r + 2] >> (8 * ch)) & 0xFFu) << 16) | (((px[4 * r + 3] >> (8 * ch)) & 0xFFu) << 24);
   t.own_block = own_block;
   t.own_word = (uint32_t)(own_block >> 32);
   uint32_t pal[4];
   palette_of_block(own_block, pal);
-  t.orig_err = block_error(t.px, pal, t.own_word);
+  t.orig_err = block_error(px, pal, t.own_word);
 }
 
 // floor(x / 3) for 0 <= x < 2^31 in one IMAD.HI
 __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0x55555556u); }
 
-// err_diff of (this lane's target, uniform `word`), or kRejected.  cf = word_coefs(word).
-__device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, float4 cf) {
+// Sum over the 16 pixels of (pixel - palette[index])^2 for one channel: plane = 4 words of
+// pixel bytes, palch = that channel of the 4 palette entries packed (entry v in byte v).
+__device__ __forceinline__ uint32_t plane_error(const uint32_t *plane, uint32_t palch, const uint32_t *sel, uint32_t sum) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint32_t c = __byte_perm(palch, 0u, sel[r]);
+    const uint32_t d = __vabsdiffu4(plane[r], c);
+    sum = __dp4a(d, d, sum);
+  }
+  return sum;
+}
+
+constexpr int kRejectedSmall = 65535;  // "rejected" marker that fits the packed winner keys
+
+// err_diff of (this lane's target, warp-uniform `word`), or kRejectedSmall.
+// lut5/lut6: 256-entry tables of ToFiveBits / ToSixBits (dxt_image.cpp:72-121) in shared memory.
+__device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, const WordInfo &wi,
+                                            const uint8_t *lut5, const uint8_t *lut6) {
   const float w23 = 2.0f / 3.0f, w13 = 1.0f / 3.0f;
   float ax0 = 0.f, ax1 = 0.f, ax2 = 0.f, bx0 = 0.f, bx1 = 0.f, bx2 = 0.f;
 #pragma unroll
@@ -84,38 +131,44 @@ __device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, 
       ax2 = __fadd_rn(ax2, __fmul_rn(p2, w13)); bx2 = __fadd_rn(bx2, __fmul_rn(p2, w23));
     }
   }
-  const float asq = cf.x, bsq = cf.y, ab = cf.z, f = cf.w;
-  int r1 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(ax0, bsq), __fmul_rn(bx0, ab))));
-  int r2 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(bx0, asq), __fmul_rn(ax0, ab))));
-  int g1 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(ax1, bsq), __fmul_rn(bx1, ab))));
-  int g2 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(bx1, asq), __fmul_rn(ax1, ab))));
-  int b1 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(ax2, bsq), __fmul_rn(bx2, ab))));
-  int b2 = quantise_endpoint(__fmul_rn(f, __fsub_rn(__fmul_rn(bx2, asq), __fmul_rn(ax2, ab))));
-  r1 = snap_bits<0xF8, 4, 5>(r1);  r2 = snap_bits<0xF8, 4, 5>(r2);
-  g1 = snap_bits<0xFC, 2, 6>(g1);  g2 = snap_bits<0xFC, 2, 6>(g2);
-  b1 = snap_bits<0xF8, 4, 5>(b1);  b2 = snap_bits<0xF8, 4, 5>(b2);
-  const uint32_t pk1 = ((uint32_t)(r1 & 0xF8) << 8) | ((uint32_t)(g1 & 0xFC) << 3) | ((uint32_t)b1 >> 3);
-  const uint32_t pk2 = ((uint32_t)(r2 & 0xF8) << 8) | ((uint32_t)(g2 & 0xFC) << 3) | ((uint32_t)b2 >> 3);
-  uint32_t pal[4];
-  pal[0] = (uint32_t)r1 | ((uint32_t)g1 << 8) | ((uint32_t)b1 << 16);
-  pal[1] = (uint32_t)r2 | ((uint32_t)g2 << 8) | ((uint32_t)b2 << 16);
-  pal[2] = div3(2u * r1 + r2) | (div3(2u * g1 + g2) << 8) | (div3(2u * b1 + b2) << 16);
-  pal[3] = div3(r1 + 2u * r2) | (div3(g1 + 2u * g2) << 8) | (div3(b1 + 2u * b2) << 16);
-  uint32_t sum = 0;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const uint32_t v = (word >> (2 * k)) & 3u;  // warp-uniform
-    uint32_t c;
-    if (v == 0u) c = pal[0];
-    else if (v == 1u) c = pal[1];
-    else if (v == 2u) c = pal[2];
-    else c = pal[3];
-    const uint32_t d = __vabsdiffu4(t.px[k], c);
-    sum = __dp4a(d, d, sum);
+  const float asq = wi.cf.x, bsq = wi.cf.y, ab = wi.cf.z, f = wi.cf.w;
+  const float q0 = __fmul_rn(f, __fsub_rn(__fmul_rn(ax0, bsq), __fmul_rn(bx0, ab)));
+  const float q1 = __fmul_rn(f, __fsub_rn(__fmul_rn(bx0, asq), __fmul_rn(ax0, ab)));
+  const float q2 = __fmul_rn(f, __fsub_rn(__fmul_rn(ax1, bsq), __fmul_rn(bx1, ab)));
+  const float q3 = __fmul_rn(f, __fsub_rn(__fmul_rn(bx1, asq), __fmul_rn(ax1, ab)));
+  const float q4 = __fmul_rn(f, __fsub_rn(__fmul_rn(ax2, bsq), __fmul_rn(bx2, ab)));
+  const float q5 = __fmul_rn(f, __fsub_rn(__fmul_rn(bx2, asq), __fmul_rn(ax2, ab)));
+  uint32_t r1, r2, g1, g2, b1, b2;
+  if (word_is_degenerate(word)) {  // warp-uniform, rare: exact cvttss2si emulation
+    r1 = (uint32_t)quantise_endpoint(q0); r2 = (uint32_t)quantise_endpoint(q1);
+    g1 = (uint32_t)quantise_endpoint(q2); g2 = (uint32_t)quantise_endpoint(q3);
+    b1 = (uint32_t)quantise_endpoint(q4); b2 = (uint32_t)quantise_endpoint(q5);
+  } else {  // finite and far inside int32: saturating F2I (negative -> 0) + min == cast + clamp
+    r1 = min(__float2uint_rz(__fadd_rn(q0, 0.5f)), 255u); r2 = min(__float2uint_rz(__fadd_rn(q1, 0.5f)), 255u);
+    g1 = min(__float2uint_rz(__fadd_rn(q2, 0.5f)), 255u); g2 = min(__float2uint_rz(__fadd_rn(q3, 0.5f)), 255u);
+    b1 = min(__float2uint_rz(__fadd_rn(q4, 0.5f)), 255u); b2 = min(__float2uint_rz(__fadd_rn(q5, 0.5f)), 255u);
   }
+  r1 = lut5[r1]; r2 = lut5[r2]; g1 = lut6[g1]; g2 = lut6[g2]; b1 = lut5[b1]; b2 = lut5[b2];
+  const uint32_t pk1 = ((r1 & 0xF8u) << 8) | ((g1 & 0xFCu) << 3) | (b1 >> 3);
+  const uint32_t pk2 = ((r2 & 0xF8u) << 8) | ((g2 & 0xFCu) << 3) | (b2 >> 3);
+  // palette per channel, entry v in byte v: ep1, ep2, (2*ep1+ep2)/3, (ep1+2*ep2)/3
+  const uint32_t palr = r1 | (r2 << 8) | (div3(2u * r1 + r2) << 16) | (div3(r1 + 2u * r2) << 24);
+  const uint32_t palg = g1 | (g2 << 8) | (div3(2u * g1 + g2) << 16) | (div3(g1 + 2u * g2) << 24);
+  const uint32_t palb = b1 | (b2 << 8) | (div3(2u * b1 + b2) << 16) | (div3(b1 + 2u * b2) << 24);
+  uint32_t sum = plane_error(t.pl + 0, palr, wi.sel, 0u);
+  sum = plane_error(t.pl + 4, palg, wi.sel, sum);
+  sum = plane_error(t.pl + 8, palb, wi.sel, sum);
   int e = (int)(sum / 48u) - t.orig_err;
-  e = (pk1 > pk2) ? e : kRejected;
+  e = (pk1 > pk2) ? e : kRejectedSmall;
   return (word == t.own_word) ? 0 : e;
+}
+
+// The block this lane's target emits when `word` (not necessarily uniform) wins.
+__device__ __forceinline__ uint64_t lane_winning_block(const LaneTarget &t, uint32_t word) {
+  if (word == t.own_word) return t.own_block;
+  uint32_t ep1, ep2;
+  refit_endpoints(t.pf, word, ep1, ep2);
+  return (uint64_t)pack565_rgbx(ep1) | ((uint64_t)pack565_rgbx(ep2) << 16) | ((uint64_t)word << 32);
 }
 
 }  // namespace mptc
