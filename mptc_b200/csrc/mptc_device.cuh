@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda/atomic>
 
 namespace mptc {
 
@@ -237,5 +238,56 @@ __device__ __forceinline__ int winner_resolve(const WinnerState &s, int W, int &
   row = col = 0;
   return 0x7fffffff;
 }
+
+// ------------------------------------------------------------------------------------------
+// Shared by K2/K3: build the per-target context in shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void build_target(TargetCtx &t, const uint8_t *frame, int w, int bx, int by,
+                                             uint64_t own_block) {
+  // called by one thread
+  uint32_t px[16];
+  load_block_rgbx(frame, w, bx, by, px);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    t.px[k] = px[k];
+    t.pf[3 * k + 0] = __uint2float_rn(px[k] & 0xFF);
+    t.pf[3 * k + 1] = __uint2float_rn((px[k] >> 8) & 0xFF);
+    t.pf[3 * k + 2] = __uint2float_rn((px[k] >> 16) & 0xFF);
+  }
+  t.own_block = own_block;
+  t.own_word = (uint32_t)(own_block >> 32);
+  uint32_t pal[4];
+  palette_of_block(own_block, pal);
+  t.orig_err = block_error(px, pal, t.own_word);
+}
+
+template <int NWARPS>
+__device__ __forceinline__ void winner_block_reduce(WinnerState &s, WinnerState *smem) {
+  winner_warp_reduce(s);
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    WinnerState o;
+    winner_init(o);
+    if (lane < NWARPS) o = smem[lane];
+    winner_warp_reduce(o);
+    if (lane == 0) smem[0] = o;
+  }
+  __syncthreads();
+  s = smem[0];
+}
+
+
+// device-scope acquire / release on the wavefront progress counters
+__device__ __forceinline__ int ld_acquire(const int *p) {
+  cuda::atomic_ref<int, cuda::thread_scope_device> r(*const_cast<int *>(p));
+  return r.load(cuda::memory_order_acquire);
+}
+__device__ __forceinline__ void st_release(int *p, int val) {
+  cuda::atomic_ref<int, cuda::thread_scope_device> r(*p);
+  r.store(val, cuda::memory_order_release);
+}
+
 
 }  // namespace mptc

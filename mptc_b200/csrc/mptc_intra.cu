@@ -1,0 +1,365 @@
+// mptc_intra.cu -- K3: intra search (DXTImage::IntraSearch + the winner apply of Reencode,
+// codec/dxt_image.cpp:652-713, :912-955) as a row-staggered wavefront over GROUPS of 32
+// consecutive blocks.
+//
+// Dependency: block (x, y) reads the FINAL index words of (x-sa..x-1, y) and of
+// (x-sa..x+sa-1, y-1..y-2sa+1).  One CTA walks one block row left to right, a group of 32
+// targets at a time (lane = target):
+//   1. wait until every row of the group's window has published enough final blocks;
+//   2. load the union window's words, plus the group's own initial words (what a block keeps
+//      when it turns out unique), and de-duplicate them in shared memory;
+//   3. evaluate every distinct word once per target (warp = word, lane = target);
+//   4. all warps scan the rows ABOVE for every target (those words are already final);
+//   5. one warp resolves the targets in order: only the <= sa positions to the LEFT in the same
+//      row depend on earlier decisions of this group, and their err_diff values are already in
+//      the table, because a block's final word is either a word of its window or its own
+//      initial word.  Each decision is a 16-position scan + a warp reduction.
+// The index word of every decided block is published immediately (the high half of the 8-byte
+// block); endpoints are refitted for the whole group afterwards (nobody waits on them).
+// progress[f][y] = number of leading blocks of row y whose index words are final; rows are
+// handed out in increasing order through a ticket, so a waiting CTA only ever depends on CTAs
+// that already hold a ticket: no deadlock for any grid size.
+#include "mptc_kernels.h"
+#include "mptc_uniform_eval.cuh"
+
+namespace mptc {
+
+namespace {
+
+constexpr int kG = 32;                        // targets per group
+constexpr int kThreads = 256, kWarps = kThreads / 32;
+constexpr int kMaxWords = 256;                // distinct words per group on the fast path
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr uint16_t kNone = 0xFFFFu;
+constexpr int kPublishEvery = 8;              // decisions between progress publications
+
+struct GroupSmem {
+  WordInfo *info;      // [kMaxWords]
+  int *err;            // [kMaxWords + 1][33]; last row = rejected for every target
+  uint8_t *lut5, *lut6;
+  uint32_t *keys;      // [HT + 1]
+  uint32_t *ulist;     // [NP + kG]
+  uint16_t *pos_uid;   // [R][UW]: row 0 = the group's own row, row r = r rows above
+  uint16_t *slot_uid;  // [HT + 1]
+};
+
+__host__ __device__ inline int pow2_at_least(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+__host__ __device__ inline size_t group_smem_bytes(int sa, int *np_out, int *ht_out) {
+  const int R = 2 * sa, UW = kG + 2 * sa - 1;
+  const int NP = R * UW;
+  const int HT = pow2_at_least(NP + kG + (NP + kG) / 4);
+  if (np_out) *np_out = NP;
+  if (ht_out) *ht_out = HT;
+  size_t b = 0;
+  b += (size_t)kMaxWords * sizeof(WordInfo);
+  b += (size_t)(kMaxWords + 1) * 33 * sizeof(int);
+  b += 512;
+  b += (size_t)(HT + 1) * 4;
+  b += (size_t)(NP + kG) * 4;
+  b += (size_t)NP * 2;
+  b += (size_t)(HT + 1) * 2;
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ uint16_t wordset_insert(uint32_t *keys, uint32_t hmask, int hshift, int HT, int *special,
+                                                   uint32_t word) {
+  if (word == kEmpty) {
+    *special = 1;
+    return (uint16_t)HT;
+  }
+  uint32_t h = (word * 0x9E3779B1u) >> hshift;
+  for (;;) {
+    const uint32_t old = atomicCAS(&keys[h], kEmpty, word);
+    if (old == kEmpty || old == word) break;
+    h = (h + 1u) & hmask;
+  }
+  return (uint16_t)h;
+}
+
+__device__ __forceinline__ uint32_t ldcg_word(const uint64_t *blocks, size_t idx) {
+  // index word = high half of the little-endian 8-byte block; L2 load (other CTAs write it)
+  return __ldcg(reinterpret_cast<const uint32_t *>(blocks) + 2 * idx + 1);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_item, s_count, s_special;
+  __shared__ WinnerState s_partial[kG];
+  __shared__ uint16_t s_own_uid[kG];
+  __shared__ int s_dec[kG];          // (row << 8) | col of the winner, -1 = unique
+  __shared__ TargetCtx s_t;          // slow path only
+  __shared__ WinnerState s_red[kWarps];
+
+  const int W = 2 * sa, R = 2 * sa, UW = kG + 2 * sa - 1;
+  int NP, HT;
+  group_smem_bytes(sa, &NP, &HT);
+  GroupSmem sm;
+  {
+    unsigned char *p = smem_raw;
+    sm.info = reinterpret_cast<WordInfo *>(p);  p += (size_t)kMaxWords * sizeof(WordInfo);
+    sm.err = reinterpret_cast<int *>(p);        p += (size_t)(kMaxWords + 1) * 33 * sizeof(int);
+    sm.lut5 = p; sm.lut6 = p + 256;             p += 512;
+    sm.keys = reinterpret_cast<uint32_t *>(p);  p += (size_t)(HT + 1) * 4;
+    sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)(NP + kG) * 4;
+    sm.pos_uid = reinterpret_cast<uint16_t *>(p); p += (size_t)NP * 2;
+    sm.slot_uid = reinterpret_cast<uint16_t *>(p);
+  }
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t hmask = (uint32_t)HT - 1u;
+  const int hshift = 33 - __ffs(HT);
+  const int n_items = n_gops * v.bh;
+
+  sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
+  sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
+  if (tid < 33) sm.err[kMaxWords * 33 + tid] = kRejectedSmall;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) return;
+    const int gop_i = item % n_gops, by = item / n_gops;
+    const int f = v.first + gop_i * v.gop + k_in_gop;
+    if (f >= v.first + v.count) continue;
+    const uint8_t *frame = v.rgb + v.frame_bytes * f;
+    uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
+    const uint64_t *init = v.init_blocks + (size_t)f * v.nb;
+    const uint8_t *flags = v.flags + (size_t)f * v.nb;
+    uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
+    int *progress = v.progress + (size_t)f * v.bh;
+
+    for (int x0 = 0; x0 < v.bw; x0 += kG) {
+      const int x_end = min(x0 + kG, v.bw);
+      // ---- which blocks of the group still need the intra search ----------------------------
+      const int gx = x0 + lane;
+      const bool in_row = gx < v.bw;
+      const bool todo = in_row && flags[(size_t)by * v.bw + gx] == 0;
+      const unsigned todo_mask = __ballot_sync(0xffffffffu, todo);   // identical in every warp
+      if (todo_mask == 0u) {
+        if (tid == 0) st_release(progress + by, x_end);
+        continue;
+      }
+
+      // ---- wait for the window rows; clear the word table meanwhile ---------------------------
+      if (wid == 0) {
+        const int need = min(x_end - 1 + sa, v.bw);
+        for (int base = 1; base < R; base += 32) {
+          const int r = base + lane;
+          bool ok = r >= R || by - r < 0;
+          while (!__all_sync(0xffffffffu, ok)) {
+            if (!ok) ok = ld_acquire(progress + by - r) >= need;
+            if (!ok) __nanosleep(40);
+          }
+        }
+      } else {
+        for (int s = tid - 32; s <= HT; s += kThreads - 32) sm.keys[s] = kEmpty;
+      }
+      if (tid == 0) { s_count = 0; s_special = 0; }
+      __syncthreads();
+
+      // ---- load the union window and insert its words -------------------------------------------
+      for (int p = tid; p < NP; p += kThreads) {
+        const int r = p / UW, uc = p - r * UW;
+        const int j = by - r, i = x0 - sa + uc;
+        uint16_t slot = kNone;
+        bool valid = i >= 0 && i < v.bw && j >= 0;
+        if (r == 0) valid = valid && (i < x0 || (i < x_end && flags[(size_t)by * v.bw + i] != 0));
+        if (valid) slot = wordset_insert(sm.keys, hmask, hshift, HT, &s_special, ldcg_word(cur, (size_t)j * v.bw + i));
+        sm.pos_uid[p] = slot;
+      }
+      LaneTarget t;
+      if (in_row) {
+        load_lane_target(t, frame, v.w, gx, by, init[(size_t)by * v.bw + gx]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
+        t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+      }
+      if (wid == 0)   // a unique block keeps its own initial word: later targets may reuse it
+        s_own_uid[lane] = todo ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, t.own_word) : kNone;
+      __syncthreads();
+
+      // ---- dense ids ------------------------------------------------------------------------------
+      for (int s = tid; s <= HT; s += kThreads) {
+        const bool occ = (s < HT) ? (sm.keys[s] != kEmpty) : (s_special != 0);
+        if (occ) {
+          const int uid = atomicAdd(&s_count, 1);
+          sm.slot_uid[s] = (uint16_t)uid;
+          sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;
+        }
+      }
+      __syncthreads();
+      const int U = s_count;
+
+      if (U > kMaxWords) {
+        // ---- slow path (little duplication, e.g. noise): one target at a time, every window
+        // position evaluated directly (the same code as the direct kernel) --------------------------
+        for (int g = 0; g < x_end - x0; ++g) {
+          if (!((todo_mask >> g) & 1u)) continue;
+          const int bx = x0 + g, b = by * v.bw + bx;
+          if (tid == 0) build_target(s_t, frame, v.w, bx, by, init[b]);
+          __syncthreads();
+          WinnerState s;
+          winner_init(s);
+          for (int p = tid; p < W * W; p += kThreads) {
+            const int row = p / W, col = p - row * W;
+            const int j = by - row, i = bx + sa - 1 - col;
+            if (i < 0 || j < 0 || i >= v.bw || (row == 0 && i >= bx)) continue;
+            winner_update(s, eval_candidate(s_t, ldcg_word(cur, (size_t)j * v.bw + i)), row, col, W);
+          }
+          winner_block_reduce<kWarps>(s, s_red);
+          if (tid == 0) {
+            int row, col;
+            const int min_err = winner_resolve(s, W, row, col);
+            if (min_err <= thr) {
+              cur[b] = winning_block(s_t, ldcg_word(cur, (size_t)(by - row) * v.bw + (bx + sa - 1 - col)));
+              motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);
+              motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);
+            } else {
+              motion[2 * b + 0] = 255;
+              motion[2 * b + 1] = 255;
+            }
+            __threadfence();
+            st_release(progress + by, bx + 1);
+          }
+          __syncthreads();
+        }
+        if (tid == 0) st_release(progress + by, x_end);
+        continue;
+      }
+
+      // ---- ids per position, per-word constants ------------------------------------------------------
+      for (int p = tid; p < NP; p += kThreads) {
+        const uint16_t slot = sm.pos_uid[p];
+        sm.pos_uid[p] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
+      }
+      if (tid < kG) {
+        const uint16_t slot = s_own_uid[tid];
+        s_own_uid[tid] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
+      }
+      for (int u = tid; u < U; u += kThreads) sm.info[u] = word_info(sm.ulist[u]);
+      __syncthreads();
+
+      // ---- evaluate: warp = one distinct word, lane = target ------------------------------------------
+      for (int u = wid; u < U; u += kWarps) {
+        const uint32_t word = sm.ulist[u];
+        const WordInfo wi = sm.info[u];
+        sm.err[u * 33 + lane] = eval_uniform(t, word, wi, sm.lut5, sm.lut6);
+      }
+      __syncthreads();
+
+      // ---- rows above: every target, all warps (scan order: j downwards, i downwards) ------------------
+      for (int g = wid; g < x_end - x0; g += kWarps) {
+        if (!((todo_mask >> g) & 1u)) continue;
+        WinnerState ws;
+        winner_init(ws);
+        const int *errg = sm.err + g;
+        const int rows = min(R - 1, by);
+        for (int row = 1; row <= rows; ++row) {
+          const uint16_t *urow = sm.pos_uid + row * UW + g + W - 1;   // uc = g + W - 1 - col
+          for (int col = lane; col < W; col += 32)
+            winner_update_fast(ws, errg[(int)urow[-col] * 33], (uint32_t)(row * W + col), (row << 7) | (127 - col));
+        }
+        winner_warp_reduce(ws);
+        if (lane == 0) s_partial[g] = ws;
+      }
+      __syncthreads();
+
+      // ---- the group's own row: in order, one warp -------------------------------------------------------
+      if (wid == 0) {
+        int since_publish = 0;
+        for (int g = 0; g < x_end - x0; ++g) {
+          if (!((todo_mask >> g) & 1u)) continue;
+          const int bx = x0 + g;
+          WinnerState ws;
+          winner_init(ws);
+          const int *errg = sm.err + g;
+          for (int l = lane; l < sa; l += 32) {          // position i = bx - 1 - l, scan column sa + l
+            if (bx - 1 - l < 0) continue;
+            const int u = sm.pos_uid[g + sa - 1 - l];      // row 0, uc = i - (x0 - sa)
+            winner_update_fast(ws, errg[u * 33], (uint32_t)(sa + l), 127 - (sa + l));
+          }
+          winner_warp_reduce(ws);
+          winner_merge(ws, s_partial[g]);
+          int row, col;
+          const int min_err = winner_resolve(ws, W, row, col);
+          uint16_t uid;
+          int dec;
+          if (min_err <= thr) {
+            uid = sm.pos_uid[row * UW + g + W - 1 - col];
+            dec = (row << 8) | col;
+          } else {
+            uid = s_own_uid[g];
+            dec = -1;
+          }
+          if (lane == 0) {
+            sm.pos_uid[sa + g] = uid;                        // row 0, this block's own position
+            s_dec[g] = dec;
+            reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + bx) + 1] = sm.ulist[uid];
+            if (++since_publish >= kPublishEvery && g + 1 < x_end - x0) {
+              since_publish = 0;
+              __threadfence();
+              st_release(progress + by, bx + 1);
+            }
+          }
+          __syncwarp();
+        }
+        // ---- endpoints + motion for the whole group, then the final publication ----------------------
+        if (todo) {
+          const int dec = s_dec[lane];
+          const size_t b = (size_t)by * v.bw + gx;
+          if (dec >= 0) {
+            const int row = dec >> 8, col = dec & 0xFF;
+            cur[b] = lane_winning_block(t, sm.ulist[sm.pos_uid[sa + lane]]);
+            motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);   // x = (i - bx) + sa
+            motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);   // y = (j - by) + 2sa - 1
+          } else {
+            motion[2 * b + 0] = 255;
+            motion[2 * b + 1] = 255;
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(progress + by, x_end);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
+                                  cudaStream_t s) {
+  static int max_optin = -1, max_ctas = 0;
+  static size_t configured = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (max_optin < 0) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t bytes = group_smem_bytes(sa, nullptr, nullptr);
+  if (bytes + 4096 > (size_t)max_optin) return false;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(k_intra_wavefront_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+      return false;
+    configured = bytes;
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intra_wavefront_tiled, kThreads, bytes);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    max_ctas = (per_sm < 1 ? 1 : per_sm) * sms;
+  }
+  const int items = n_gops * v.bh;
+  const int grid = items < max_ctas ? items : max_ctas;
+  k_intra_wavefront_tiled<<<grid, kThreads, bytes, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
+  return true;
+}
+
+}  // namespace mptc

@@ -11,7 +11,6 @@
 #include "mptc_kernels.h"
 #include "mptc_device.cuh"
 
-#include <cuda/atomic>
 
 namespace mptc {
 
@@ -209,45 +208,6 @@ __global__ void __launch_bounds__(128) k_dxt1_fit(const uint8_t *__restrict__ rg
 }
 
 // ------------------------------------------------------------------------------------------
-// Shared by K2/K3: build the per-target context in shared memory.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void build_target(TargetCtx &t, const uint8_t *frame, int w, int bx, int by,
-                                             uint64_t own_block) {
-  // called by one thread
-  uint32_t px[16];
-  load_block_rgbx(frame, w, bx, by, px);
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    t.px[k] = px[k];
-    t.pf[3 * k + 0] = __uint2float_rn(px[k] & 0xFF);
-    t.pf[3 * k + 1] = __uint2float_rn((px[k] >> 8) & 0xFF);
-    t.pf[3 * k + 2] = __uint2float_rn((px[k] >> 16) & 0xFF);
-  }
-  t.own_block = own_block;
-  t.own_word = (uint32_t)(own_block >> 32);
-  uint32_t pal[4];
-  palette_of_block(own_block, pal);
-  t.orig_err = block_error(px, pal, t.own_word);
-}
-
-template <int NWARPS>
-__device__ __forceinline__ void winner_block_reduce(WinnerState &s, WinnerState *smem) {
-  winner_warp_reduce(s);
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) smem[wid] = s;
-  __syncthreads();
-  if (wid == 0) {
-    WinnerState o;
-    winner_init(o);
-    if (lane < NWARPS) o = smem[lane];
-    winner_warp_reduce(o);
-    if (lane == 0) smem[0] = o;
-  }
-  __syncthreads();
-  s = smem[0];
-}
-
-// ------------------------------------------------------------------------------------------
 // K2: inter search.  One CTA per target block; threads stride over the (2sa)^2 window of the
 // previous frame's FINAL index words.
 // ------------------------------------------------------------------------------------------
@@ -303,15 +263,6 @@ k_inter_search(SeqView v, int k_in_gop, int sa, int thr) {
 // on already holds a ticket and is resident: no deadlock for any grid size.
 // Blocks with flags != 0 (found by the inter search) are already final and are skipped.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_acquire(const int *p) {
-  cuda::atomic_ref<int, cuda::thread_scope_device> r(*const_cast<int *>(p));
-  return r.load(cuda::memory_order_acquire);
-}
-__device__ __forceinline__ void st_release(int *p, int val) {
-  cuda::atomic_ref<int, cuda::thread_scope_device> r(*p);
-  r.store(val, cuda::memory_order_release);
-}
-
 __global__ void __launch_bounds__(kSearchThreads)
 k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__restrict__ ticket) {
   __shared__ TargetCtx t;
@@ -548,7 +499,8 @@ void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int
 
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                             int max_ctas, cudaStream_t s) {
-  int items = n_gops * v.bh;
+  if (launch_intra_wavefront_tiled(v, k_in_gop, n_gops, sa, thr, ticket, s)) return;
+  int items = n_gops * v.bh;  // direct (one target at a time) fallback for very large windows
   int grid = items < max_ctas ? items : max_ctas;
   k_intra_wavefront<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
 }

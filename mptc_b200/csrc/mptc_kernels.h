@@ -26,6 +26,7 @@ struct SeqView {
 cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
 void launch_dxt1_fit(const SeqView &v, cudaStream_t s);
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
+bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket, cudaStream_t s);
 bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                             int max_ctas, cudaStream_t s);
