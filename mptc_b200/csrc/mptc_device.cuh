@@ -200,6 +200,32 @@ __device__ __forceinline__ void winner_update_fast(WinnerState &s, int e, uint32
   s.lastneg = max(s.lastneg, key | ~(e >> 31));                   // -1 unless e < 0
 }
 
+// Scans rows [row_begin, row_end) of one target's W-wide window.  The word id of window
+// position (row, col) is pos[row * stride + cdir * col]; errcol[id * 33] is that word's err_diff
+// for this target.  Lanes stride over the flattened scan index (= row * W + col, the reference's
+// loop order), so there is no per-position division.  kRemap handles the multi-chunk case:
+// ids outside [c0, c0 + cn) read the all-rejected row `dummy`.
+template <bool kRemap>
+__device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos, int stride, int cdir,
+                                            const int *errcol, int W, int row_begin, int row_end, int lane,
+                                            int c0, int cn, int dummy) {
+  const int rstep = 32 / W, cstep = 32 - rstep * W;
+  int row = row_begin + lane / W, col = lane - (lane / W) * W;
+  const int end = row_end * W;
+#pragma unroll 4
+  for (int idx = row_begin * W + lane; idx < end; idx += 32) {
+    int u = pos[row * stride + cdir * col];
+    if (kRemap) {
+      u -= c0;
+      u = ((unsigned)u < (unsigned)cn) ? u : dummy;
+    }
+    winner_update_fast(ws, errcol[u * 33], (uint32_t)idx, (row << 7) | (127 - col));
+    col += cstep;
+    row += rstep;
+    if (col >= W) { col -= W; ++row; }
+  }
+}
+
 __device__ __forceinline__ void winner_merge(WinnerState &s, const WinnerState &o) {
   s.first = min(s.first, o.first);
   s.lastneg = max(s.lastneg, o.lastneg);

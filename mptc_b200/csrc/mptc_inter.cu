@@ -170,14 +170,13 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
 
   for (int c0 = 0; c0 < U; c0 += kChunk) {
     const int cn = min(kChunk, U - c0);
-    for (int u = tid; u < cn; u += kThreads) sm.info[u] = word_info(sm.ulist[c0 + u]);
+    for (int u = tid; u < cn; u += kThreads) word_info(sm.ulist[c0 + u], sm.info[u]);
     __syncthreads();
 
     // evaluate: warp = one distinct word, lane = target
     for (int u = wid; u < cn; u += kWarps) {
       const uint32_t word = sm.ulist[c0 + u];
-      const WordInfo wi = sm.info[u];
-      sm.err[u * 33 + lane] = eval_uniform(t, word, wi, sm.lut5, sm.lut6);
+      sm.err[u * 33 + lane] = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6);
     }
     __syncthreads();
 
@@ -190,18 +189,9 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
       const int tt = wid + q * kWarps;
       const int ttx = tt & (kTileX - 1), tty = tt >> 3;
       if (tx0 + ttx >= v.bw || ty0 + tty >= v.bh) continue;   // warp-uniform
-      const int *errt = sm.err + tt;
-      for (int row = 0; row < W; ++row) {
-        const uint16_t *urow = sm.pos_uid + (tty + row) * UW + ttx;
-        for (int col = lane; col < W; col += 32) {
-          int u = urow[col];
-          if (!single) {
-            u -= c0;
-            u = ((unsigned)u < (unsigned)cn) ? u : kChunk;
-          }
-          winner_update_fast(ws[q], errt[u * 33], (uint32_t)(row * W + col), (row << 7) | (127 - col));
-        }
-      }
+      const uint16_t *pos = sm.pos_uid + tty * UW + ttx;
+      if (single) scan_window<false>(ws[q], pos, UW, 1, sm.err + tt, W, 0, W, lane, 0, 0, kChunk);
+      else        scan_window<true>(ws[q], pos, UW, 1, sm.err + tt, W, 0, W, lane, c0, cn, kChunk);
     }
     __syncthreads();
   }

@@ -248,14 +248,13 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         const uint16_t slot = s_own_uid[tid];
         s_own_uid[tid] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
       }
-      for (int u = tid; u < U; u += kThreads) sm.info[u] = word_info(sm.ulist[u]);
+      for (int u = tid; u < U; u += kThreads) word_info(sm.ulist[u], sm.info[u]);
       __syncthreads();
 
       // ---- evaluate: warp = one distinct word, lane = target ------------------------------------------
       for (int u = wid; u < U; u += kWarps) {
         const uint32_t word = sm.ulist[u];
-        const WordInfo wi = sm.info[u];
-        sm.err[u * 33 + lane] = eval_uniform(t, word, wi, sm.lut5, sm.lut6);
+        sm.err[u * 33 + lane] = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6);
       }
       __syncthreads();
 
@@ -264,13 +263,8 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         if (!((todo_mask >> g) & 1u)) continue;
         WinnerState ws;
         winner_init(ws);
-        const int *errg = sm.err + g;
-        const int rows = min(R - 1, by);
-        for (int row = 1; row <= rows; ++row) {
-          const uint16_t *urow = sm.pos_uid + row * UW + g + W - 1;   // uc = g + W - 1 - col
-          for (int col = lane; col < W; col += 32)
-            winner_update_fast(ws, errg[(int)urow[-col] * 33], (uint32_t)(row * W + col), (row << 7) | (127 - col));
-        }
+        // uc = g + W - 1 - col: positions run right to left (scan order i downwards)
+        scan_window<false>(ws, sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, 1, min(R - 1, by) + 1, lane, 0, 0, kMaxWords);
         winner_warp_reduce(ws);
         if (lane == 0) s_partial[g] = ws;
       }

@@ -2,13 +2,11 @@
 //
 // The tiled search kernels evaluate one de-duplicated index word against 32 target blocks
 // at a time: lane = target (pixels live in that lane's registers), word = the same for the
-// whole warp.  Every branch on the word's 2-bit indices is therefore non-divergent, so the
-// ordered FP32 accumulation of RecalculateEndpoints (dxt_image.cpp:298-318) only issues the
-// operations the index actually needs:
-//   index 0 (a=1, b=0): ax += P          (P*1 is exact, bx + P*0 = bx exactly)
-//   index 1 (a=0, b=1): bx += P
-//   index 2 (a=2/3, b=1/3) / index 3 (a=1/3, b=2/3): separately rounded products, then adds
-// which is bit-identical to the reference's "always multiply, always add" loop.
+// whole warp.  Everything that depends on the word only (the per-pixel weights a, b, the
+// asq/bsq/ab/f terms, the index selectors for the error sum) is computed once per distinct word
+// into shared memory (WordInfo) and read back with broadcast loads; the ordered FP32
+// accumulation of RecalculateEndpoints (dxt_image.cpp:298-318) is then 2 FMUL + 1 packed FADD2
+// per pixel and channel, each operation individually rounded exactly like the reference.
 // NOTE: __fmul2_rn + __fadd2_rn must NOT be used for the products: ptxas (12.9) contracts
 // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (profiles/micro/f32x2_test.cu), which changes results.
 #pragma once
@@ -36,12 +34,13 @@ __device__ __forceinline__ float4 word_coefs(uint32_t word) {
 
 // Per distinct word: everything that depends on the index word only.
 struct WordInfo {
-  float4 cf;      // asq, bsq, ab, f = 1/(asq*bsq - ab*ab)
+  float4 cf;        // asq, bsq, ab, f = 1/(asq*bsq - ab*ab)
   uint32_t sel[4];  // per block row: PRMT selector, nibble i = 2-bit index of pixel 4*row + i
+  float2 w[16];     // per pixel: (a, b) = ((3-order)/3, order/3), idx_to_order = {0,3,1,2}
 };
 
-__device__ __forceinline__ WordInfo word_info(uint32_t word) {
-  WordInfo wi;
+__device__ __forceinline__ void word_info(uint32_t word, WordInfo &wi) {
+  const float w23 = 2.0f / 3.0f, w13 = 1.0f / 3.0f;
   wi.cf = word_coefs(word);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -50,7 +49,13 @@ __device__ __forceinline__ WordInfo word_info(uint32_t word) {
     x = (x | (x << 2)) & 0x3333u;
     wi.sel[r] = x;
   }
-  return wi;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const uint32_t v = (word >> (2 * k)) & 3u;
+    const float a = (v & 2u) ? ((v & 1u) ? w13 : w23) : ((v & 1u) ? 0.0f : 1.0f);
+    const float b = (v & 2u) ? ((v & 1u) ? w23 : w13) : ((v & 1u) ? 1.0f : 0.0f);
+    wi.w[k] = make_float2(a, b);
+  }
 }
 
 // All 16 indices equal <=> the least-squares system is singular (exact determinant 0; for any
@@ -111,26 +116,19 @@ constexpr int kRejectedSmall = 65535;  // "rejected" marker that fits the packed
 // lut5/lut6: 256-entry tables of ToFiveBits / ToSixBits (dxt_image.cpp:72-121) in shared memory.
 __device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, const WordInfo &wi,
                                             const uint8_t *lut5, const uint8_t *lut6) {
-  const float w23 = 2.0f / 3.0f, w13 = 1.0f / 3.0f;
-  float ax0 = 0.f, ax1 = 0.f, ax2 = 0.f, bx0 = 0.f, bx1 = 0.f, bx2 = 0.f;
+  // wi lives in shared memory: every read below is a warp-uniform (broadcast) load
+  // (ax_j, bx_j) accumulated as pairs: two individually rounded products, one packed add.
+  // (Scalar FMUL + FADD2 is not contracted by ptxas; FMUL2 + FADD2 would be.)
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const uint32_t v = (word >> (2 * k)) & 3u;  // warp-uniform
+    const float2 w = wi.w[k];   // warp-uniform broadcast load
     const float p0 = t.pf[3 * k + 0], p1 = t.pf[3 * k + 1], p2 = t.pf[3 * k + 2];
-    if (v == 0u) {
-      ax0 = __fadd_rn(ax0, p0); ax1 = __fadd_rn(ax1, p1); ax2 = __fadd_rn(ax2, p2);
-    } else if (v == 1u) {
-      bx0 = __fadd_rn(bx0, p0); bx1 = __fadd_rn(bx1, p1); bx2 = __fadd_rn(bx2, p2);
-    } else if (v == 2u) {
-      ax0 = __fadd_rn(ax0, __fmul_rn(p0, w23)); bx0 = __fadd_rn(bx0, __fmul_rn(p0, w13));
-      ax1 = __fadd_rn(ax1, __fmul_rn(p1, w23)); bx1 = __fadd_rn(bx1, __fmul_rn(p1, w13));
-      ax2 = __fadd_rn(ax2, __fmul_rn(p2, w23)); bx2 = __fadd_rn(bx2, __fmul_rn(p2, w13));
-    } else {
-      ax0 = __fadd_rn(ax0, __fmul_rn(p0, w13)); bx0 = __fadd_rn(bx0, __fmul_rn(p0, w23));
-      ax1 = __fadd_rn(ax1, __fmul_rn(p1, w13)); bx1 = __fadd_rn(bx1, __fmul_rn(p1, w23));
-      ax2 = __fadd_rn(ax2, __fmul_rn(p2, w13)); bx2 = __fadd_rn(bx2, __fmul_rn(p2, w23));
-    }
+    s0 = __fadd2_rn(s0, make_float2(__fmul_rn(p0, w.x), __fmul_rn(p0, w.y)));
+    s1 = __fadd2_rn(s1, make_float2(__fmul_rn(p1, w.x), __fmul_rn(p1, w.y)));
+    s2 = __fadd2_rn(s2, make_float2(__fmul_rn(p2, w.x), __fmul_rn(p2, w.y)));
   }
+  const float ax0 = s0.x, bx0 = s0.y, ax1 = s1.x, bx1 = s1.y, ax2 = s2.x, bx2 = s2.y;
   const float asq = wi.cf.x, bsq = wi.cf.y, ab = wi.cf.z, f = wi.cf.w;
   const float q0 = __fmul_rn(f, __fsub_rn(__fmul_rn(ax0, bsq), __fmul_rn(bx0, ab)));
   const float q1 = __fmul_rn(f, __fsub_rn(__fmul_rn(bx0, asq), __fmul_rn(ax0, ab)));
