@@ -193,37 +193,58 @@ __device__ __forceinline__ void winner_update(WinnerState &s, int e, int row, in
 }
 
 // Branch-free form for the tiled kernels.  e must be a real err_diff (|e| <= 65025) or 65535
-// for "rejected"; p = row*W + col; key = (row << 7) | (127 - col).
-__device__ __forceinline__ void winner_update_fast(WinnerState &s, int e, uint32_t p, int key) {
+// for "rejected".  Positions are encoded as p = (row << 7) | col (col < 128), which orders
+// exactly like the reference's row-major scan and needs no division to decode; the
+// "last row, first column" key of the strictly-negative rule is then p ^ 127.
+__device__ __forceinline__ void winner_update_fast(WinnerState &s, int e, uint32_t p) {
   s.best = min(s.best, (uint32_t)(e * 16384) + (p + (65536u << 14)));
   s.first = min(s.first, p | ((uint32_t)(-e) & 0x80000000u));   // sign(-e) set <=> e > 0
-  s.lastneg = max(s.lastneg, key | ~(e >> 31));                   // -1 unless e < 0
+  s.lastneg = max(s.lastneg, (int)(p ^ 127u) | ~(e >> 31));       // -1 unless e < 0
 }
 
 // Scans rows [row_begin, row_end) of one target's W-wide window.  The word id of window
 // position (row, col) is pos[row * stride + cdir * col]; errcol[id * 33] is that word's err_diff
-// for this target.  Lanes stride over the flattened scan index (= row * W + col, the reference's
-// loop order), so there is no per-position division.  kRemap handles the multi-chunk case:
-// ids outside [c0, c0 + cn) read the all-rejected row `dummy`.
+// for this target.  Lanes stride over the flattened scan order, so there is no per-position
+// division.  kRemap handles the multi-chunk case: ids outside [c0, c0 + cn) read the
+// all-rejected row `dummy`.
 template <bool kRemap>
 __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos, int stride, int cdir,
                                             const int *errcol, int W, int row_begin, int row_end, int lane,
                                             int c0, int cn, int dummy) {
   const int rstep = 32 / W, cstep = 32 - rstep * W;
   int row = row_begin + lane / W, col = lane - (lane / W) * W;
-  const int end = row_end * W;
 #pragma unroll 4
-  for (int idx = row_begin * W + lane; idx < end; idx += 32) {
+  for (; row < row_end;) {
     int u = pos[row * stride + cdir * col];
     if (kRemap) {
       u -= c0;
       u = ((unsigned)u < (unsigned)cn) ? u : dummy;
     }
-    winner_update_fast(ws, errcol[u * 33], (uint32_t)idx, (row << 7) | (127 - col));
+    winner_update_fast(ws, errcol[u * 33], (uint32_t)((row << 7) | col));
     col += cstep;
     row += rstep;
     if (col >= W) { col -= W; ++row; }
   }
+}
+
+// Decodes a WinnerState built with winner_update_fast.
+__device__ __forceinline__ int winner_resolve_fast(const WinnerState &s, int &row, int &col) {
+  if (s.first < 0x80000000u) {
+    row = (int)(s.first >> 7);
+    col = (int)(s.first & 127u);
+    if (s.lastneg >= 0 && (s.lastneg >> 7) > row) {
+      row = s.lastneg >> 7;
+      col = 127 - (s.lastneg & 127);
+    }
+    return 0;
+  }
+  if ((s.best >> 14) < 131071u) {
+    row = (int)((s.best >> 7) & 127u);
+    col = (int)(s.best & 127u);
+    return (int)(s.best >> 14) - 65536;
+  }
+  row = col = 0;
+  return 0x7fffffff;
 }
 
 __device__ __forceinline__ void winner_merge(WinnerState &s, const WinnerState &o) {

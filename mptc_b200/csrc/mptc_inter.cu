@@ -203,7 +203,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     if (lane == 0) {
       int row, col;
       const int tt = wid + q * kWarps;
-      s_res_err[tt] = winner_resolve(ws[q], W, row, col);
+      s_res_err[tt] = winner_resolve_fast(ws[q], row, col);
       s_res_pos[tt] = (row << 8) | col;
     }
   }

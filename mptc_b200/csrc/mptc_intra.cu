@@ -27,11 +27,12 @@ namespace mptc {
 namespace {
 
 constexpr int kG = 32;                        // targets per group
-constexpr int kThreads = 256, kWarps = kThreads / 32;
+constexpr int kThreads = 512, kWarps = kThreads / 32;
 constexpr int kMaxWords = 256;                // distinct words per group on the fast path
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint16_t kNone = 0xFFFFu;
 constexpr int kPublishEvery = 8;              // decisions between progress publications
+constexpr int kSparseTodo = 2;                // groups with this few targets take the direct path
 
 struct GroupSmem {
   WordInfo *info;      // [kMaxWords]
@@ -88,12 +89,11 @@ __device__ __forceinline__ uint32_t ldcg_word(const uint64_t *blocks, size_t idx
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_item, s_count, s_special;
   __shared__ WinnerState s_partial[kG];
-  __shared__ uint16_t s_own_uid[kG];
   __shared__ int s_dec[kG];          // (row << 8) | col of the winner, -1 = unique
   __shared__ TargetCtx s_t;          // slow path only
   __shared__ WinnerState s_red[kWarps];
@@ -117,8 +117,10 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
   const int hshift = 33 - __ffs(HT);
   const int n_items = n_gops * v.bh;
 
-  sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
-  sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
+  if (tid < 256) {
+    sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);
+    sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
+  }
   if (tid < 33) sm.err[kMaxWords * 33 + tid] = kRejectedSmall;
 
   for (;;) {
@@ -157,7 +159,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           bool ok = r >= R || by - r < 0;
           while (!__all_sync(0xffffffffu, ok)) {
             if (!ok) ok = ld_acquire(progress + by - r) >= need;
-            if (!ok) __nanosleep(40);
+            if (!ok) __nanosleep(32);
           }
         }
       } else {
@@ -166,45 +168,59 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       if (tid == 0) { s_count = 0; s_special = 0; }
       __syncthreads();
 
-      // ---- load the union window and insert its words -------------------------------------------
-      for (int p = tid; p < NP; p += kThreads) {
-        const int r = p / UW, uc = p - r * UW;
-        const int j = by - r, i = x0 - sa + uc;
-        uint16_t slot = kNone;
-        bool valid = i >= 0 && i < v.bw && j >= 0;
-        if (r == 0) valid = valid && (i < x0 || (i < x_end && flags[(size_t)by * v.bw + i] != 0));
-        if (valid) slot = wordset_insert(sm.keys, hmask, hshift, HT, &s_special, ldcg_word(cur, (size_t)j * v.bw + i));
-        sm.pos_uid[p] = slot;
-      }
+      // Few targets in the group (typical for the leftovers of an inter frame): evaluating every
+      // distinct word for 32 lanes would cost more than evaluating their windows directly.
+      const bool sparse = __popc(todo_mask) <= kSparseTodo;
+      int U = 0;
       LaneTarget t;
-      if (in_row) {
-        load_lane_target(t, frame, v.w, gx, by, init[(size_t)by * v.bw + gx]);
-      } else {
+      if (!sparse) {
+        // ---- load the union window (loads first, then the hash inserts) -------------------------
+        for (int p0 = 0; p0 < NP; p0 += 4 * kThreads) {
+          uint32_t wv[4];
+          bool ok[4];
 #pragma unroll
-        for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+          for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q * kThreads + tid;
+            const int r = p / UW, uc = p - r * UW;
+            const int j = by - r, i = x0 - sa + uc;
+            bool valid = p < NP && i >= 0 && i < v.bw && j >= 0;
+            if (r == 0) valid = valid && (i < x0 || (i < x_end && flags[(size_t)by * v.bw + i] != 0));
+            ok[q] = valid;
+            wv[q] = valid ? ldcg_word(cur, (size_t)j * v.bw + i) : 0u;
+          }
 #pragma unroll
-        for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
-        t.own_block = 0; t.own_word = 0; t.orig_err = 0;
-      }
-      if (wid == 0)   // a unique block keeps its own initial word: later targets may reuse it
-        s_own_uid[lane] = todo ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, t.own_word) : kNone;
-      __syncthreads();
-
-      // ---- dense ids ------------------------------------------------------------------------------
-      for (int s = tid; s <= HT; s += kThreads) {
-        const bool occ = (s < HT) ? (sm.keys[s] != kEmpty) : (s_special != 0);
-        if (occ) {
-          const int uid = atomicAdd(&s_count, 1);
-          sm.slot_uid[s] = (uint16_t)uid;
-          sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;
+          for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q * kThreads + tid;
+            if (p < NP) sm.pos_uid[p] = ok[q] ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, wv[q]) : kNone;
+          }
         }
-      }
-      __syncthreads();
-      const int U = s_count;
+        if (in_row) {
+          load_lane_target(t, frame, v.w, gx, by, init[(size_t)by * v.bw + gx]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
+          t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+        }
+        __syncthreads();
 
-      if (U > kMaxWords) {
-        // ---- slow path (little duplication, e.g. noise): one target at a time, every window
-        // position evaluated directly (the same code as the direct kernel) --------------------------
+        // ---- dense ids ----------------------------------------------------------------------------
+        for (int s = tid; s <= HT; s += kThreads) {
+          const bool occ = (s < HT) ? (sm.keys[s] != kEmpty) : (s_special != 0);
+          if (occ) {
+            const int uid = atomicAdd(&s_count, 1);
+            sm.slot_uid[s] = (uint16_t)uid;
+            sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;
+          }
+        }
+        __syncthreads();
+        U = s_count;
+      }
+
+      if (sparse || U + kG > kMaxWords) {
+        // ---- direct path: one target at a time, every window position evaluated (the same code
+        // as the direct kernel).  Also taken when the window has little duplication (noise). ------
         for (int g = 0; g < x_end - x0; ++g) {
           if (!((todo_mask >> g) & 1u)) continue;
           const int bx = x0 + g, b = by * v.bw + bx;
@@ -244,18 +260,12 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         const uint16_t slot = sm.pos_uid[p];
         sm.pos_uid[p] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
       }
-      if (tid < kG) {
-        const uint16_t slot = s_own_uid[tid];
-        s_own_uid[tid] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
-      }
       for (int u = tid; u < U; u += kThreads) word_info(sm.ulist[u], sm.info[u]);
       __syncthreads();
 
       // ---- evaluate: warp = one distinct word, lane = target ------------------------------------------
-      for (int u = wid; u < U; u += kWarps) {
-        const uint32_t word = sm.ulist[u];
-        sm.err[u * 33 + lane] = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6);
-      }
+      for (int u = wid; u < U; u += kWarps)
+        sm.err[u * 33 + lane] = eval_uniform(t, sm.ulist[u], sm.info[u], sm.lut5, sm.lut6);
       __syncthreads();
 
       // ---- rows above: every target, all warps (scan order: j downwards, i downwards) ------------------
@@ -263,7 +273,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         if (!((todo_mask >> g) & 1u)) continue;
         WinnerState ws;
         winner_init(ws);
-        // uc = g + W - 1 - col: positions run right to left (scan order i downwards)
+        // uc = g + W - 1 - col: positions run right to left
         scan_window<false>(ws, sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, 1, min(R - 1, by) + 1, lane, 0, 0, kMaxWords);
         winner_warp_reduce(ws);
         if (lane == 0) s_partial[g] = ws;
@@ -276,29 +286,53 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         for (int g = 0; g < x_end - x0; ++g) {
           if (!((todo_mask >> g) & 1u)) continue;
           const int bx = x0 + g;
+          // row 0: position i = bx - 1 - l sits at scan column sa + l
           WinnerState ws;
           winner_init(ws);
-          const int *errg = sm.err + g;
-          for (int l = lane; l < sa; l += 32) {          // position i = bx - 1 - l, scan column sa + l
-            if (bx - 1 - l < 0) continue;
-            const int u = sm.pos_uid[g + sa - 1 - l];      // row 0, uc = i - (x0 - sa)
-            winner_update_fast(ws, errg[u * 33], (uint32_t)(sa + l), 127 - (sa + l));
-          }
-          winner_warp_reduce(ws);
+          for (int l = lane; l < sa; l += 32)
+            if (bx - 1 - l >= 0)
+              winner_update_fast(ws, sm.err[(int)sm.pos_uid[g + sa - 1 - l] * 33 + g], (uint32_t)(sa + l));
+          ws.best = __reduce_min_sync(0xffffffffu, ws.best);
+          ws.first = __reduce_min_sync(0xffffffffu, ws.first);
+          ws.lastneg = __reduce_max_sync(0xffffffffu, ws.lastneg);
           winner_merge(ws, s_partial[g]);
           int row, col;
-          const int min_err = winner_resolve(ws, W, row, col);
-          uint16_t uid;
-          int dec;
+          const int min_err = winner_resolve_fast(ws, row, col);
+          int uid, dec;
           if (min_err <= thr) {
             uid = sm.pos_uid[row * UW + g + W - 1 - col];
             dec = (row << 8) | col;
           } else {
-            uid = s_own_uid[g];
+            // Unique: the block keeps its own initial word, which later targets of this group may
+            // reuse.  Rare, so it is only evaluated now: look it up / add it to the word table.
             dec = -1;
+            const uint32_t word = __shfl_sync(0xffffffffu, t.own_word, g);
+            int slot = -1;
+            if (word == kEmpty) {
+              slot = s_special ? HT : -1;
+            } else {
+              uint32_t h = (word * 0x9E3779B1u) >> hshift, kv;
+              while ((kv = sm.keys[h]) != kEmpty && kv != word) h = (h + 1u) & hmask;
+              __syncwarp();                            // every lane has read before lane 0 writes
+              if (kv != word && lane == 0) sm.keys[h] = word;
+              slot = (kv == word) ? (int)h : -(int)h - 2;   // negative: new entry at slot h
+            }
+            if (slot >= 0) {
+              uid = sm.slot_uid[slot];
+            } else {
+              uid = U++;
+              if (lane == 0) {
+                if (word == kEmpty) { s_special = 1; sm.slot_uid[HT] = (uint16_t)uid; }
+                else sm.slot_uid[-slot - 2] = (uint16_t)uid;
+                sm.ulist[uid] = word;
+                word_info(word, sm.info[uid]);
+              }
+              __syncwarp();
+              sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
+            }
           }
           if (lane == 0) {
-            sm.pos_uid[sa + g] = uid;                        // row 0, this block's own position
+            sm.pos_uid[sa + g] = (uint16_t)uid;            // row 0, this block's own position
             s_dec[g] = dec;
             reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + bx) + 1] = sm.ulist[uid];
             if (++since_publish >= kPublishEvery && g + 1 < x_end - x0) {
