@@ -1,0 +1,66 @@
+/* mptc_codec.h -- host side of the encoder above the GPU hot path: the sequential arithmetic
+ * coder and the stream assembly, C-ABI.  Exported by the same libmptc_b200.so.
+ *
+ * These replace, bit for bit, the reference's host code that consumes DXTImage results:
+ *   mptc_arith_encode      EntropyEncode(std::vector<uint8_t>&, ...)  codec/codec.cpp:186-197
+ *                          (entropy::Arithmetic_Codec + Adaptive_Data_Model(257),
+ *                           entropy/arithmetic_codec.cpp:360-387, :498-571, :749-829)
+ *   mptc_frame_payload     EntropyEncode(std::unique_ptr<DXTImage>&, ...) codec.cpp:1115-1158
+ *                          + the packaging half of CompressEndpoint      codec.cpp:841-899
+ *   mptc_encode_stream     CompressMultiUnique                           codec.cpp:1307-1532
+ *                          (frames come from memory instead of a PNG directory)
+ * All functions return 0 on success, negative MPTC_E_* codes otherwise (mptc_gpu.h).
+ */
+#ifndef MPTC_CODEC_H
+#define MPTC_CODEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mptc_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPTC_E_SPACE (-5) /* output buffer too small; *out_bytes holds the size needed */
+
+/* Adaptive arithmetic coding of n byte symbols with a fresh 257-symbol model. */
+int mptc_arith_encode(const uint8_t *sym, size_t n, uint8_t *out, size_t cap, size_t *out_bytes);
+
+/* One frame's payload: u32 n_unique, u32 motion bytes + stream, then four (u32 size, stream)
+ * records: ep1 Y, ep1 Co|Cg, ep2 Y, ep2 Co|Cg.  motion: 2*nb bytes; planes: 6 planes of
+ * plane_syms bytes each (plane_syms = pbw*pbh).  sizes[5] receives the compressed sizes
+ * (motion, Y1, C1, Y2, C2).  threads > 1 codes the five streams concurrently. */
+int mptc_frame_payload(const uint8_t *motion, size_t nb, const uint8_t *planes, size_t plane_syms,
+                       uint32_t n_unique, int threads, uint8_t *out, size_t cap, size_t *out_bytes,
+                       uint32_t *sizes);
+
+/* Stream header fields that CompressMultiUnique patches at offset 14 (codec.cpp:1514-1520). */
+typedef struct mptc_stream_stats {
+  uint32_t max_unique_bytes, max_comp_palette, max_comp_motion, max_comp_ep_y, max_comp_ep_c;
+  uint32_t n_groups;
+  double gpu_ms;      /* device time of the hot path (CUDA events) */
+  double entropy_ms;  /* wall time of arithmetic coding + assembly on `threads` host threads */
+} mptc_stream_stats;
+
+/* Whole-sequence encode to the reference's stream format: 34-byte
+ * header, then per group of p->gop frames: u32 palette size, palette stream, u32 unique bytes,
+ * frame payloads.  Uses intra_interval == unique_interval == p->gop.  Frames beyond the last
+ * full group are encoded but not written, exactly like the reference (codec.cpp:1477-1504).
+ * The GPU part runs on `ctx`; the arithmetic coder runs on `threads` host threads. */
+int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
+                       const mptc_gpu_params *p, int threads, uint8_t *out, size_t cap,
+                       size_t *out_bytes, mptc_stream_stats *stats);
+
+/* The same assembly from results already on the host (e.g. gathered from several GPUs):
+ * motion n*2*nb, unique n*nb u32 (frame f at unique + f*nb), n_unique n, planes n*6*plane_syms. */
+int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, const uint8_t *motion,
+                         const uint32_t *unique, const uint32_t *n_unique, const uint8_t *planes,
+                         int threads, uint8_t *out, size_t cap, size_t *out_bytes,
+                         mptc_stream_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPTC_CODEC_H */

@@ -231,3 +231,91 @@ class Context:
                                                      _ptr(out["n_unique"]), _ptr(out.get("planes"))))
         self.w, self.h, self.nb, self.pbw, self.pbh = w, h, nb, pbw, pbh
         return out
+
+
+# ---- host codec (include/mptc_codec.h) -----------------------------------------------------------
+CODEC_EXPORTS = ["mptc_arith_encode", "mptc_frame_payload", "mptc_encode_stream", "mptc_assemble_stream"]
+
+
+class StreamStats(C.Structure):
+    _fields_ = [("max_unique_bytes", C.c_uint32), ("max_comp_palette", C.c_uint32), ("max_comp_motion", C.c_uint32),
+                ("max_comp_ep_y", C.c_uint32), ("max_comp_ep_c", C.c_uint32), ("n_groups", C.c_uint32),
+                ("gpu_ms", C.c_double), ("entropy_ms", C.c_double)]
+
+
+def _codec():
+    L = load()
+    if not getattr(L, "_codec_ready", False):
+        vp, ci, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.mptc_arith_encode.argtypes = [vp, sz, vp, sz, C.POINTER(sz)]
+        L.mptc_frame_payload.argtypes = [vp, sz, vp, sz, C.c_uint32, ci, vp, sz, C.POINTER(sz), vp]
+        L.mptc_encode_stream.argtypes = [vp, vp, ci, ci, ci, C.POINTER(Params), ci, vp, sz, C.POINTER(sz),
+                                         C.POINTER(StreamStats)]
+        L.mptc_assemble_stream.argtypes = [ci, ci, ci, C.POINTER(Params), vp, vp, vp, vp, ci, vp, sz, C.POINTER(sz),
+                                           C.POINTER(StreamStats)]
+        L._codec_ready = True
+    return L
+
+
+def arith_encode(sym: np.ndarray) -> bytes:
+    sym = np.ascontiguousarray(sym, dtype=np.uint8)
+    cap = 2 * sym.size + 64
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t(0)
+    r = _codec().mptc_arith_encode(sym.ctypes.data, sym.size, out.ctypes.data, cap, C.byref(n))
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_arith_encode failed: {r}")
+    return out[: n.value].tobytes()
+
+
+def frame_payload(motion: np.ndarray, planes: np.ndarray, n_unique: int, threads: int = 1):
+    """-> (payload bytes, sizes[5])."""
+    motion = np.ascontiguousarray(motion, dtype=np.uint8)
+    planes = np.ascontiguousarray(planes, dtype=np.uint8)
+    nb = motion.size // 2
+    ps = planes.size // 6
+    cap = 2 * (motion.size + planes.size) + 1024
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t(0)
+    sizes = np.zeros(5, dtype=np.uint32)
+    r = _codec().mptc_frame_payload(motion.ctypes.data, nb, planes.ctypes.data, ps, n_unique, threads,
+                                    out.ctypes.data, cap, C.byref(n), sizes.ctypes.data)
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_frame_payload failed: {r}")
+    return out[: n.value].tobytes(), sizes
+
+
+def assemble_stream(w, h, search_area, err_threshold, gop, motion, unique, n_unique, planes, threads=1):
+    """Host-only stream assembly from per-frame results -> (bytes, StreamStats)."""
+    motion = np.ascontiguousarray(motion, dtype=np.uint8)
+    unique = np.ascontiguousarray(unique, dtype=np.uint32)
+    n_unique = np.ascontiguousarray(n_unique, dtype=np.uint32)
+    planes = np.ascontiguousarray(planes, dtype=np.uint8)
+    n = n_unique.size
+    cap = 2 * (motion.size + planes.size) + 4 * unique.size + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    nbytes = C.c_size_t(0)
+    st = StreamStats()
+    p = Params(search_area, err_threshold, gop)
+    r = _codec().mptc_assemble_stream(n, w, h, C.byref(p), motion.ctypes.data, unique.ctypes.data,
+                                      n_unique.ctypes.data, planes.ctypes.data, threads, out.ctypes.data, cap,
+                                      C.byref(nbytes), C.byref(st))
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_assemble_stream failed: {r}")
+    return out[: nbytes.value].tobytes(), st
+
+
+def encode_stream(ctx: "Context", frames: np.ndarray, search_area, err_threshold, gop, threads=1):
+    """GPU hot path + host arithmetic coding -> (stream bytes, StreamStats)."""
+    assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+    n, h, w = frames.shape[:3]
+    cap = frames.nbytes // 2 + (1 << 20)
+    out = np.empty(cap, dtype=np.uint8)
+    nbytes = C.c_size_t(0)
+    st = StreamStats()
+    p = Params(search_area, err_threshold, gop)
+    r = _codec().mptc_encode_stream(ctx._p, frames.ctypes.data, n, w, h, C.byref(p), threads, out.ctypes.data, cap,
+                                    C.byref(nbytes), C.byref(st))
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_encode_stream failed: {r}: {ctx._L.mptc_gpu_last_error(ctx._p).decode()}")
+    return out[: nbytes.value].tobytes(), st

@@ -1,0 +1,289 @@
+// mptc_host.cpp -- the host side above the GPU hot path: arithmetic coding and stream assembly
+// (include/mptc_codec.h).  The coder is inherently sequential per stream, so it stays on the
+// host (BASELINE.json north_star) and is parallelised ACROSS streams: every frame has five
+// independent streams and every group one palette stream (codec/codec.cpp:1115-1158, :1479).
+#include "../../include/mptc_codec.h"
+#include "mptc_host.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+namespace mptc {
+
+namespace {
+constexpr uint32_t kMinLength = 0x01000000u;   // renormalisation threshold (AC__MinLength)
+constexpr unsigned kLengthShift = 15;          // DM__LengthShift
+}  // namespace
+
+RangeEncoder::RangeEncoder(unsigned symbols) : n_(symbols), dist_(symbols), count_(symbols) {}
+
+// Adaptive_Data_Model::reset (arithmetic_codec.cpp:818-829)
+void RangeEncoder::reset_model() {
+  total_ = 0;
+  cycle_ = n_;
+  for (unsigned k = 0; k < n_; ++k) count_[k] = 1;
+  update_model();
+  until_ = cycle_ = (n_ + 6) >> 1;
+}
+
+// Adaptive_Data_Model::update, encoder flavour (arithmetic_codec.cpp:781-816)
+void RangeEncoder::update_model() {
+  if ((total_ += cycle_) > (1u << kLengthShift)) {
+    total_ = 0;
+    for (unsigned k = 0; k < n_; ++k) total_ += (count_[k] = (count_[k] + 1) >> 1);
+  }
+  const uint32_t scale = 0x80000000u / total_;
+  uint32_t sum = 0;
+  for (unsigned k = 0; k < n_; ++k) {
+    dist_[k] = (scale * sum) >> (31 - kLengthShift);
+    sum += count_[k];
+  }
+  cycle_ = (5 * cycle_) >> 2;
+  const uint32_t max_cycle = (n_ + 6) << 3;
+  if (cycle_ > max_cycle) cycle_ = max_cycle;
+  until_ = cycle_;
+}
+
+void RangeEncoder::encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out) {
+  reset_model();
+  const size_t start = out.size();
+  out.resize(start + 2 * n + 16);   // an adaptive-model symbol never costs more than 15 bits
+  uint8_t *const buf = out.data() + start;
+  uint8_t *p = buf;
+  uint32_t base = 0, length = 0xFFFFFFFFu;
+  const uint32_t last = n_ - 1;
+  auto carry = [&]() {                      // propagate_carry (:81-86)
+    uint8_t *q = p - 1;
+    while (*q == 0xFFu) *q-- = 0;
+    ++*q;
+  };
+  auto renorm = [&]() {                     // renorm_enc_interval (:90-96)
+    do {
+      *p++ = (uint8_t)(base >> 24);
+      base <<= 8;
+    } while ((length <<= 8) < kMinLength);
+  };
+  for (size_t i = 0; i < n; ++i) {          // Arithmetic_Codec::encode (:360-387)
+    const uint32_t s = sym[i], before = base;
+    uint32_t x;
+    if (s == last) {
+      x = dist_[s] * (length >> kLengthShift);
+      base += x;
+      length -= x;
+    } else {
+      length >>= kLengthShift;
+      x = dist_[s] * length;
+      base += x;
+      length = dist_[s + 1] * length - x;
+    }
+    if (before > base) carry();
+    if (length < kMinLength) renorm();
+    ++count_[s];
+    if (--until_ == 0) update_model();
+  }
+  const uint32_t before = base;             // stop_encoder (:547-571)
+  if (length > 2 * kMinLength) {
+    base += kMinLength;
+    length = kMinLength >> 1;
+  } else {
+    base += kMinLength >> 1;
+    length = kMinLength >> 9;
+  }
+  if (before > base) carry();
+  renorm();
+  out.resize(start + (size_t)(p - buf));
+}
+
+namespace {
+
+void put_u32(std::vector<uint8_t> &v, uint32_t x) {
+  const size_t o = v.size();
+  v.resize(o + 4);
+  memcpy(v.data() + o, &x, 4);
+}
+
+// Runs `n_tasks` independent tasks on up to `threads` host threads.
+template <typename F>
+void parallel_for(int n_tasks, int threads, F &&fn) {
+  if (threads < 1) threads = 1;
+  if (threads > n_tasks) threads = n_tasks;
+  if (threads <= 1) {
+    for (int i = 0; i < n_tasks; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&]() {
+      for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) fn(i);
+    });
+  for (auto &th : pool) th.join();
+}
+
+struct StreamJob {
+  const uint8_t *sym;
+  size_t n;
+  std::vector<uint8_t> out;
+};
+
+int copy_out(const std::vector<uint8_t> &bytes, uint8_t *out, size_t cap, size_t *out_bytes) {
+  if (out_bytes) *out_bytes = bytes.size();
+  if (bytes.size() > cap || !out) return MPTC_E_SPACE;
+  memcpy(out, bytes.data(), bytes.size());
+  return MPTC_OK;
+}
+
+// The five streams of a frame in the order EntropyEncode/CompressEndpoint emit them.
+void frame_jobs(const uint8_t *motion, size_t nb, const uint8_t *planes, size_t ps, StreamJob jobs[5]) {
+  jobs[0] = {motion, 2 * nb, {}};              // (x, y) interleaved (codec.cpp:1124-1127)
+  jobs[1] = {planes + 0 * ps, ps, {}};         // ep1 Y
+  jobs[2] = {planes + 1 * ps, 2 * ps, {}};     // ep1 Co | Cg (codec.cpp:843)
+  jobs[3] = {planes + 3 * ps, ps, {}};         // ep2 Y
+  jobs[4] = {planes + 4 * ps, 2 * ps, {}};     // ep2 Co | Cg (codec.cpp:873)
+}
+
+void append_frame_payload(std::vector<uint8_t> &out, uint32_t n_unique, StreamJob jobs[5]) {
+  put_u32(out, n_unique);                      // codec.cpp:1140-1142
+  for (int s = 0; s < 5; ++s) {
+    put_u32(out, (uint32_t)jobs[s].out.size());
+    out.insert(out.end(), jobs[s].out.begin(), jobs[s].out.end());
+  }
+}
+
+}  // namespace
+}  // namespace mptc
+
+using namespace mptc;
+
+extern "C" {
+
+int mptc_arith_encode(const uint8_t *sym, size_t n, uint8_t *out, size_t cap, size_t *out_bytes) {
+  if (!sym && n) return MPTC_E_ARG;
+  std::vector<uint8_t> bytes;
+  RangeEncoder enc;
+  enc.encode_all(sym, n, bytes);
+  return copy_out(bytes, out, cap, out_bytes);
+}
+
+int mptc_frame_payload(const uint8_t *motion, size_t nb, const uint8_t *planes, size_t plane_syms,
+                       uint32_t n_unique, int threads, uint8_t *out, size_t cap, size_t *out_bytes,
+                       uint32_t *sizes) {
+  if (!motion || !planes) return MPTC_E_ARG;
+  StreamJob jobs[5];
+  frame_jobs(motion, nb, planes, plane_syms, jobs);
+  parallel_for(5, threads, [&](int s) {
+    RangeEncoder enc;
+    enc.encode_all(jobs[s].sym, jobs[s].n, jobs[s].out);
+  });
+  std::vector<uint8_t> bytes;
+  append_frame_payload(bytes, n_unique, jobs);
+  if (sizes)
+    for (int s = 0; s < 5; ++s) sizes[s] = (uint32_t)jobs[s].out.size();
+  return copy_out(bytes, out, cap, out_bytes);
+}
+
+int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, const uint8_t *motion,
+                         const uint32_t *unique, const uint32_t *n_unique, const uint8_t *planes,
+                         int threads, uint8_t *out, size_t cap, size_t *out_bytes,
+                         mptc_stream_stats *stats) {
+  if (!p || !motion || !unique || !n_unique || !planes || n_frames < 1) return MPTC_E_ARG;
+  if (p->gop < 1 || p->gop > 255 || p->search_area < 1 || p->search_area > 63) return MPTC_E_ARG;
+  const auto t0 = std::chrono::steady_clock::now();
+  const size_t nb = (size_t)(w / 4) * (h / 4);
+  const size_t ps = (size_t)((w / 4 + 63) / 64 * 64) * ((h / 4 + 63) / 64 * 64);
+  const int n_groups = n_frames / p->gop;          // a trailing partial group is never written
+  const int n_used = n_groups * p->gop;
+
+  // every stream of every written frame + one palette stream per group, all independent
+  std::vector<StreamJob> jobs((size_t)n_used * 5 + n_groups);
+  std::vector<std::vector<uint8_t>> palettes(n_groups);
+  for (int f = 0; f < n_used; ++f)
+    frame_jobs(motion + (size_t)f * 2 * nb, nb, planes + (size_t)f * 6 * ps, ps, &jobs[(size_t)f * 5]);
+  for (int g = 0; g < n_groups; ++g) {             // combined palette (codec.cpp:1473-1479)
+    std::vector<uint8_t> &pal = palettes[g];
+    for (int f = g * p->gop; f < (g + 1) * p->gop; ++f) {
+      const uint8_t *src = reinterpret_cast<const uint8_t *>(unique + (size_t)f * nb);
+      pal.insert(pal.end(), src, src + (size_t)n_unique[f] * 4);
+    }
+    jobs[(size_t)n_used * 5 + g] = {pal.data(), pal.size(), {}};
+  }
+  parallel_for((int)jobs.size(), threads, [&](int i) {
+    RangeEncoder enc;
+    enc.encode_all(jobs[i].sym, jobs[i].n, jobs[i].out);
+  });
+
+  mptc_stream_stats st;
+  memset(&st, 0, sizeof st);
+  st.n_groups = (uint32_t)n_groups;
+  std::vector<uint8_t> bytes;
+  bytes.reserve(64 + (size_t)n_used * nb);
+  put_u32(bytes, (uint32_t)h);                     // header (codec.cpp:1358-1367)
+  put_u32(bytes, (uint32_t)w);
+  bytes.push_back((uint8_t)p->gop);
+  bytes.push_back((uint8_t)p->search_area);
+  put_u32(bytes, (uint32_t)n_groups);
+  const size_t patch_at = bytes.size();            // == 14
+  for (int k = 0; k < 5; ++k) put_u32(bytes, 0);
+  for (int g = 0; g < n_groups; ++g) {
+    const std::vector<uint8_t> &cpal = jobs[(size_t)n_used * 5 + g].out;
+    put_u32(bytes, (uint32_t)cpal.size());
+    bytes.insert(bytes.end(), cpal.begin(), cpal.end());
+    put_u32(bytes, (uint32_t)palettes[g].size());
+    if ((uint32_t)cpal.size() > st.max_comp_palette) st.max_comp_palette = (uint32_t)cpal.size();
+    if ((uint32_t)palettes[g].size() > st.max_unique_bytes) st.max_unique_bytes = (uint32_t)palettes[g].size();
+    for (int f = g * p->gop; f < (g + 1) * p->gop; ++f) {
+      StreamJob *fj = &jobs[(size_t)f * 5];
+      append_frame_payload(bytes, n_unique[f], fj);
+      const uint32_t m = (uint32_t)fj[0].out.size();
+      if (m > st.max_comp_motion) st.max_comp_motion = m;
+      for (int s : {1, 3}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_y) st.max_comp_ep_y = (uint32_t)fj[s].out.size();
+      for (int s : {2, 4}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_c) st.max_comp_ep_c = (uint32_t)fj[s].out.size();
+    }
+  }
+  const uint32_t patch[5] = {st.max_unique_bytes, st.max_comp_palette, st.max_comp_motion, st.max_comp_ep_y,
+                             st.max_comp_ep_c};   // codec.cpp:1514-1520
+  memcpy(bytes.data() + patch_at, patch, sizeof patch);
+  st.entropy_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (stats) {
+    const double gpu_ms = stats->gpu_ms;
+    *stats = st;
+    stats->gpu_ms = gpu_ms;
+  }
+  return copy_out(bytes, out, cap, out_bytes);
+}
+
+int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
+                       const mptc_gpu_params *p, int threads, uint8_t *out, size_t cap,
+                       size_t *out_bytes, mptc_stream_stats *stats) {
+  if (!ctx || !frames || !p || n_frames < 1) return MPTC_E_ARG;
+  if (w < 4 || h < 4 || (w & 3) || (h & 3)) return MPTC_E_ARG;
+  const size_t nb = (size_t)(w / 4) * (h / 4);
+  const size_t ps = (size_t)((w / 4 + 63) / 64 * 64) * ((h / 4 + 63) / 64 * 64);
+  const size_t n = (size_t)n_frames;
+  // pinned staging for the results (freed on every exit path below)
+  uint64_t *blocks = static_cast<uint64_t *>(mptc_gpu_host_alloc(n * nb * 8));
+  uint8_t *motion = static_cast<uint8_t *>(mptc_gpu_host_alloc(n * nb * 2));
+  uint32_t *unique = static_cast<uint32_t *>(mptc_gpu_host_alloc(n * nb * 4));
+  uint32_t *n_unique = static_cast<uint32_t *>(mptc_gpu_host_alloc(n * 4));
+  uint8_t *planes = static_cast<uint8_t *>(mptc_gpu_host_alloc(n * 6 * ps));
+  int r = MPTC_E_NOMEM;
+  if (blocks && motion && unique && n_unique && planes) {
+    r = mptc_gpu_encode_sequence(ctx, frames, n_frames, w, h, p, blocks, motion, unique, n_unique, planes);
+    if (r == MPTC_OK) {
+      mptc_stream_stats st;
+      memset(&st, 0, sizeof st);
+      float ms = 0.f;
+      if (mptc_gpu_last_encode_ms(ctx, 0, &ms) == MPTC_OK) st.gpu_ms = ms;
+      r = mptc_assemble_stream(n_frames, w, h, p, motion, unique, n_unique, planes, threads, out, cap, out_bytes, &st);
+      if (stats) *stats = st;
+    }
+  }
+  mptc_gpu_host_free(blocks); mptc_gpu_host_free(motion); mptc_gpu_host_free(unique);
+  mptc_gpu_host_free(n_unique); mptc_gpu_host_free(planes);
+  return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+// mptc_host.h -- host-side codec pieces (arithmetic coder, stream assembly).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace mptc {
+
+// Adaptive multi-symbol model + 32-bit range coder, bit-compatible with the reference's
+// entropy::Adaptive_Data_Model / entropy::Arithmetic_Codec (entropy/arithmetic_codec.cpp).
+class RangeEncoder {
+ public:
+  explicit RangeEncoder(unsigned symbols = 257);
+  // Appends the code bytes of `sym[0..n)` (fresh model, start .. stop) to `out`.
+  void encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out);
+
+ private:
+  void reset_model();
+  void update_model();
+  unsigned n_;
+  std::vector<uint32_t> dist_, count_;
+  uint32_t total_ = 0, cycle_ = 0, until_ = 0;
+};
+
+}  // namespace mptc

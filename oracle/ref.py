@@ -41,6 +41,7 @@ def lib():
         L.mptc_ref_arith_encode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.mptc_ref_compress_multi_unique.argtypes = [C.c_char_p, C.c_char_p, C.c_uint, C.c_int, C.c_uint, C.c_uint]
         L.mptc_ref_selfcheck_png.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.mptc_ref_write_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
         L.mptc_ref_quiet()
         _lib = L
     return _lib
@@ -138,3 +139,9 @@ def encode_sequence(frames: np.ndarray, search_area: int, err_threshold: int, go
         out.append(fr)
         prev = fr
     return out
+
+
+def write_png(path: str, rgb: np.ndarray):
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    if lib().mptc_ref_write_png(path.encode(), rgb.shape[1], rgb.shape[0], rgb.ctypes.data) != 0:
+        raise RuntimeError("stbi_write_png failed")

@@ -227,4 +227,10 @@ int mptc_ref_selfcheck_png(int w, int h, const uint8_t *rgb) {
   return bad;
 }
 
+// Writes a frame as PNG with the reference's bundled stb_image_write (for building the PNG
+// directory that CompressMultiUnique reads).
+int mptc_ref_write_png(const char *path, int w, int h, const uint8_t *rgb) {
+  return stbi_write_png(path, w, h, 3, rgb, 3 * w) ? 0 : -1;
+}
+
 }  // extern "C"

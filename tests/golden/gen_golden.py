@@ -59,6 +59,24 @@ def run_case(w, h, n, seed, sa, thr, gop, store):
     return out
 
 
+def reference_stream(frames, sa, thr, gop):
+    """Runs the reference's own CompressMultiUnique (codec.cpp:1307) on a PNG directory in a
+    fresh process (its max_* header fields are process-global, codec.cpp:73-77)."""
+    import subprocess
+    import tempfile
+    from PIL import Image
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "in"))
+        for i, fr in enumerate(frames):
+            Image.fromarray(fr, "RGB").save(os.path.join(d, "in", f"{i:05d}.png"))
+        out = os.path.join(d, "out.mptc")
+        code = ("import sys; sys.path.insert(0, %r); from oracle import ref; "
+                "ref.lib().mptc_ref_compress_multi_unique(%r.encode(), %r.encode(), %d, %d, %d, %d)"
+                % (ROOT, os.path.join(d, "in"), out, sa, thr, gop, gop))
+        subprocess.check_call([sys.executable, "-c", code], cwd=d, stdout=subprocess.DEVNULL)
+        return open(out, "rb").read()
+
+
 def main():
     assert ref.available(), "build oracle/_ref first: make -C oracle ref"
     assert ref.selfcheck_png(make_sequence(64, 64, 1)[0]) == 0
@@ -81,6 +99,12 @@ def main():
         out["enc_" + k] = np.frombuffer(ref.arith_encode(s), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, "arith.npz"), **out)
     print("wrote arith")
+    # whole-stream fixture: 256x256 x 4 frames, sa 4, thr 50, gop 2 (two groups)
+    frames = make_sequence(256, 256, 4, seed=77)
+    stream = reference_stream(frames, 4, 50, 2)
+    np.savez_compressed(os.path.join(HERE, "stream_256x256_sa4_gop2.npz"), params=np.array([256, 256, 4, 77, 4, 50, 2]),
+                        frames_sha=np.array(sha(frames)), stream=np.frombuffer(stream, dtype=np.uint8))
+    print("wrote stream", len(stream), "bytes")
 
 
 if __name__ == "__main__":
