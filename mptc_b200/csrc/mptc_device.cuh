@@ -211,9 +211,24 @@ template <bool kRemap>
 __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos, int stride, int cdir,
                                             const int *errcol, int W, int row_begin, int row_end, int lane,
                                             int c0, int cn, int dummy) {
+  if (W == 32) {
+    // default search area (16): one window row per step, lane = column
+    const uint16_t *q = pos + row_begin * stride + cdir * lane;
+    uint32_t p = (uint32_t)((row_begin << 7) | lane);
+#pragma unroll 4
+    for (int row = row_begin; row < row_end; ++row, q += stride, p += 128u) {
+      int u = *q;
+      if (kRemap) {
+        u -= c0;
+        u = ((unsigned)u < (unsigned)cn) ? u : dummy;
+      }
+      winner_update_fast(ws, errcol[u * 33], p);
+    }
+    return;
+  }
   const int rstep = 32 / W, cstep = 32 - rstep * W;
   int row = row_begin + lane / W, col = lane - (lane / W) * W;
-#pragma unroll 4
+#pragma unroll 2
   for (; row < row_end;) {
     int u = pos[row * stride + cdir * col];
     if (kRemap) {
