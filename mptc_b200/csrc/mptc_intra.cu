@@ -87,6 +87,15 @@ __device__ __forceinline__ uint32_t ldcg_word(const uint64_t *blocks, size_t idx
   return __ldcg(reinterpret_cast<const uint32_t *>(blocks) + 2 * idx + 1);
 }
 
+#ifdef MPTC_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_MARK(i) do { if (tid == 0) { long long now_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+#define PHASE_DECL long long t_mark_ = clock64()
+#else
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_DECL do { } while (0)
+#endif
+
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -94,7 +103,6 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_item, s_count, s_special;
   __shared__ WinnerState s_partial[kG];
-  __shared__ int s_dec[kG];          // (row << 8) | col of the winner, -1 = unique
   __shared__ TargetCtx s_t;          // slow path only
   __shared__ WinnerState s_red[kWarps];
 
@@ -139,8 +147,10 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
     int *progress = v.progress + (size_t)f * v.bh;
 
+    PHASE_DECL;
     for (int x0 = 0; x0 < v.bw; x0 += kG) {
       const int x_end = min(x0 + kG, v.bw);
+      PHASE_MARK(0);
       // ---- which blocks of the group still need the intra search ----------------------------
       const int gx = x0 + lane;
       const bool in_row = gx < v.bw;
@@ -167,6 +177,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       }
       if (tid == 0) { s_count = 0; s_special = 0; }
       __syncthreads();
+      PHASE_MARK(1);   // wait for rows above
 
       // Few targets in the group (typical for the leftovers of an inter frame): evaluating every
       // distinct word for 32 lanes would cost more than evaluating their windows directly.
@@ -216,6 +227,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         }
         __syncthreads();
         U = s_count;
+        PHASE_MARK(2);   // window load + hash + ids
       }
 
       if (sparse || U + kG > kMaxWords) {
@@ -262,52 +274,66 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       }
       for (int u = tid; u < U; u += kThreads) word_info(sm.ulist[u], sm.info[u]);
       __syncthreads();
+      PHASE_MARK(3);   // remap + word info
 
       // ---- evaluate: warp = one distinct word, lane = target ------------------------------------------
       for (int u = wid; u < U; u += kWarps)
         sm.err[u * 33 + lane] = eval_uniform(t, sm.ulist[u], sm.info[u], sm.lut5, sm.lut6);
       __syncthreads();
+      PHASE_MARK(4);   // evaluate
+#ifdef MPTC_PHASE_TIMING
+      if (tid == 0) { atomicAdd(&g_phase_cycles[10], (unsigned long long)U); atomicAdd(&g_phase_cycles[11], 1ull); }
+#endif
 
-      // ---- rows above: every target, all warps (scan order: j downwards, i downwards) ------------------
+      // ---- everything that is already final: the rows above and the part of the own row that
+      // lies left of the group.  Every target, all warps (scan order: j downwards, i downwards). ----
       for (int g = wid; g < x_end - x0; g += kWarps) {
         if (!((todo_mask >> g) & 1u)) continue;
         WinnerState ws;
         winner_init(ws);
         // uc = g + W - 1 - col: positions run right to left
         scan_window<false>(ws, sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, 1, min(R - 1, by) + 1, lane, 0, 0, kMaxWords);
+        for (int l = lane; l < sa; l += 32)      // own row: position i = x0 + g - 1 - l, scan column sa + l
+          if (l >= g && x0 + g - 1 - l >= 0)
+            winner_update_fast(ws, sm.err[(int)sm.pos_uid[g + sa - 1 - l] * 33 + g], (uint32_t)(sa + l));
         winner_warp_reduce(ws);
         if (lane == 0) s_partial[g] = ws;
       }
       __syncthreads();
+      PHASE_MARK(5);   // rows above
 
-      // ---- the group's own row: in order, one warp -------------------------------------------------------
+      // ---- the group's own row, in order, by one warp.  Lane l owns target l and keeps its
+      // WinnerState in registers; when block g is final, its word is PUSHED to the <= sa targets
+      // to its right (one table read + update per lane), so a decision costs one resolve by a
+      // single lane and one shuffle instead of a warp-wide scan + reduction. ----------------------------
       if (wid == 0) {
+        constexpr int kNeedOwn = 0x7fff0000;
+        const int n = x_end - x0;
+        WinnerState ws;
+        winner_init(ws);
+        if (todo) ws = s_partial[lane];
+        int my_uid = (in_row && !todo) ? (int)sm.pos_uid[sa + lane] : 0;   // already-final blocks of the group
+        int my_dec = -2;
         int since_publish = 0;
-        for (int g = 0; g < x_end - x0; ++g) {
-          if (!((todo_mask >> g) & 1u)) continue;
-          const int bx = x0 + g;
-          // row 0: position i = bx - 1 - l sits at scan column sa + l
-          WinnerState ws;
-          winner_init(ws);
-          for (int l = lane; l < sa; l += 32)
-            if (bx - 1 - l >= 0)
-              winner_update_fast(ws, sm.err[(int)sm.pos_uid[g + sa - 1 - l] * 33 + g], (uint32_t)(sa + l));
-          ws.best = __reduce_min_sync(0xffffffffu, ws.best);
-          ws.first = __reduce_min_sync(0xffffffffu, ws.first);
-          ws.lastneg = __reduce_max_sync(0xffffffffu, ws.lastneg);
-          winner_merge(ws, s_partial[g]);
-          int row, col;
-          const int min_err = winner_resolve_fast(ws, row, col);
-          int uid, dec;
-          if (min_err <= thr) {
-            uid = sm.pos_uid[row * UW + g + W - 1 - col];
-            dec = (row << 8) | col;
-          } else {
-            // Unique: the block keeps its own initial word, which later targets of this group may
-            // reuse.  Rare, so it is only evaluated now: look it up / add it to the word table.
-            dec = -1;
+        for (int g = 0; g < n; ++g) {
+          const bool is_todo = (todo_mask >> g) & 1u;
+          if (is_todo && lane == g) {
+            int row, col;
+            const int min_err = winner_resolve_fast(ws, row, col);
+            if (min_err <= thr) {
+              my_uid = sm.pos_uid[row * UW + lane + W - 1 - col];
+              my_dec = (row << 8) | col;
+            } else {
+              my_uid = kNeedOwn;   // unique: the block keeps its own initial word
+              my_dec = -1;
+            }
+          }
+          int uid = __shfl_sync(0xffffffffu, my_uid, g);
+          if (uid == kNeedOwn) {
+            // Rare, so the own word is only looked up / added to the word table (and evaluated for
+            // the 32 targets) now.  Warp-uniform branch.
             const uint32_t word = __shfl_sync(0xffffffffu, t.own_word, g);
-            int slot = -1;
+            int slot;
             if (word == kEmpty) {
               slot = s_special ? HT : -1;
             } else {
@@ -330,26 +356,28 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
               __syncwarp();
               sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
             }
+            if (lane == g) my_uid = uid;
           }
-          if (lane == 0) {
-            sm.pos_uid[sa + g] = (uint16_t)uid;            // row 0, this block's own position
-            s_dec[g] = dec;
-            reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + bx) + 1] = sm.ulist[uid];
-            if (++since_publish >= kPublishEvery && g + 1 < x_end - x0) {
-              since_publish = 0;
-              __threadfence();
-              st_release(progress + by, bx + 1);
-            }
+          if (is_todo && lane == g) {
+            sm.pos_uid[sa + g] = (uint16_t)uid;              // own row, this block's position
+            reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + x0 + g) + 1] = sm.ulist[uid];
           }
           __syncwarp();
+          const int d = lane - g;                            // push to the targets on the right
+          if (d >= 1 && d <= sa && todo) winner_update_fast(ws, sm.err[uid * 33 + lane], (uint32_t)(sa + d - 1));
+          if (is_todo && ++since_publish >= kPublishEvery && g + 1 < n) {
+            since_publish = 0;
+            if (lane == 0) st_release(progress + by, x0 + g + 1);   // release is cumulative over the warp's
+          }                                                          // stores ordered by __syncwarp above
         }
-        // ---- endpoints + motion for the whole group, then the final publication ----------------------
+        __syncwarp();
+        if (lane == 0) st_release(progress + by, x_end);     // index words are final: dependants may go on
+        // ---- endpoints + motion for the whole group (nobody waits on these inside the kernel) ------
         if (todo) {
-          const int dec = s_dec[lane];
           const size_t b = (size_t)by * v.bw + gx;
-          if (dec >= 0) {
-            const int row = dec >> 8, col = dec & 0xFF;
-            cur[b] = lane_winning_block(t, sm.ulist[sm.pos_uid[sa + lane]]);
+          if (my_dec >= 0) {
+            const int row = my_dec >> 8, col = my_dec & 0xFF;
+            cur[b] = lane_winning_block(t, sm.ulist[my_uid]);
             motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);   // x = (i - bx) + sa
             motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);   // y = (j - by) + 2sa - 1
           } else {
@@ -357,14 +385,20 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             motion[2 * b + 1] = 255;
           }
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release(progress + by, x_end);
       }
       __syncthreads();
+      PHASE_MARK(6);   // in-row resolve + write
     }
   }
 }
+
+#ifdef MPTC_PHASE_TIMING
+extern "C" void mptc_debug_phase_cycles(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z); }
+}
+#endif
 
 bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                                   cudaStream_t s) {
