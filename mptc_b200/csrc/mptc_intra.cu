@@ -101,7 +101,7 @@ __device__ unsigned long long g_phase_cycles[16];
 __global__ void __launch_bounds__(kThreads, 1)
 k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_item, s_count, s_special;
+  __shared__ int s_item, s_count, s_special, s_done;
   __shared__ WinnerState s_partial[kG];
   __shared__ TargetCtx s_t;          // slow path only
   __shared__ WinnerState s_red[kWarps];
@@ -175,7 +175,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       } else {
         for (int s = tid - 32; s <= HT; s += kThreads - 32) sm.keys[s] = kEmpty;
       }
-      if (tid == 0) { s_count = 0; s_special = 0; }
+      if (tid == 0) { s_count = 0; s_special = 0; s_done = 0; }
       __syncthreads();
       PHASE_MARK(1);   // wait for rows above
 
@@ -302,40 +302,44 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       __syncthreads();
       PHASE_MARK(5);   // rows above
 
-      // ---- the group's own row, in order, by one warp.  Lane l owns target l and keeps its
-      // WinnerState in registers; when block g is final, its word is PUSHED to the <= sa targets
-      // to its right (one table read + update per lane), so a decision costs one resolve by a
-      // single lane and one shuffle instead of a warp-wide scan + reduction. ----------------------------
+      // ---- the group's own row, in order, by one warp.  Lane l owns target l: its WinnerState and
+      // its current candidate decision live in registers.  When block g is final its word is
+      // PUSHED to the <= sa targets on its right (one table read + update per lane) and every lane
+      // re-resolves its candidate, so step g only costs: shuffle lane g's candidate -> table read
+      // -> update -> resolve.  Warp 1 publishes the progress counter (the device-scope fence is
+      // off the critical path). ---------------------------------------------------------------------
       if (wid == 0) {
         constexpr int kNeedOwn = 0x7fff0000;
         const int n = x_end - x0;
         WinnerState ws;
         winner_init(ws);
         if (todo) ws = s_partial[lane];
-        int my_uid = (in_row && !todo) ? (int)sm.pos_uid[sa + lane] : 0;   // already-final blocks of the group
-        int my_dec = -2;
-        int since_publish = 0;
-        for (int g = 0; g < n; ++g) {
-          const bool is_todo = (todo_mask >> g) & 1u;
-          if (is_todo && lane == g) {
-            int row, col;
-            const int min_err = winner_resolve_fast(ws, row, col);
-            if (min_err <= thr) {
-              my_uid = sm.pos_uid[row * UW + lane + W - 1 - col];
-              my_dec = (row << 8) | col;
-            } else {
-              my_uid = kNeedOwn;   // unique: the block keeps its own initial word
-              my_dec = -1;
-            }
+        int cand_uid = (in_row && !todo) ? (int)sm.pos_uid[sa + lane] : 0;   // already-final blocks
+        int cand_dec = -2;
+        auto resolve = [&]() {
+          int row, col;
+          const int min_err = winner_resolve_fast(ws, row, col);
+          if (min_err <= thr) {
+            cand_uid = sm.pos_uid[row * UW + lane + W - 1 - col];
+            cand_dec = (row << 8) | col;
+          } else {
+            cand_uid = kNeedOwn;   // unique: the block keeps its own initial word
+            cand_dec = -1;
           }
-          int uid = __shfl_sync(0xffffffffu, my_uid, g);
+        };
+        if (todo) resolve();
+        int stored = 0;           // blocks [0, stored) of the group have their words in global memory
+        for (int g = 0; g < n; ++g) {
+          int uid = __shfl_sync(0xffffffffu, cand_uid, g);   // lane g has received all its pushes
           if (uid == kNeedOwn) {
             // Rare, so the own word is only looked up / added to the word table (and evaluated for
             // the 32 targets) now.  Warp-uniform branch.
             const uint32_t word = __shfl_sync(0xffffffffu, t.own_word, g);
             int slot;
             if (word == kEmpty) {
-              slot = s_special ? HT : -1;
+              const int present = s_special;
+              __syncwarp();                            // every lane has read before lane 0 writes
+              slot = present ? HT : -1;
             } else {
               uint32_t h = (word * 0x9E3779B1u) >> hshift, kv;
               while ((kv = sm.keys[h]) != kEmpty && kv != word) h = (h + 1u) & hmask;
@@ -356,33 +360,50 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
               __syncwarp();
               sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
             }
-            if (lane == g) my_uid = uid;
           }
-          if (is_todo && lane == g) {
+          if (lane == g) {
+            cand_uid = uid;                                  // final for this lane from now on
             sm.pos_uid[sa + g] = (uint16_t)uid;              // own row, this block's position
-            reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + x0 + g) + 1] = sm.ulist[uid];
           }
           __syncwarp();
           const int d = lane - g;                            // push to the targets on the right
-          if (d >= 1 && d <= sa && todo) winner_update_fast(ws, sm.err[uid * 33 + lane], (uint32_t)(sa + d - 1));
-          if (is_todo && ++since_publish >= kPublishEvery && g + 1 < n) {
-            since_publish = 0;
-            if (lane == 0) st_release(progress + by, x0 + g + 1);   // release is cumulative over the warp's
-          }                                                          // stores ordered by __syncwarp above
+          if (d >= 1 && d <= sa && todo) {
+            winner_update_fast(ws, sm.err[uid * 33 + lane], (uint32_t)(sa + d - 1));
+            resolve();
+          }
+          if ((g & (kPublishEvery - 1)) == kPublishEvery - 1 || g == n - 1) {
+            // index words of blocks [stored, g]: one coalesced store, then hand over to the publisher
+            if (lane >= stored && lane <= g && todo)
+              reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + x0 + lane) + 1] = sm.ulist[cand_uid];
+            stored = g + 1;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile int *>(&s_done) = g + 1;
+          }
         }
-        __syncwarp();
-        if (lane == 0) st_release(progress + by, x_end);     // index words are final: dependants may go on
+        PHASE_MARK(7);   // in-row decisions
         // ---- endpoints + motion for the whole group (nobody waits on these inside the kernel) ------
         if (todo) {
           const size_t b = (size_t)by * v.bw + gx;
-          if (my_dec >= 0) {
-            const int row = my_dec >> 8, col = my_dec & 0xFF;
-            cur[b] = lane_winning_block(t, sm.ulist[my_uid]);
+          if (cand_dec >= 0) {
+            const int row = cand_dec >> 8, col = cand_dec & 0xFF;
+            cur[b] = lane_winning_block(t, sm.ulist[cand_uid]);
             motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);   // x = (i - bx) + sa
             motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);   // y = (j - by) + 2sa - 1
           } else {
             motion[2 * b + 0] = 255;
             motion[2 * b + 1] = 255;
+          }
+        }
+      } else if (wid == 1 && lane == 0) {
+        // publisher: turns the decider's block-scope hand-over into device-scope progress
+        const int n = x_end - x0;
+        for (int last = 0; last < n;) {
+          const int d = *reinterpret_cast<volatile int *>(&s_done);
+          if (d > last) {
+            __threadfence();
+            st_release(progress + by, x0 + d);
+            last = d;
           }
         }
       }

@@ -22,8 +22,8 @@ for it in range(2):
     ctx.seq_encode(0, 4, SA, THR, 1)   # gop 1: four intra frames in one launch
     ctx.sync()
 L.mptc_debug_phase_cycles(buf, 0)
-names = ["loop/todo", "wait rows above", "load+hash+ids", "remap+wordinfo", "evaluate", "rows above scan", "in-row resolve+write"]
-tot = sum(buf[i] for i in range(7))
+names = ["loop/todo", "wait rows above", "load+hash+ids", "remap+wordinfo", "evaluate", "rows above scan", "endpoint refit+write+sync", "in-row decisions", "final release"]
+tot = sum(buf[i] for i in range(9))
 groups = buf[11]
 print("intra ms", ctx.last_encode_ms("intra"), "groups", groups, "avg distinct words/group", buf[10] / max(groups, 1))
 for i, n in enumerate(names):
