@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    extra = ["-DMPTC_PHASE_TIMING"] if os.environ.get("MPTC_PHASE_TIMING") else []   # profiling builds only
+    extra = ["-DMPTC_PHASE_TIMING=" + os.environ["MPTC_PHASE_TIMING"]] if os.environ.get("MPTC_PHASE_TIMING") else []   # profiling builds only
+    extra += os.environ.get("MPTC_EXTRA_NVCC_FLAGS", "").split()
     cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

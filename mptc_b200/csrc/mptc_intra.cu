@@ -31,7 +31,10 @@ constexpr int kThreads = 512, kWarps = kThreads / 32;
 constexpr int kMaxWords = 256;                // distinct words per group on the fast path
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint16_t kNone = 0xFFFFu;
-constexpr int kPublishEvery = 8;              // decisions between progress publications
+#ifndef MPTC_PUBLISH_EVERY
+#define MPTC_PUBLISH_EVERY 8
+#endif
+constexpr int kPublishEvery = MPTC_PUBLISH_EVERY;   // decisions between progress publications (power of 2)
 constexpr int kSparseTodo = 2;                // groups with this few targets take the direct path
 
 struct GroupSmem {
@@ -314,63 +317,48 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         WinnerState ws;
         winner_init(ws);
         if (todo) ws = s_partial[lane];
-        int cand_uid = (in_row && !todo) ? (int)sm.pos_uid[sa + lane] : 0;   // already-final blocks
-        int cand_dec = -2;
-        auto resolve = [&]() {
+        // Lane state.  The pushes reach target l in DECREASING scan position (block g sits at
+        // row 0, column sa + (l - g) - 1 of l's scan, and row 0 is scanned first), so every pushed
+        // candidate is the earliest one seen so far.  With the reference's rule:
+        //   err <= 0  -> it becomes the first non-positive candidate; the winner is then the
+        //                "last row with a negative" candidate if one exists in a row above
+        //                (fixed before the loop), else this candidate itself;
+        //   err  > 0  -> it only matters while no non-positive candidate exists, and then wins
+        //                ties against everything scanned later (err <= best so far).
+        // A step is therefore a handful of selects; no shared-memory traffic besides the table read.
+        int cand_uid, cand_dec, best_e, ln_uid, ln_dec;
+        bool found, has_first, ln_valid;
+        {
           int row, col;
           const int min_err = winner_resolve_fast(ws, row, col);
-          if (min_err <= thr) {
-            cand_uid = sm.pos_uid[row * UW + lane + W - 1 - col];
-            cand_dec = (row << 8) | col;
-          } else {
-            cand_uid = kNeedOwn;   // unique: the block keeps its own initial word
-            cand_dec = -1;
-          }
-        };
-        if (todo) resolve();
+          found = todo ? (min_err <= thr) : true;
+          cand_dec = (row << 8) | col;
+          cand_uid = todo ? (int)sm.pos_uid[found ? row * UW + lane + W - 1 - col : 0]
+                          : (in_row ? (int)sm.pos_uid[sa + lane] : 0);   // already-final blocks of the group
+          has_first = ws.first < 0x80000000u;
+          best_e = min_err;                                 // only read while !has_first
+          ln_valid = ws.lastneg >= 0 && (ws.lastneg >> 7) >= 1;
+          const int lrow = ws.lastneg >> 7, lcol = 127 - (ws.lastneg & 127);
+          ln_dec = (lrow << 8) | lcol;
+          ln_uid = sm.pos_uid[ln_valid ? lrow * UW + lane + W - 1 - lcol : 0];
+        }
+        const bool zero_ok = 0 <= thr;
+        const int *err_lane = sm.err + lane;
         int stored = 0;           // blocks [0, stored) of the group have their words in global memory
-        for (int g = 0; g < n; ++g) {
-          int uid = __shfl_sync(0xffffffffu, cand_uid, g);   // lane g has received all its pushes
-          if (uid == kNeedOwn) {
-            // Rare, so the own word is only looked up / added to the word table (and evaluated for
-            // the 32 targets) now.  Warp-uniform branch.
-            const uint32_t word = __shfl_sync(0xffffffffu, t.own_word, g);
-            int slot;
-            if (word == kEmpty) {
-              const int present = s_special;
-              __syncwarp();                            // every lane has read before lane 0 writes
-              slot = present ? HT : -1;
-            } else {
-              uint32_t h = (word * 0x9E3779B1u) >> hshift, kv;
-              while ((kv = sm.keys[h]) != kEmpty && kv != word) h = (h + 1u) & hmask;
-              __syncwarp();                            // every lane has read before lane 0 writes
-              if (kv != word && lane == 0) sm.keys[h] = word;
-              slot = (kv == word) ? (int)h : -(int)h - 2;   // negative: new entry at slot h
-            }
-            if (slot >= 0) {
-              uid = sm.slot_uid[slot];
-            } else {
-              uid = U++;
-              if (lane == 0) {
-                if (word == kEmpty) { s_special = 1; sm.slot_uid[HT] = (uint16_t)uid; }
-                else sm.slot_uid[-slot - 2] = (uint16_t)uid;
-                sm.ulist[uid] = word;
-                word_info(word, sm.info[uid]);
-              }
-              __syncwarp();
-              sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
-            }
-          }
-          if (lane == g) {
-            cand_uid = uid;                                  // final for this lane from now on
-            sm.pos_uid[sa + g] = (uint16_t)uid;              // own row, this block's position
-          }
-          __syncwarp();
-          const int d = lane - g;                            // push to the targets on the right
-          if (d >= 1 && d <= sa && todo) {
-            winner_update_fast(ws, sm.err[uid * 33 + lane], (uint32_t)(sa + d - 1));
-            resolve();
-          }
+        // Everything of step g after lane g's word id is known.
+        auto finish_step = [&](int g, int uid, bool unique) {
+          if (lane == g) { cand_uid = uid; found = true; cand_dec = unique ? -1 : cand_dec; }   // final from now on
+          const int d = lane - g;                            // push to the <= sa targets on the right
+          const int e = err_lane[uid * 33];
+          const bool acc = d >= 1 && d <= sa && todo && e != kRejectedSmall;
+          const bool nonpos = acc && e <= 0;
+          const bool better = acc && e > 0 && !has_first && e <= best_e;
+          const int c = sa + d - 1;
+          cand_uid = nonpos ? (ln_valid ? ln_uid : uid) : (better ? uid : cand_uid);
+          cand_dec = nonpos ? (ln_valid ? ln_dec : c) : (better ? c : cand_dec);
+          found = nonpos ? zero_ok : (better ? (e <= thr) : found);
+          best_e = better ? e : best_e;
+          has_first = has_first || nonpos;
           if ((g & (kPublishEvery - 1)) == kPublishEvery - 1 || g == n - 1) {
             // index words of blocks [stored, g]: one coalesced store, then hand over to the publisher
             if (lane >= stored && lane <= g && todo)
@@ -380,6 +368,47 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             __syncwarp();
             if (lane == 0) *reinterpret_cast<volatile int *>(&s_done) = g + 1;
           }
+        };
+        for (int g = 0; g < n;) {
+          // Hot loop: a lone warp is bound by instruction latency, so it is kept short and
+          // straight-line.  Leaves as soon as a block turns out unique.
+          int uid = 0;
+          for (; g < n; ++g) {
+            uid = __shfl_sync(0xffffffffu, found ? cand_uid : kNeedOwn, g);   // lane g has all its pushes
+            if (uid == kNeedOwn) break;
+            finish_step(g, uid, false);
+          }
+          if (g >= n) break;
+          // Rare: block g keeps its own initial word, which later targets may reuse; look it up /
+          // add it to the word table and evaluate it for the 32 targets.  Warp-uniform.
+          const uint32_t word = __shfl_sync(0xffffffffu, t.own_word, g);
+          int slot;
+          if (word == kEmpty) {
+            const int present = s_special;
+            __syncwarp();                            // every lane has read before lane 0 writes
+            slot = present ? HT : -1;
+          } else {
+            uint32_t h = (word * 0x9E3779B1u) >> hshift, kv;
+            while ((kv = sm.keys[h]) != kEmpty && kv != word) h = (h + 1u) & hmask;
+            __syncwarp();                            // every lane has read before lane 0 writes
+            if (kv != word && lane == 0) sm.keys[h] = word;
+            slot = (kv == word) ? (int)h : -(int)h - 2;   // negative: new entry at slot h
+          }
+          if (slot >= 0) {
+            uid = sm.slot_uid[slot];
+          } else {
+            uid = U++;
+            if (lane == 0) {
+              if (word == kEmpty) { s_special = 1; sm.slot_uid[HT] = (uint16_t)uid; }
+              else sm.slot_uid[-slot - 2] = (uint16_t)uid;
+              sm.ulist[uid] = word;
+              word_info(word, sm.info[uid]);
+            }
+            __syncwarp();
+            sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
+          }
+          finish_step(g, uid, true);
+          ++g;
         }
         PHASE_MARK(7);   // in-row decisions
         // ---- endpoints + motion for the whole group (nobody waits on these inside the kernel) ------
@@ -404,6 +433,8 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             __threadfence();
             st_release(progress + by, x0 + d);
             last = d;
+          } else {
+            __nanosleep(64);   // do not hammer the shared-memory pipe the decider warp depends on
           }
         }
       }
