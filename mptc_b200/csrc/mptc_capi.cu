@@ -33,7 +33,7 @@ struct mptc_gpu_ctx {
   size_t frame_bytes = 0, plane_bytes = 0;  // plane_bytes = 6*pbw*pbh
   uint8_t *d_rgb = nullptr;
   uint64_t *d_init = nullptr, *d_final = nullptr;
-  uint8_t *d_motion = nullptr, *d_flags = nullptr, *d_planes = nullptr;
+  uint8_t *d_motion = nullptr, *d_flags = nullptr, *d_planes = nullptr, *d_row_todo = nullptr;
   uint32_t *d_unique = nullptr, *d_nunique = nullptr;
   int *d_progress = nullptr, *d_tickets = nullptr;
   unsigned long long *d_cand = nullptr;
@@ -89,9 +89,9 @@ void build_match_table(uint8_t *table, int bits) {
 void free_seq(mptc_gpu_ctx *c) {
   cudaFree(c->d_rgb); cudaFree(c->d_init); cudaFree(c->d_final); cudaFree(c->d_motion);
   cudaFree(c->d_flags); cudaFree(c->d_planes); cudaFree(c->d_unique); cudaFree(c->d_nunique);
-  cudaFree(c->d_progress);
+  cudaFree(c->d_progress); cudaFree(c->d_row_todo);
   c->d_rgb = nullptr; c->d_init = c->d_final = nullptr; c->d_motion = c->d_flags = c->d_planes = nullptr;
-  c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr;
+  c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr; c->d_row_todo = nullptr;
   c->cap_frames = 0; c->w = c->h = 0;
   c->encoded = false;
 }
@@ -99,7 +99,7 @@ void free_seq(mptc_gpu_ctx *c) {
 SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
   SeqView v;
   v.rgb = c->d_rgb; v.init_blocks = c->d_init; v.final_blocks = c->d_final; v.motion = c->d_motion;
-  v.flags = c->d_flags; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.planes = c->d_planes;
+  v.flags = c->d_flags; v.row_todo = c->d_row_todo; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.planes = c->d_planes;
   v.progress = c->d_progress; v.frame_bytes = c->frame_bytes;
   v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb;
   v.first = first; v.count = count; v.gop = gop;
@@ -149,6 +149,7 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
   CU(c, cudaMemsetAsync(c->d_tickets, 0, sizeof(int) * gop, s));
   CU(c, cudaMemsetAsync(c->d_progress + (size_t)first * c->bh, 0, sizeof(int) * (size_t)count * c->bh, s));
   CU(c, cudaMemsetAsync(c->d_flags + (size_t)first * c->nb, 0, (size_t)count * c->nb, s));
+  CU(c, cudaMemsetAsync(c->d_row_todo + (size_t)first * c->bh, 0, (size_t)count * c->bh, s));
   CU(c, cudaMemsetAsync(c->d_cand, 0, 2 * sizeof(unsigned long long), s));
   if (fit) {
     StageEvent &e = stage_begin(c, 1);
@@ -252,6 +253,7 @@ int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
   CU(c, cudaMalloc(&c->d_final, F * nb * 8));
   CU(c, cudaMalloc(&c->d_motion, F * nb * 2));
   CU(c, cudaMalloc(&c->d_flags, F * nb));
+  CU(c, cudaMalloc(&c->d_row_todo, F * c->bh));
   CU(c, cudaMalloc(&c->d_unique, F * nb * 4));
   CU(c, cudaMalloc(&c->d_nunique, F * 4));
   CU(c, cudaMalloc(&c->d_planes, F * c->plane_bytes));

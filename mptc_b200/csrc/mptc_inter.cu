@@ -220,6 +220,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
       flag = 1;
     }
     v.flags[(size_t)f * v.nb + tb] = flag;
+    if (!flag) v.row_todo[(size_t)f * v.bh + tby] = 1;   // the intra wavefront has work in this row
   }
 }
 

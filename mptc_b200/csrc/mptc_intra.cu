@@ -149,6 +149,12 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     const uint8_t *flags = v.flags + (size_t)f * v.nb;
     uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
     int *progress = v.progress + (size_t)f * v.bh;
+    // Inter frames: only rows in which the inter search left blocks over have work; every other
+    // row is final already and counts as complete for its dependants without any publication.
+    const bool all_rows = (k_in_gop == 0);
+    const uint8_t *row_todo = v.row_todo + (size_t)f * v.bh;
+    if (!all_rows && !row_todo[by]) continue;
+    int published = 0;                 // tid 0: last value stored to progress[by]
 
     PHASE_DECL;
     for (int x0 = 0; x0 < v.bw; x0 += kG) {
@@ -159,9 +165,10 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       const bool in_row = gx < v.bw;
       const bool todo = in_row && flags[(size_t)by * v.bw + gx] == 0;
       const unsigned todo_mask = __ballot_sync(0xffffffffu, todo);   // identical in every warp
-      if (todo_mask == 0u) {
-        if (tid == 0) st_release(progress + by, x_end);
-        continue;
+      if (todo_mask == 0u) continue;    // nothing to do here; published lazily below / at the row end
+      if (tid == 0 && published < x0) {  // blocks skipped so far are final
+        st_release(progress + by, x0);
+        published = x0;
       }
 
       // ---- wait for the window rows; clear the word table meanwhile ---------------------------
@@ -169,7 +176,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         const int need = min(x_end - 1 + sa, v.bw);
         for (int base = 1; base < R; base += 32) {
           const int r = base + lane;
-          bool ok = r >= R || by - r < 0;
+          bool ok = r >= R || by - r < 0 || (!all_rows && !row_todo[by - r]);
           while (!__all_sync(0xffffffffu, ok)) {
             if (!ok) ok = ld_acquire(progress + by - r) >= need;
             if (!ok) __nanosleep(32);
@@ -441,6 +448,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       __syncthreads();
       PHASE_MARK(6);   // in-row resolve + write
     }
+    if (tid == 0) st_release(progress + by, v.bw);   // covers trailing groups that had nothing to do
   }
 }
 

@@ -249,6 +249,7 @@ k_inter_search(SeqView v, int k_in_gop, int sa, int thr) {
       flag = 1;
     }
     v.flags[(size_t)f * v.nb + b] = flag;
+    if (!flag) v.row_todo[(size_t)f * v.bh + by] = 1;
   }
 }
 

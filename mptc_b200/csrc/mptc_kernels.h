@@ -13,6 +13,7 @@ struct SeqView {
   uint64_t *final_blocks;  // [F][nb]   after Reencode
   uint8_t *motion;         // [F][nb][2]
   uint8_t *flags;          // [F][nb]   1 = final after the inter search
+  uint8_t *row_todo;       // [F][bh]   1 = the row has blocks the inter search left over
   uint32_t *unique;        // [F][nb]
   uint32_t *n_unique;      // [F]
   uint8_t *planes;         // [F][6][pbh][pbw]
