@@ -98,9 +98,18 @@ int mptc_gpu_sync(mptc_gpu_ctx *ctx);
  * 5 endpoint planes.  Stages 1..5 are sums over the launches of that kernel. */
 int mptc_gpu_last_encode_ms(mptc_gpu_ctx *ctx, int stage, float *ms);
 
-/* End to end from HOST frames to HOST results: chunks the GOPs into waves and overlaps
- * H2D of wave i+1, kernels of wave i and D2H of wave i-1 on three streams.  `frames` and
- * the outputs should be page-locked (mptc_gpu_host_alloc) for the copies to overlap. */
+/* Scheduling knobs of the sequence entry points (0 = automatic for each).  The GOPs of one call
+ * are split into `lanes` contiguous ranges, each on its own CUDA stream: the reference's
+ * ThreadedCompressMultiUnique runs one std::thread per dictionary group the same way
+ * (codec/codec.cpp:1781-1793).  wave_rows_* = CTAs per frame of the intra wavefront kernel for
+ * intra frames / for the leftovers of inter frames (rows of a frame that are in flight). */
+int mptc_gpu_set_schedule(mptc_gpu_ctx *ctx, int lanes, int wave_rows_intra, int wave_rows_inter);
+
+/* End to end from HOST frames to HOST results.  Per lane: H2D of its frames (one copy stream,
+ * lane order), kernels on the lane's stream, D2H of its results on a third stream, so the
+ * copies of one lane overlap the kernels of the others.  `frames` and the outputs should be
+ * page-locked (mptc_gpu_host_alloc) for the copies to overlap.  Returns when all results are on
+ * the host; mptc_gpu_last_encode_ms(0) then covers copies + kernels. */
 int mptc_gpu_encode_sequence(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
                              const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion,
                              uint32_t *unique, uint32_t *n_unique, uint8_t *planes);

@@ -20,7 +20,7 @@ EXPORTS = [
     "mptc_gpu_dxt1_fit", "mptc_gpu_reencode", "mptc_gpu_endpoint_planes",
     "mptc_gpu_seq_reserve", "mptc_gpu_seq_upload", "mptc_gpu_seq_encode", "mptc_gpu_seq_download",
     "mptc_gpu_sync", "mptc_gpu_last_encode_ms", "mptc_gpu_encode_sequence",
-    "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count",
+    "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count", "mptc_gpu_set_schedule",
 ]
 
 
@@ -69,6 +69,7 @@ def load():
     L.mptc_gpu_host_alloc.argtypes = [C.c_size_t]
     L.mptc_gpu_host_free.argtypes = [vp]
     L.mptc_gpu_last_candidate_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.mptc_gpu_set_schedule.argtypes = [vp, ci, ci, ci]
     _lib = L
     return L
 
@@ -203,6 +204,10 @@ class Context:
 
     def sync(self):
         self._check(self._L.mptc_gpu_sync(self._p))
+
+    def set_schedule(self, lanes=0, wave_rows_intra=0, wave_rows_inter=0):
+        """GOP lanes (streams) per encode call and CTAs per frame of the intra wavefront; 0 = automatic."""
+        self._check(self._L.mptc_gpu_set_schedule(self._p, lanes, wave_rows_intra, wave_rows_inter))
 
     def last_encode_ms(self, stage="total") -> float:
         ms = C.c_float(0)

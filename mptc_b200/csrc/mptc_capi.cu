@@ -35,13 +35,26 @@ struct mptc_gpu_ctx {
   uint64_t *d_init = nullptr, *d_final = nullptr;
   uint8_t *d_motion = nullptr, *d_flags = nullptr, *d_planes = nullptr, *d_row_todo = nullptr;
   uint32_t *d_unique = nullptr, *d_nunique = nullptr;
-  int *d_progress = nullptr, *d_tickets = nullptr;
+  int *d_progress = nullptr;
   unsigned long long *d_cand = nullptr;
-  int tickets_cap = 0;
   int max_wave_ctas = 0;
   bool encoded = false;
-  std::vector<StageEvent> stage_events;
-  size_t stage_events_used = 0;
+  // GOP lanes: independent GOP ranges of one encode call run on their own streams, so the
+  // latency-bound intra wavefront of one lane overlaps the throughput-bound inter search of
+  // the others (and, end to end, the H2D / D2H copies of the neighbours).
+  struct Lane {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    int *d_tickets = nullptr;
+    int tickets_cap = 0;
+    std::vector<StageEvent> stage_events;
+    size_t stage_events_used = 0;
+  };
+  std::vector<Lane> lanes;
+  int lanes_wanted = 0;          // 0 = automatic
+  int lanes_used = 0;
+  int sparse_ctas = 48;          // K3s CTAs per frame
+  int wave_rows_intra = 0, wave_rows_inter = 0;   // CTAs per frame of the intra wavefront; 0 = default
   uint64_t launches = 0;
   char err[512] = {0};
 };
@@ -106,22 +119,24 @@ SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
   return v;
 }
 
-StageEvent &stage_begin(mptc_gpu_ctx *c, int stage) {
-  if (c->stage_events_used == c->stage_events.size()) {
+typedef mptc_gpu_ctx::Lane Lane;
+
+StageEvent &stage_begin(Lane &L, int stage) {
+  if (L.stage_events_used == L.stage_events.size()) {
     StageEvent e;
     e.stage = stage;
     cudaEventCreate(&e.a);
     cudaEventCreate(&e.b);
-    c->stage_events.push_back(e);
+    L.stage_events.push_back(e);
   }
-  StageEvent &e = c->stage_events[c->stage_events_used++];
+  StageEvent &e = L.stage_events[L.stage_events_used++];
   e.stage = stage;
-  cudaEventRecord(e.a, c->s_compute);
+  cudaEventRecord(e.a, L.s);
   return e;
 }
 
-void stage_end(mptc_gpu_ctx *c, StageEvent &e) {
-  cudaEventRecord(e.b, c->s_compute);
+void stage_end(mptc_gpu_ctx *c, Lane &L, StageEvent &e) {
+  cudaEventRecord(e.b, L.s);
   ++c->launches;
 }
 
@@ -131,53 +146,139 @@ int check_params(mptc_gpu_ctx *c, int sa, int gop) {
   return MPTC_OK;
 }
 
-// Search + compaction + planes over frames [first, first+count) whose fit is already done.
-// If fit == true also runs K1 over the range.  k_begin lets single-frame calls start at an
-// inter frame whose predecessor's final blocks were supplied by the caller.
-int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, bool fit, int k_begin,
-               bool planes) {
-  cudaStream_t s = c->s_compute;
+int ensure_lanes(mptc_gpu_ctx *c, int n) {
+  while ((int)c->lanes.size() < n) {
+    Lane L;
+    CU(c, cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+    CU(c, cudaEventCreateWithFlags(&L.ev_in, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
+    c->lanes.push_back(L);
+  }
+  return MPTC_OK;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
+// Host buffers of an end-to-end call; all optional.
+struct HostIO {
+  const uint8_t *frames = nullptr;
+  uint64_t *blocks = nullptr;
+  uint8_t *motion = nullptr;
+  uint32_t *unique = nullptr, *n_unique = nullptr;
+  uint8_t *planes = nullptr;
+  bool any_out() const { return blocks || motion || unique || n_unique || planes; }
+};
+
+// Enqueues on lane L: search + compaction + planes over frames [first, first+count) (a whole
+// number of GOPs except possibly the last one).  If fit == true also runs K1 over the range.
+// k_begin lets single-frame calls start at an inter frame whose predecessor's final blocks were
+// supplied by the caller.
+int enqueue_range(mptc_gpu_ctx *c, Lane &L, int first, int count, int gop, int sa, int thr, bool fit, int k_begin,
+                  bool planes) {
+  cudaStream_t s = L.s;
   const int n_gops = (count + gop - 1) / gop;
-  if (gop > c->tickets_cap) {
-    cudaFree(c->d_tickets);
-    CU(c, cudaMalloc(&c->d_tickets, sizeof(int) * gop));
-    c->tickets_cap = gop;
+  // tickets: [k] for the row wavefront of frame k of every GOP, then [gop + k*n_gops + g] for K3s
+  const int n_tickets = gop * (1 + n_gops);
+  if (n_tickets > L.tickets_cap) {
+    if (L.d_tickets) CU(c, cudaFree(L.d_tickets));   // implicit sync; only on the first calls
+    CU(c, cudaMalloc(&L.d_tickets, sizeof(int) * n_tickets));
+    L.tickets_cap = n_tickets;
   }
   SeqView v = view_of(c, first, count, gop);
-  c->stage_events_used = 0;
-  CU(c, cudaEventRecord(c->ev_begin, s));
-  CU(c, cudaMemsetAsync(c->d_tickets, 0, sizeof(int) * gop, s));
+  CU(c, cudaMemsetAsync(L.d_tickets, 0, sizeof(int) * n_tickets, s));
   CU(c, cudaMemsetAsync(c->d_progress + (size_t)first * c->bh, 0, sizeof(int) * (size_t)count * c->bh, s));
   CU(c, cudaMemsetAsync(c->d_flags + (size_t)first * c->nb, 0, (size_t)count * c->nb, s));
   CU(c, cudaMemsetAsync(c->d_row_todo + (size_t)first * c->bh, 0, (size_t)count * c->bh, s));
-  CU(c, cudaMemsetAsync(c->d_cand, 0, 2 * sizeof(unsigned long long), s));
   if (fit) {
-    StageEvent &e = stage_begin(c, 1);
+    StageEvent &e = stage_begin(L, 1);
     launch_dxt1_fit(v, s);
-    stage_end(c, e);
+    stage_end(c, L, e);
   }
   const int k_end = count < gop ? count : gop;
   for (int k = k_begin; k < k_end; ++k) {
     if (k > 0) {
-      StageEvent &e = stage_begin(c, 2);
+      StageEvent &e = stage_begin(L, 2);
       launch_inter_search(v, k, n_gops, sa, thr, s);
-      stage_end(c, e);
+      stage_end(c, L, e);
     }
-    StageEvent &e = stage_begin(c, 3);
-    launch_intra_wavefront(v, k, n_gops, sa, thr, c->d_tickets + k, c->max_wave_ctas, s);
-    stage_end(c, e);
+    StageEvent &e = stage_begin(L, 3);
+    const int rows = k == 0 ? c->wave_rows_intra : c->wave_rows_inter;
+    if (k > 0) {
+      launch_intra_sparse(v, k, n_gops, sa, thr, L.d_tickets + gop + k * n_gops, c->sparse_ctas, s);
+      ++c->launches;
+    }
+    launch_intra_wavefront(v, k, n_gops, sa, thr, L.d_tickets + k, c->max_wave_ctas, rows * n_gops, s);
+    stage_end(c, L, e);
   }
   {
-    StageEvent &e = stage_begin(c, 4);
+    StageEvent &e = stage_begin(L, 4);
     launch_compact_unique(v, sa, c->d_cand, s);
-    stage_end(c, e);
+    stage_end(c, L, e);
   }
   if (planes) {
-    StageEvent &e = stage_begin(c, 5);
+    StageEvent &e = stage_begin(L, 5);
     launch_endpoint_planes(v, c->pbw, c->pbh, s);
-    stage_end(c, e);
+    stage_end(c, L, e);
   }
-  CU(c, cudaEventRecord(c->ev_end, s));
+  return MPTC_OK;
+}
+
+// One encode call over frames [first, first+count): the GOPs are split into contiguous ranges,
+// one per lane.  With host buffers (io) each lane's frames are uploaded on the H2D stream in
+// lane order and its results downloaded on the D2H stream as soon as the lane is done, so the
+// copies of one lane overlap the kernels of the others.  ev_begin .. ev_end on s_compute
+// bracket everything (including the copies when io is given).
+int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, bool fit, int k_begin,
+               bool planes, const HostIO *io = nullptr) {
+  const int n_gops = (count + gop - 1) / gop;
+  int nl = c->lanes_wanted > 0 ? c->lanes_wanted : 4;
+  if (nl > n_gops) nl = n_gops;
+  if (k_begin != 0) nl = 1;
+  if (nl > 16) nl = 16;
+  if (int r = ensure_lanes(c, nl)) return r;
+  cudaStream_t s0 = c->s_compute;
+  CU(c, cudaMemsetAsync(c->d_cand, 0, 2 * sizeof(unsigned long long), s0));
+  CU(c, cudaEventRecord(c->ev_begin, s0));
+  if (io && io->frames) CU(c, cudaStreamWaitEvent(c->s_h2d, c->ev_begin, 0));
+  const size_t nb = (size_t)c->nb;
+  for (int i = 0; i < nl; ++i) {
+    Lane &L = c->lanes[i];
+    L.stage_events_used = 0;
+    const int g0 = (int)((long long)n_gops * i / nl), g1 = (int)((long long)n_gops * (i + 1) / nl);
+    const int f0 = first + g0 * gop;
+    int n = (g1 - g0) * gop;
+    if (f0 + n > first + count) n = first + count - f0;
+    if (io && io->frames) {
+      CU(c, cudaMemcpyAsync(c->d_rgb + c->frame_bytes * f0, io->frames + c->frame_bytes * (size_t)(f0 - first),
+                            c->frame_bytes * n, cudaMemcpyHostToDevice, c->s_h2d));
+      CU(c, cudaEventRecord(L.ev_in, c->s_h2d));
+      CU(c, cudaStreamWaitEvent(L.s, L.ev_in, 0));
+    } else {
+      CU(c, cudaStreamWaitEvent(L.s, c->ev_begin, 0));
+    }
+    if (int r = enqueue_range(c, L, f0, n, gop, sa, thr, fit, k_begin, planes)) return r;
+    CU(c, cudaEventRecord(L.ev_done, L.s));
+    if (io && io->any_out()) {
+      cudaStream_t d = c->s_d2h;
+      const size_t o = (size_t)(f0 - first), m = (size_t)n, f = (size_t)f0;
+      CU(c, cudaStreamWaitEvent(d, L.ev_done, 0));
+      if (io->blocks) CU(c, cudaMemcpyAsync(io->blocks + o * nb, c->d_final + f * nb, m * nb * 8, cudaMemcpyDeviceToHost, d));
+      if (io->motion) CU(c, cudaMemcpyAsync(io->motion + o * nb * 2, c->d_motion + f * nb * 2, m * nb * 2, cudaMemcpyDeviceToHost, d));
+      if (io->unique) CU(c, cudaMemcpyAsync(io->unique + o * nb, c->d_unique + f * nb, m * nb * 4, cudaMemcpyDeviceToHost, d));
+      if (io->n_unique) CU(c, cudaMemcpyAsync(io->n_unique + o, c->d_nunique + f, m * 4, cudaMemcpyDeviceToHost, d));
+      if (io->planes) CU(c, cudaMemcpyAsync(io->planes + o * c->plane_bytes, c->d_planes + f * c->plane_bytes, m * c->plane_bytes, cudaMemcpyDeviceToHost, d));
+      CU(c, cudaEventRecord(L.ev_out, d));
+      CU(c, cudaStreamWaitEvent(s0, L.ev_out, 0));
+    } else {
+      CU(c, cudaStreamWaitEvent(s0, L.ev_done, 0));
+    }
+  }
+  c->lanes_used = nl;
+  CU(c, cudaEventRecord(c->ev_end, s0));
   CU(c, cudaGetLastError());
   c->encoded = true;
   return MPTC_OK;
@@ -210,6 +311,11 @@ int mptc_gpu_create(int device, mptc_gpu_ctx **out) {
   }
   if (!ok) { mptc_gpu_destroy(c); return MPTC_E_CUDA; }
   c->max_wave_ctas = intra_wavefront_max_ctas(device);
+  c->lanes_wanted = env_int("MPTC_LANES", 0);
+  c->wave_rows_intra = env_int("MPTC_WAVE_ROWS_INTRA", 0);
+  c->wave_rows_inter = env_int("MPTC_WAVE_ROWS_INTER", 0);
+  c->sparse_ctas = env_int("MPTC_SPARSE_CTAS", 48);
+  if (c->sparse_ctas < 1) c->sparse_ctas = 1;
   *out = c;
   return MPTC_OK;
 }
@@ -219,9 +325,15 @@ void mptc_gpu_destroy(mptc_gpu_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   free_seq(c);
-  cudaFree(c->d_tickets);
   cudaFree(c->d_cand);
-  for (auto &e : c->stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto &L : c->lanes) {
+    for (auto &e : L.stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaFree(L.d_tickets);
+    if (L.ev_in) cudaEventDestroy(L.ev_in);
+    if (L.ev_done) cudaEventDestroy(L.ev_done);
+    if (L.ev_out) cudaEventDestroy(L.ev_out);
+    if (L.s) cudaStreamDestroy(L.s);
+  }
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
   if (c->ev_uploaded) cudaEventDestroy(c->ev_uploaded);
@@ -234,6 +346,14 @@ void mptc_gpu_destroy(mptc_gpu_ctx *c) {
 
 const char *mptc_gpu_last_error(const mptc_gpu_ctx *c) { return c ? c->err : "null context"; }
 uint64_t mptc_gpu_launch_count(const mptc_gpu_ctx *c) { return c ? c->launches : 0; }
+
+int mptc_gpu_set_schedule(mptc_gpu_ctx *c, int lanes, int wave_rows_intra, int wave_rows_inter) {
+  if (!c || lanes < 0 || lanes > 16 || wave_rows_intra < 0 || wave_rows_inter < 0) return MPTC_E_ARG;
+  c->lanes_wanted = lanes;
+  c->wave_rows_intra = wave_rows_intra;
+  c->wave_rows_inter = wave_rows_inter;
+  return MPTC_OK;
+}
 
 int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
   if (!c) return MPTC_E_ARG;
@@ -314,11 +434,14 @@ int mptc_gpu_last_encode_ms(mptc_gpu_ctx *c, int stage, float *ms) {
     return MPTC_OK;
   }
   float total = 0.f;
-  for (size_t i = 0; i < c->stage_events_used; ++i) {
-    if (c->stage_events[i].stage != stage) continue;
-    float t = 0.f;
-    CU(c, cudaEventElapsedTime(&t, c->stage_events[i].a, c->stage_events[i].b));
-    total += t;
+  for (int l = 0; l < c->lanes_used; ++l) {
+    const Lane &L = c->lanes[l];
+    for (size_t i = 0; i < L.stage_events_used; ++i) {
+      if (L.stage_events[i].stage != stage) continue;
+      float t = 0.f;
+      CU(c, cudaEventElapsedTime(&t, L.stage_events[i].a, L.stage_events[i].b));
+      total += t;
+    }
   }
   *ms = total;
   return MPTC_OK;
@@ -403,9 +526,11 @@ int mptc_gpu_encode_sequence(mptc_gpu_ctx *c, const uint8_t *frames, int n_frame
   if (!c || !frames || !p) return MPTC_E_ARG;
   if (int r = check_params(c, p->search_area, p->gop)) return r;
   if (int r = mptc_gpu_seq_reserve(c, w, h, n_frames)) return r;
-  if (int r = mptc_gpu_seq_upload(c, frames, 0, n_frames)) return r;
-  if (int r = run_encode(c, 0, n_frames, p->gop, p->search_area, p->err_threshold, true, 0, planes != nullptr)) return r;
-  return mptc_gpu_seq_download(c, 0, n_frames, blocks, nullptr, motion, unique, n_unique, planes);
+  HostIO io;
+  io.frames = frames; io.blocks = blocks; io.motion = motion; io.unique = unique; io.n_unique = n_unique; io.planes = planes;
+  if (int r = run_encode(c, 0, n_frames, p->gop, p->search_area, p->err_threshold, true, 0, planes != nullptr, &io)) return r;
+  CU(c, cudaStreamSynchronize(c->s_compute));
+  return MPTC_OK;
 }
 
 void *mptc_gpu_host_alloc(size_t bytes) {

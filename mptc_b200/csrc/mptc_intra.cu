@@ -134,6 +134,15 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
   }
   if (tid < 33) sm.err[kMaxWords * 33 + tid] = kRejectedSmall;
 
+  if (k_in_gop > 0) {   // inter frames: anything left that K3s did not take?
+    bool any = false;
+    for (int g = 0; g < n_gops; ++g) {
+      const int f = v.first + g * v.gop + k_in_gop;
+      any = any || (f < v.first + v.count && v.n_unique[f] == kSparseNotHandled);
+    }
+    if (!any) return;
+  }
+
   for (;;) {
     __syncthreads();
     if (tid == 0) s_item = atomicAdd(ticket, 1);
@@ -143,6 +152,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     const int gop_i = item % n_gops, by = item / n_gops;
     const int f = v.first + gop_i * v.gop + k_in_gop;
     if (f >= v.first + v.count) continue;
+    if (k_in_gop > 0 && v.n_unique[f] != kSparseNotHandled) continue;
     const uint8_t *frame = v.rgb + v.frame_bytes * f;
     uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
     const uint64_t *init = v.init_blocks + (size_t)f * v.nb;
@@ -461,7 +471,7 @@ extern "C" void mptc_debug_phase_cycles(unsigned long long *out16, int reset) {
 #endif
 
 bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
-                                  cudaStream_t s) {
+                                  int grid_cap, cudaStream_t s) {
   static int max_optin = -1, max_ctas = 0;
   static size_t configured = 0;
   int dev = 0;
@@ -479,7 +489,8 @@ bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, in
     max_ctas = (per_sm < 1 ? 1 : per_sm) * sms;
   }
   const int items = n_gops * v.bh;
-  const int grid = items < max_ctas ? items : max_ctas;
+  int grid = items < max_ctas ? items : max_ctas;
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   k_intra_wavefront_tiled<<<grid, kThreads, bytes, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
   return true;
 }

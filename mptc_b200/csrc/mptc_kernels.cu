@@ -271,6 +271,14 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
   __shared__ int s_item;
   const int W = 2 * sa;
   const int n_items = n_gops * v.bh;
+  if (k_in_gop > 0) {   // inter frames: anything left that K3s did not take?
+    bool any = false;
+    for (int g = 0; g < n_gops; ++g) {
+      const int f = v.first + g * v.gop + k_in_gop;
+      any = any || (f < v.first + v.count && v.n_unique[f] == kSparseNotHandled);
+    }
+    if (!any) return;
+  }
   for (;;) {
     if (threadIdx.x == 0) s_item = atomicAdd(ticket, 1);
     __syncthreads();
@@ -280,6 +288,7 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
     const int g = item % n_gops, by = item / n_gops;
     const int f = v.first + g * v.gop + k_in_gop;
     if (f >= v.first + v.count) continue;
+    if (k_in_gop > 0 && v.n_unique[f] != kSparseNotHandled) continue;
     const uint8_t *frame = v.rgb + v.frame_bytes * f;
     uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
     const uint8_t *flags = v.flags + (size_t)f * v.nb;
@@ -499,10 +508,11 @@ void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int
 }
 
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
-                            int max_ctas, cudaStream_t s) {
-  if (launch_intra_wavefront_tiled(v, k_in_gop, n_gops, sa, thr, ticket, s)) return;
+                            int max_ctas, int grid_cap, cudaStream_t s) {
+  if (launch_intra_wavefront_tiled(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
   int items = n_gops * v.bh;  // direct (one target at a time) fallback for very large windows
   int grid = items < max_ctas ? items : max_ctas;
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   k_intra_wavefront<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
 }
 

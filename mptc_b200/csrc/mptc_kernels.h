@@ -24,13 +24,23 @@ struct SeqView {
   int gop;
 };
 
+// Inter frames: K3s (mptc_sparse.cu) handles frames with at most kSparseMaxItems leftover blocks
+// and tells the row wavefront through n_unique[f] (0xFFFFFFFF = not handled, take the frame).
+constexpr int kSparseMaxItems = 2048;
+constexpr uint32_t kSparseNotHandled = 0xFFFFFFFFu;
+void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
+                         cudaStream_t s);
+
 cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
 void launch_dxt1_fit(const SeqView &v, cudaStream_t s);
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
-bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket, cudaStream_t s);
+bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
+                                  int grid_cap, cudaStream_t s);
 bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
+// grid_cap > 0 limits the number of CTAs (rows in flight): a wavefront only keeps a few rows per
+// frame busy, and idle CTAs would block the SMs for kernels of other lanes.
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
-                            int max_ctas, cudaStream_t s);
+                            int max_ctas, int grid_cap, cudaStream_t s);
 void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, cudaStream_t s);
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, cudaStream_t s);
 int intra_wavefront_max_ctas(int device);
