@@ -22,12 +22,18 @@
 #include "mptc_kernels.h"
 #include "mptc_uniform_eval.cuh"
 
+#include <cstdlib>
+
 namespace mptc {
 
 namespace {
 
 constexpr int kG = 32;                        // targets per group
-constexpr int kThreads = 512, kWarps = kThreads / 32;
+#ifndef MPTC_K3_THREADS
+#define MPTC_K3_THREADS 512
+#endif
+constexpr int kThreads = MPTC_K3_THREADS, kWarps = kThreads / 32;
+constexpr int kCtasPerSm = kThreads <= 256 ? 2 : 1;
 constexpr int kMaxWords = 256;                // distinct words per group on the fast path
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint16_t kNone = 0xFFFFu;
@@ -36,13 +42,17 @@ constexpr uint16_t kNone = 0xFFFFu;
 #endif
 constexpr int kPublishEvery = MPTC_PUBLISH_EVERY;   // decisions between progress publications (power of 2)
 constexpr int kSparseTodo = 2;                // groups with this few targets take the direct path
+#ifndef MPTC_NEAR_ROWS
+#define MPTC_NEAR_ROWS 2
+#endif
+constexpr int kNear = MPTC_NEAR_ROWS;         // rows directly above that are consumed incrementally (<= 31)
 
 struct GroupSmem {
   WordInfo *info;      // [kMaxWords]
   int *err;            // [kMaxWords + 1][33]; last row = rejected for every target
   uint8_t *lut5, *lut6;
   uint32_t *keys;      // [HT + 1]
-  uint32_t *ulist;     // [NP + kG]
+  uint32_t *ulist;     // [kMaxWords + kG]
   uint16_t *pos_uid;   // [R][UW]: row 0 = the group's own row, row r = r rows above
   uint16_t *slot_uid;  // [HT + 1]
 };
@@ -64,7 +74,7 @@ __host__ __device__ inline size_t group_smem_bytes(int sa, int *np_out, int *ht_
   b += (size_t)(kMaxWords + 1) * 33 * sizeof(int);
   b += 512;
   b += (size_t)(HT + 1) * 4;
-  b += (size_t)(NP + kG) * 4;
+  b += (size_t)(kMaxWords + kG) * 4;
   b += (size_t)NP * 2;
   b += (size_t)(HT + 1) * 2;
   return (b + 15) & ~(size_t)15;
@@ -101,10 +111,11 @@ __device__ unsigned long long g_phase_cycles[16];
 
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1)
-k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__restrict__ ticket) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, int *__restrict__ ticket) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_item, s_count, s_special, s_done;
+  __shared__ int s_item, s_count, s_special, s_done, s_abort;
+  __shared__ int s_avail[kNear + 1];   // [r]: leading blocks of row by-r that are in the word table
   __shared__ WinnerState s_partial[kG];
   __shared__ TargetCtx s_t;          // slow path only
   __shared__ WinnerState s_red[kWarps];
@@ -119,14 +130,14 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     sm.err = reinterpret_cast<int *>(p);        p += (size_t)(kMaxWords + 1) * 33 * sizeof(int);
     sm.lut5 = p; sm.lut6 = p + 256;             p += 512;
     sm.keys = reinterpret_cast<uint32_t *>(p);  p += (size_t)(HT + 1) * 4;
-    sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)(NP + kG) * 4;
+    sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)(kMaxWords + kG) * 4;
     sm.pos_uid = reinterpret_cast<uint16_t *>(p); p += (size_t)NP * 2;
     sm.slot_uid = reinterpret_cast<uint16_t *>(p);
   }
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t hmask = (uint32_t)HT - 1u;
   const int hshift = 33 - __ffs(HT);
-  const int n_items = n_gops * v.bh;
+  const int n_items = n_gops * v.bh * split;   // one item = one row, or 1/split of its groups
 
   if (tid < 256) {
     sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);
@@ -149,7 +160,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     __syncthreads();
     const int item = s_item;
     if (item >= n_items) return;
-    const int gop_i = item % n_gops, by = item / n_gops;
+    const int gop_i = item % n_gops, by = (item / n_gops) / split, part = (item / n_gops) % split;
     const int f = v.first + gop_i * v.gop + k_in_gop;
     if (f >= v.first + v.count) continue;
     if (k_in_gop > 0 && v.n_unique[f] != kSparseNotHandled) continue;
@@ -167,7 +178,10 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     int published = 0;                 // tid 0: last value stored to progress[by]
 
     PHASE_DECL;
-    for (int x0 = 0; x0 < v.bw; x0 += kG) {
+    // split > 1 (intra frames only): `split` CTAs share the row, CTA `part` takes every split-th
+    // group.  The part of the own row that lies left of the group is then just another "near
+    // row" (r = 0): the next group's tables are built while the neighbour CTA still decides.
+    for (int x0 = part * kG; x0 < v.bw; x0 += split * kG) {
       const int x_end = min(x0 + kG, v.bw);
       PHASE_MARK(0);
       // ---- which blocks of the group still need the intra search ----------------------------
@@ -176,15 +190,19 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       const bool todo = in_row && flags[(size_t)by * v.bw + gx] == 0;
       const unsigned todo_mask = __ballot_sync(0xffffffffu, todo);   // identical in every warp
       if (todo_mask == 0u) continue;    // nothing to do here; published lazily below / at the row end
-      if (tid == 0 && published < x0) {  // blocks skipped so far are final
+      if (split == 1 && tid == 0 && published < x0) {  // blocks skipped so far are final
         st_release(progress + by, x0);
         published = x0;
       }
 
-      // ---- wait for the window rows; clear the word table meanwhile ---------------------------
+      // ---- wait for the FAR window rows; clear the word table meanwhile.  The kNear rows directly
+      // above are not waited for: what they have published so far goes into the word table now,
+      // the rest is consumed by the decider warp as it is published (near_update below), so a row
+      // can follow the row above at a distance of ~sa blocks instead of a whole group + sa. ---------
+      const bool sparse = __popc(todo_mask) <= kSparseTodo;
+      const int need = min(x_end - 1 + sa, v.bw);
       if (wid == 0) {
-        const int need = min(x_end - 1 + sa, v.bw);
-        for (int base = 1; base < R; base += 32) {
+        for (int base = sparse ? 1 : kNear + 1; base < R; base += 32) {
           const int r = base + lane;
           bool ok = r >= R || by - r < 0 || (!all_rows && !row_todo[by - r]);
           while (!__all_sync(0xffffffffu, ok)) {
@@ -192,16 +210,27 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             if (!ok) __nanosleep(32);
           }
         }
+        if (lane >= 1 && lane <= kNear) {
+          const int r = lane;
+          const bool complete = r >= R || by - r < 0 || (!all_rows && !row_todo[by - r]);
+          s_avail[r] = (sparse || complete) ? need : min(ld_acquire(progress + by - r), need);
+        } else if (lane == 0) {
+          int a = x0;
+          if (split > 1) {
+            a = min(ld_acquire(progress + by), x0);
+            while (sparse && a < x0) { __nanosleep(32); a = min(ld_acquire(progress + by), x0); }
+          }
+          s_avail[0] = a;
+        }
       } else {
         for (int s = tid - 32; s <= HT; s += kThreads - 32) sm.keys[s] = kEmpty;
       }
-      if (tid == 0) { s_count = 0; s_special = 0; s_done = 0; }
+      if (tid == 0) { s_count = 0; s_special = 0; s_done = 0; s_abort = -1; }
       __syncthreads();
       PHASE_MARK(1);   // wait for rows above
 
       // Few targets in the group (typical for the leftovers of an inter frame): evaluating every
       // distinct word for 32 lanes would cost more than evaluating their windows directly.
-      const bool sparse = __popc(todo_mask) <= kSparseTodo;
       int U = 0;
       LaneTarget t;
       if (!sparse) {
@@ -215,7 +244,8 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             const int r = p / UW, uc = p - r * UW;
             const int j = by - r, i = x0 - sa + uc;
             bool valid = p < NP && i >= 0 && i < v.bw && j >= 0;
-            if (r == 0) valid = valid && (i < x0 || (i < x_end && flags[(size_t)by * v.bw + i] != 0));
+            if (r == 0) valid = valid && (i < s_avail[0] || (i >= x0 && i < x_end && flags[(size_t)by * v.bw + i] != 0));
+            if (r >= 1 && r <= kNear) valid = valid && i < s_avail[r];
             ok[q] = valid;
             wv[q] = valid ? ldcg_word(cur, (size_t)j * v.bw + i) : 0u;
           }
@@ -242,7 +272,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           if (occ) {
             const int uid = atomicAdd(&s_count, 1);
             sm.slot_uid[s] = (uint16_t)uid;
-            sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;
+            if (uid < kMaxWords) sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;   // more: direct path
           }
         }
         __syncthreads();
@@ -250,10 +280,22 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         PHASE_MARK(2);   // window load + hash + ids
       }
 
-      if (sparse || U + kG > kMaxWords) {
-        // ---- direct path: one target at a time, every window position evaluated (the same code
-        // as the direct kernel).  Also taken when the window has little duplication (noise). ------
-        for (int g = 0; g < x_end - x0; ++g) {
+      // ---- direct path: one target at a time, every window position evaluated (the same code as
+      // the direct kernel).  Taken for sparse groups, when the window has little duplication
+      // (noise), and to finish a group whose word table overflowed in the decider. ----------------
+      auto direct_targets = [&](int g_begin, bool wait_near) {
+        if (wait_near) {   // the direct evaluation reads every window row from global memory
+          if (wid == 0 && lane >= 1 && lane <= kNear) {
+            const int r = lane;
+            const bool complete = r >= R || by - r < 0 || (!all_rows && !row_todo[by - r]);
+            if (!complete)
+              while (ld_acquire(progress + by - r) < need) __nanosleep(32);
+          } else if (wid == 0 && lane == 0 && split > 1) {
+            while (ld_acquire(progress + by) < x0) __nanosleep(32);
+          }
+          __syncthreads();
+        }
+        for (int g = g_begin; g < x_end - x0; ++g) {
           if (!((todo_mask >> g) & 1u)) continue;
           const int bx = x0 + g, b = by * v.bw + bx;
           if (tid == 0) build_target(s_t, frame, v.w, bx, by, init[b]);
@@ -284,6 +326,9 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           __syncthreads();
         }
         if (tid == 0) st_release(progress + by, x_end);
+      };
+      if (sparse || U + kG > kMaxWords) {
+        direct_targets(0, !sparse);
         continue;
       }
 
@@ -331,7 +376,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       if (wid == 0) {
         constexpr int kNeedOwn = 0x7fff0000;
         const int n = x_end - x0;
-        WinnerState ws;
+        WinnerState ws;            // everything target `lane` has seen so far (rows above, near rows, pushes)
         winner_init(ws);
         if (todo) ws = s_partial[lane];
         // Lane state.  The pushes reach target l in DECREASING scan position (block g sits at
@@ -339,13 +384,15 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         // candidate is the earliest one seen so far.  With the reference's rule:
         //   err <= 0  -> it becomes the first non-positive candidate; the winner is then the
         //                "last row with a negative" candidate if one exists in a row above
-        //                (fixed before the loop), else this candidate itself;
+        //                (fixed between near-row updates), else this candidate itself;
         //   err  > 0  -> it only matters while no non-positive candidate exists, and then wins
         //                ties against everything scanned later (err <= best so far).
         // A step is therefore a handful of selects; no shared-memory traffic besides the table read.
-        int cand_uid, cand_dec, best_e, ln_uid, ln_dec;
-        bool found, has_first, ln_valid;
-        {
+        int cand_uid = 0, cand_dec = 0, best_e = 0, ln_uid = 0, ln_dec = 0;
+        bool found = true, has_first = false, ln_valid = false;
+        // (Re)derives the select-only state of the still undecided lanes (lane >= g) from ws.
+        auto derive = [&](int g) {
+          if (todo && lane < g) return;   // decided: cand_* are final
           int row, col;
           const int min_err = winner_resolve_fast(ws, row, col);
           found = todo ? (min_err <= thr) : true;
@@ -358,13 +405,17 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           const int lrow = ws.lastneg >> 7, lcol = 127 - (ws.lastneg & 127);
           ln_dec = (lrow << 8) | lcol;
           ln_uid = sm.pos_uid[ln_valid ? lrow * UW + lane + W - 1 - lcol : 0];
-        }
+        };
+        derive(0);
         const bool zero_ok = 0 <= thr;
         const int *err_lane = sm.err + lane;
         int stored = 0;           // blocks [0, stored) of the group have their words in global memory
         // Everything of step g after lane g's word id is known.
         auto finish_step = [&](int g, int uid, bool unique) {
-          if (lane == g) { cand_uid = uid; found = true; cand_dec = unique ? -1 : cand_dec; }   // final from now on
+          if (lane == g) {   // final from now on
+            cand_uid = uid; found = true; cand_dec = unique ? -1 : cand_dec;
+            sm.pos_uid[sa + g] = (uint16_t)uid;              // row 0 of the window, for later derive()s
+          }
           const int d = lane - g;                            // push to the <= sa targets on the right
           const int e = err_lane[uid * 33];
           const bool acc = d >= 1 && d <= sa && todo && e != kRejectedSmall;
@@ -376,6 +427,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           found = nonpos ? zero_ok : (better ? (e <= thr) : found);
           best_e = better ? e : best_e;
           has_first = has_first || nonpos;
+          winner_update_fast(ws, acc ? e : kRejectedSmall, (uint32_t)c);   // off the critical chain
           if ((g & (kPublishEvery - 1)) == kPublishEvery - 1 || g == n - 1) {
             // index words of blocks [stored, g]: one coalesced store, then hand over to the publisher
             if (lane >= stored && lane <= g && todo)
@@ -386,50 +438,133 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             if (lane == 0) *reinterpret_cast<volatile int *>(&s_done) = g + 1;
           }
         };
-        for (int g = 0; g < n;) {
+        // Adds `word` (warp-uniform, known to be absent) to the word table and evaluates it for the
+        // 32 targets.  hslot = its free hash slot (lane `leader`'s value counts), HT for 0xFFFFFFFF.
+        auto add_word = [&](uint32_t word, int hslot, int leader) {
+          const int uid = U++;
+          if (lane == leader) {
+            if (word == kEmpty) { s_special = 1; sm.slot_uid[HT] = (uint16_t)uid; }
+            else { sm.keys[hslot] = word; sm.slot_uid[hslot] = (uint16_t)uid; }
+            sm.ulist[uid] = word;
+            word_info(word, sm.info[uid]);
+          }
+          __syncwarp();
+          sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
+          return uid;
+        };
+        // Per-lane lookup: uid of `word`, or -1 with hslot = the free slot where it would go.
+        auto probe = [&](uint32_t word, int &hslot) -> int {
+          if (word == kEmpty) { hslot = HT; return s_special ? (int)sm.slot_uid[HT] : -1; }
+          uint32_t h = (word * 0x9E3779B1u) >> hshift, kv;
+          while ((kv = sm.keys[h]) != kEmpty && kv != word) h = (h + 1u) & hmask;
+          hslot = (int)h;
+          return kv == word ? (int)sm.slot_uid[h] : -1;
+        };
+        // Near rows: merged[r-1] = leading blocks of row by-r whose words this group has consumed.
+        // merged[0]: the own row left of the group (all of it is needed before the first decision).
+        int merged[kNear + 1];
+#pragma unroll
+        for (int r = 0; r <= kNear; ++r) merged[r] = s_avail[r];
+        auto safe_end_of = [&]() {   // targets g < safe_end have all their near-row candidates
+          if (merged[0] < x0) return 0;
+          int m = merged[1];
+#pragma unroll
+          for (int r = 2; r <= kNear; ++r) m = min(m, merged[r]);
+          return m >= need ? n : min(n, max(0, m - sa - x0 + 1));
+        };
+        // Fetches what the near rows have published since, until target g's window is complete.
+        // Returns false if the word table is full.
+        auto near_update = [&](int g) -> bool {
+#pragma unroll
+          for (int r = 0; r <= kNear; ++r) {
+            const int need_g = r == 0 ? x0 : min(x0 + g + sa, v.bw);
+            if (merged[r] >= need_g) continue;
+            int p;
+            for (;;) {
+              p = ld_acquire(progress + by - r);
+              if (p >= need_g) break;
+              __nanosleep(32);
+            }
+            p = min(p, r == 0 ? x0 : need);
+            const int m0 = max(merged[r], max(x0 - sa, 0));
+            const size_t rowbase = (size_t)(by - r) * v.bw;
+            for (int c0 = m0; c0 < p; c0 += 32) {
+              const int c = c0 + lane;
+              const bool valid = c < p;
+              const uint32_t word = valid ? ldcg_word(cur, rowbase + c) : 0u;
+              int uid = -1, hslot = 0;
+              for (;;) {
+                if (valid && uid < 0) uid = probe(word, hslot);
+                const unsigned newm = __ballot_sync(0xffffffffu, valid && uid < 0);
+                if (newm == 0u) break;
+                if (U >= kMaxWords) return false;
+                const int leader = __ffs(newm) - 1;
+                const uint32_t w = __shfl_sync(0xffffffffu, word, leader);
+                const int nu = add_word(w, hslot, leader);
+                if (valid && word == w) uid = nu;
+                __syncwarp();
+              }
+              if (valid) sm.pos_uid[r * UW + c - (x0 - sa)] = (uint16_t)uid;
+            }
+            __syncwarp();
+            if (todo && lane >= g) {
+              const int lo = max(m0, x0 + lane - sa), hi = min(p, x0 + lane + sa);
+              for (int c = lo; c < hi; ++c) {
+                const int uid = sm.pos_uid[r * UW + c - (x0 - sa)];
+                winner_update_fast(ws, err_lane[uid * 33], (uint32_t)((r << 7) | (x0 + lane + sa - 1 - c)));
+              }
+            }
+            merged[r] = p;
+          }
+          return true;
+        };
+        int g = 0, safe_end = safe_end_of();
+        bool aborted = false;
+        while (g < n) {
+          if (g >= safe_end) {
+            if (!near_update(g)) { aborted = true; break; }
+            __syncwarp();
+            derive(g);
+            safe_end = safe_end_of();
+          }
           // Hot loop: a lone warp is bound by instruction latency, so it is kept short and
           // straight-line.  Leaves as soon as a block turns out unique.
           int uid = 0;
-          for (; g < n; ++g) {
+          for (; g < safe_end; ++g) {
             uid = __shfl_sync(0xffffffffu, found ? cand_uid : kNeedOwn, g);   // lane g has all its pushes
             if (uid == kNeedOwn) break;
             finish_step(g, uid, false);
           }
-          if (g >= n) break;
+          if (g >= safe_end) continue;
           // Rare: block g keeps its own initial word, which later targets may reuse; look it up /
           // add it to the word table and evaluate it for the 32 targets.  Warp-uniform.
           const uint32_t word = __shfl_sync(0xffffffffu, t.own_word, g);
-          int slot;
-          if (word == kEmpty) {
-            const int present = s_special;
-            __syncwarp();                            // every lane has read before lane 0 writes
-            slot = present ? HT : -1;
-          } else {
-            uint32_t h = (word * 0x9E3779B1u) >> hshift, kv;
-            while ((kv = sm.keys[h]) != kEmpty && kv != word) h = (h + 1u) & hmask;
-            __syncwarp();                            // every lane has read before lane 0 writes
-            if (kv != word && lane == 0) sm.keys[h] = word;
-            slot = (kv == word) ? (int)h : -(int)h - 2;   // negative: new entry at slot h
-          }
-          if (slot >= 0) {
-            uid = sm.slot_uid[slot];
-          } else {
-            uid = U++;
-            if (lane == 0) {
-              if (word == kEmpty) { s_special = 1; sm.slot_uid[HT] = (uint16_t)uid; }
-              else sm.slot_uid[-slot - 2] = (uint16_t)uid;
-              sm.ulist[uid] = word;
-              word_info(word, sm.info[uid]);
-            }
-            __syncwarp();
-            sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
+          int hslot;
+          uid = probe(word, hslot);
+          __syncwarp();                              // every lane has read before the table changes
+          if (uid < 0) {
+            if (U >= kMaxWords) { aborted = true; break; }
+            uid = add_word(word, hslot, 0);
           }
           finish_step(g, uid, true);
           ++g;
         }
+        const int g_end = g;       // == n unless the word table overflowed
+        if (aborted) {
+          // hand blocks [0, g) over, then let every warp finish the group on the direct path
+          if (lane >= stored && lane < g && todo)
+            reinterpret_cast<uint32_t *>(cur)[2 * ((size_t)by * v.bw + x0 + lane) + 1] = sm.ulist[cand_uid];
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) {
+            *reinterpret_cast<volatile int *>(&s_done) = g;
+            __threadfence_block();
+            *reinterpret_cast<volatile int *>(&s_abort) = g;
+          }
+        }
         PHASE_MARK(7);   // in-row decisions
-        // ---- endpoints + motion for the whole group (nobody waits on these inside the kernel) ------
-        if (todo) {
+        // ---- endpoints + motion for the decided blocks (nobody waits on these inside the kernel) ------
+        if (todo && lane < g_end) {
           const size_t b = (size_t)by * v.bw + gx;
           if (cand_dec >= 0) {
             const int row = cand_dec >> 8, col = cand_dec & 0xFF;
@@ -444,21 +579,30 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       } else if (wid == 1 && lane == 0) {
         // publisher: turns the decider's block-scope hand-over into device-scope progress
         const int n = x_end - x0;
-        for (int last = 0; last < n;) {
+        for (int last = 0;;) {
           const int d = *reinterpret_cast<volatile int *>(&s_done);
+          const int ab = *reinterpret_cast<volatile int *>(&s_abort);
           if (d > last) {
             __threadfence();
             st_release(progress + by, x0 + d);
             last = d;
+          } else if (last >= n || (ab >= 0 && last >= ab)) {
+            break;
           } else {
             __nanosleep(64);   // do not hammer the shared-memory pipe the decider warp depends on
           }
         }
       }
       __syncthreads();
+      if (s_abort >= 0) {          // word table overflow: the rest of the group, one target at a time
+        const int ab = s_abort;
+        __syncthreads();
+        direct_targets(ab, true);
+        continue;
+      }
       PHASE_MARK(6);   // in-row resolve + write
     }
-    if (tid == 0) st_release(progress + by, v.bw);   // covers trailing groups that had nothing to do
+    if (split == 1 && tid == 0) st_release(progress + by, v.bw);   // covers trailing groups that had nothing to do
   }
 }
 
@@ -488,10 +632,21 @@ bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, in
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     max_ctas = (per_sm < 1 ? 1 : per_sm) * sms;
   }
-  const int items = n_gops * v.bh;
+  static int split_intra = -1;
+  if (split_intra < 0) {
+    const char *e = getenv("MPTC_ROW_SPLIT");
+    split_intra = (e && *e) ? atoi(e) : 2;
+    if (split_intra < 1) split_intra = 1;
+  }
+  // Intra frames: `split` CTAs per row (see the kernel).  A CTA of a row waits for its neighbour,
+  // whose ticket is the next one, so at least `split` CTAs must be resident.
+  int split = k_in_gop == 0 ? split_intra : 1;
+  if (grid_cap > 0 && grid_cap < split) split = 1;
+  const int items = n_gops * v.bh * split;
   int grid = items < max_ctas ? items : max_ctas;
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
-  k_intra_wavefront_tiled<<<grid, kThreads, bytes, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
+  if (grid < split) split = 1;
+  k_intra_wavefront_tiled<<<grid, kThreads, bytes, s>>>(v, k_in_gop, n_gops, sa, thr, split, ticket);
   return true;
 }
 

@@ -13,6 +13,7 @@ from mptc_b200.synth import make_frame  # noqa: E402
 W, H, SA, THR = 1920, 1080, 16, 50
 frames = np.stack([make_frame(W, H, f) for f in (0, 15, 30, 45)])
 ctx = capi.Context(0)
+ctx.set_schedule(1, 0, 0)   # one lane: the four intra frames share one wavefront launch
 ctx.seq_reserve(W, H, 4)
 ctx.seq_upload(frames)
 L = capi.load()
