@@ -198,6 +198,17 @@ def reference_arm(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def ncu_evidence(dominant: str):
+    """Counters of the dominant kernel from the committed ncu capture (profiles/ncu_counters.json,
+    written by profiles/ncu_summary.py --json); None if the file is missing."""
+    p = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(dominant)
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
@@ -285,6 +296,34 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     clocks = sampler.stop()
     checksum = int(out["n_unique"].sum())
 
+    # ---- end to end incl. the host arithmetic coder (stream bytes out), overlapped with the GPU ----
+    cores = os.cpu_count() or 1
+    host_threads = max(1, cores // max(world, 1))      # the ranks of one box share its cores
+    stream_bytes = 0
+    for _ in range(2):
+        stream_bytes = len(capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)[0])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)
+    barrier()
+    stream_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    # ---- kernel attribution pass: one GOP lane, so that kernels do not overlap and the CUDA events
+    # around each launch measure that kernel alone (in the timed region above, kernels of different
+    # lanes share the GPU and their event intervals include each other's time) ---------------------
+    ctx.set_schedule(1, 0, 0)
+    for _ in range(2):
+        resident_step()
+    ctx.sync()
+    serial_ms, serial_total = {k: 0.0 for k in stage_ms}, 0.0
+    for _ in range(args.steps):
+        resident_step()
+        serial_total += ctx.last_encode_ms("total") / args.steps
+        for k in serial_ms:
+            serial_ms[k] += ctx.last_encode_ms(k) / args.steps
+    ctx.set_schedule(0, 0, 0)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -294,10 +333,10 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
     for k in stage_ms:
         stage_ms[k] /= args.steps
-    dominant = max(("inter", "intra"), key=lambda k: stage_ms[k])
+    dominant = max(("inter", "intra"), key=lambda k: serial_ms[k])
     n_cand = n_inter if dominant == "inter" else n_intra
     k_launches = (GOP - 1) if dominant == "inter" else GOP   # one launch covers frame k of every GOP
-    k_ms = stage_ms[dominant]
+    k_ms = serial_ms[dominant]
     achieved = n_cand * ALGO_SLOTS_PER_CANDIDATE / (k_ms * 1e-3) / 1e12
     clk = sm_max_mhz
     peak = SM_COUNT * SCHEDULERS * LANES * clk * 1e6 / 1e12
@@ -306,16 +345,13 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     # distinct candidate + ~14 B/block out
     frames_k = n_gops * ((GOP - 1) if dominant == "inter" else GOP)
     algo_bytes = frames_k * nb * (72 + 20 + 14)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            with open(tp) as f:
-                traffic = json.load(f).get(dominant)
-        except Exception:
-            traffic = None
+    # DRAM bytes per launch from the committed ncu --set full capture (per frame x frames per launch)
+    ev = ncu_evidence(dominant)
+    traffic = ev["dram_bytes_per_frame"] * n_gops if ev and "dram_bytes_per_frame" in ev else None
     roofline = {
-        "kernel": "k_inter_search" if dominant == "inter" else "k_intra_wavefront",
+        "kernel": "k_inter_search_tiled" if dominant == "inter" else "k_intra_wavefront_tiled",
+        "measured": "CUDA events around each launch in a one-lane pass of the same workload (kernels serialised)",
+        "share_of_step": k_ms / serial_total, "serial_step_ms": serial_total, "serial_stage_ms": serial_ms,
         "bound": "issue", "achieved": achieved, "peak": peak, "unit": "Tslot/s", "frac": achieved / peak,
         "peak_source": f"148 SMs x 4 schedulers x 32 lanes x {clk:.0f} MHz (clocks.max.sm, {peak_src}); issue-slot roofline per SURVEY.md 8(d)",
         "units_per_launch": n_cand / max(k_launches, 1), "launches_per_step": k_launches,
@@ -323,7 +359,8 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         "traffic": traffic,
         "hbm": {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
-        "stage_ms_per_step": stage_ms, "candidates_per_step": {"inter": n_inter, "intra": n_intra},
+        "overlapped_stage_ms_per_step": stage_ms, "candidates_per_step": {"inter": n_inter, "intra": n_intra},
+        "ncu": ev,
     }
     if clocks.get("sm_mhz"):
         roofline["frac_at_sampled_clock"] = achieved / (SM_COUNT * SCHEDULERS * LANES * clocks["sm_mhz"] * 1e6 / 1e12)
@@ -341,6 +378,9 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         "wall_ms_per_step": wall_ms,
         "e2e": {"value": pixels_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+        "e2e_stream": {"value": pixels_total / (stream_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": stream_ms,
+                       "host_threads": host_threads, "stream_bytes": stream_bytes,
+                       "note": "e2e + the host arithmetic coder and stream assembly (mptc_encode_stream), coder overlapped with the GPU"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "checksum_n_unique": checksum,
     }

@@ -40,15 +40,19 @@ int mptc_frame_payload(const uint8_t *motion, size_t nb, const uint8_t *planes, 
 typedef struct mptc_stream_stats {
   uint32_t max_unique_bytes, max_comp_palette, max_comp_motion, max_comp_ep_y, max_comp_ep_c;
   uint32_t n_groups;
-  double gpu_ms;      /* device time of the hot path (CUDA events) */
-  double entropy_ms;  /* wall time of arithmetic coding + assembly on `threads` host threads */
+  double gpu_ms;      /* device time of the hot path incl. its H2D/D2H copies (CUDA events) */
+  double entropy_ms;  /* wall time of arithmetic coding + assembly on `threads` host threads; in
+                         mptc_encode_stream this phase starts while the GPU is still running */
+  double total_ms;    /* wall time of the whole call */
 } mptc_stream_stats;
 
 /* Whole-sequence encode to the reference's stream format: 34-byte
  * header, then per group of p->gop frames: u32 palette size, palette stream, u32 unique bytes,
  * frame payloads.  Uses intra_interval == unique_interval == p->gop.  Frames beyond the last
  * full group are encoded but not written, exactly like the reference (codec.cpp:1477-1504).
- * The GPU part runs on `ctx`; the arithmetic coder runs on `threads` host threads. */
+ * The GPU part runs on `ctx`; the arithmetic coder runs on `threads` host threads, overlapped
+ * with it: every frame's five streams are coded as soon as its results have reached the host
+ * (mptc_gpu_encode_sequence_async + mptc_gpu_wait_frame). */
 int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
                        const mptc_gpu_params *p, int threads, uint8_t *out, size_t cap,
                        size_t *out_bytes, mptc_stream_stats *stats);

@@ -105,14 +105,26 @@ int mptc_gpu_last_encode_ms(mptc_gpu_ctx *ctx, int stage, float *ms);
  * intra frames / for the leftovers of inter frames (rows of a frame that are in flight). */
 int mptc_gpu_set_schedule(mptc_gpu_ctx *ctx, int lanes, int wave_rows_intra, int wave_rows_inter);
 
-/* End to end from HOST frames to HOST results.  Per lane: H2D of its frames (one copy stream,
- * lane order), kernels on the lane's stream, D2H of its results on a third stream, so the
- * copies of one lane overlap the kernels of the others.  `frames` and the outputs should be
- * page-locked (mptc_gpu_host_alloc) for the copies to overlap.  Returns when all results are on
- * the host; mptc_gpu_last_encode_ms(0) then covers copies + kernels. */
+/* End to end from HOST frames to HOST results.  The work is enqueued frame by frame: H2D of
+ * frame k of every GOP (copy stream), its kernels (the GOP lane's streams), D2H of its results
+ * (a third stream), so the copies of frame k+1 / k-1 overlap the kernels of frame k.  `frames`
+ * and the outputs should be page-locked (mptc_gpu_host_alloc) for the copies to overlap.
+ * Returns when all results are on the host; mptc_gpu_last_encode_ms(0) then covers copies +
+ * kernels. */
 int mptc_gpu_encode_sequence(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
                              const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion,
                              uint32_t *unique, uint32_t *n_unique, uint8_t *planes);
+
+/* The asynchronous form ("a batched/async encode + wait for stream overlap"):
+ * returns as soon as everything is enqueued.  mptc_gpu_wait_frame blocks until the results of
+ * frame `frame` are in the host buffers (callable from any host thread), mptc_gpu_wait until the
+ * whole call is done.  This is what lets the host's arithmetic coder (codec.cpp:1115-1158) start
+ * on the first frames while the GPU is still searching the later ones. */
+int mptc_gpu_encode_sequence_async(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
+                                   const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion,
+                                   uint32_t *unique, uint32_t *n_unique, uint8_t *planes);
+int mptc_gpu_wait_frame(mptc_gpu_ctx *ctx, int frame);
+int mptc_gpu_wait(mptc_gpu_ctx *ctx);
 
 /* Page-locked host memory for the buffers above. */
 void *mptc_gpu_host_alloc(size_t bytes);

@@ -21,6 +21,7 @@ EXPORTS = [
     "mptc_gpu_seq_reserve", "mptc_gpu_seq_upload", "mptc_gpu_seq_encode", "mptc_gpu_seq_download",
     "mptc_gpu_sync", "mptc_gpu_last_encode_ms", "mptc_gpu_encode_sequence",
     "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count", "mptc_gpu_set_schedule",
+    "mptc_gpu_encode_sequence_async", "mptc_gpu_wait_frame", "mptc_gpu_wait",
 ]
 
 
@@ -65,6 +66,9 @@ def load():
     L.mptc_gpu_sync.argtypes = [vp]
     L.mptc_gpu_last_encode_ms.argtypes = [vp, ci, C.POINTER(C.c_float)]
     L.mptc_gpu_encode_sequence.argtypes = [vp, vp, ci, ci, ci, C.POINTER(Params), vp, vp, vp, vp, vp]
+    L.mptc_gpu_encode_sequence_async.argtypes = [vp, vp, ci, ci, ci, C.POINTER(Params), vp, vp, vp, vp, vp]
+    L.mptc_gpu_wait_frame.argtypes = [vp, ci]
+    L.mptc_gpu_wait.argtypes = [vp]
     L.mptc_gpu_host_alloc.restype = vp
     L.mptc_gpu_host_alloc.argtypes = [C.c_size_t]
     L.mptc_gpu_host_free.argtypes = [vp]
@@ -219,8 +223,17 @@ class Context:
         self._check(self._L.mptc_gpu_last_candidate_count(self._p, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
-    def encode_sequence(self, frames: np.ndarray, search_area, err_threshold, gop, out=None, planes=True):
-        """End to end from host frames to host results (H2D + kernels + D2H)."""
+    def wait_frame(self, frame: int):
+        """Blocks until the results of `frame` of the last (async) encode are in the host buffers."""
+        self._check(self._L.mptc_gpu_wait_frame(self._p, frame))
+
+    def wait(self):
+        self._check(self._L.mptc_gpu_wait(self._p))
+
+    def encode_sequence(self, frames: np.ndarray, search_area, err_threshold, gop, out=None, planes=True,
+                        wait=True):
+        """End to end from host frames to host results (H2D + kernels + D2H).  wait=False returns as
+        soon as the work is enqueued (then use wait_frame / wait; keep `frames` and `out` alive)."""
         assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
         n, h, w = frames.shape[:3]
         nb = (h // 4) * (w // 4)
@@ -231,9 +244,9 @@ class Context:
             if planes:
                 out["planes"] = np.empty((n, 6, pbh, pbw), dtype=np.uint8)
         p = Params(search_area, err_threshold, gop)
-        self._check(self._L.mptc_gpu_encode_sequence(self._p, frames.ctypes.data, n, w, h, C.byref(p),
-                                                     _ptr(out["blocks"]), _ptr(out["motion"]), _ptr(out["unique"]),
-                                                     _ptr(out["n_unique"]), _ptr(out.get("planes"))))
+        fn = self._L.mptc_gpu_encode_sequence if wait else self._L.mptc_gpu_encode_sequence_async
+        self._check(fn(self._p, frames.ctypes.data, n, w, h, C.byref(p), _ptr(out.get("blocks")), _ptr(out["motion"]),
+                       _ptr(out["unique"]), _ptr(out["n_unique"]), _ptr(out.get("planes"))))
         self.w, self.h, self.nb, self.pbw, self.pbh = w, h, nb, pbw, pbh
         return out
 
@@ -245,7 +258,7 @@ CODEC_EXPORTS = ["mptc_arith_encode", "mptc_frame_payload", "mptc_encode_stream"
 class StreamStats(C.Structure):
     _fields_ = [("max_unique_bytes", C.c_uint32), ("max_comp_palette", C.c_uint32), ("max_comp_motion", C.c_uint32),
                 ("max_comp_ep_y", C.c_uint32), ("max_comp_ep_c", C.c_uint32), ("n_groups", C.c_uint32),
-                ("gpu_ms", C.c_double), ("entropy_ms", C.c_double)]
+                ("gpu_ms", C.c_double), ("entropy_ms", C.c_double), ("total_ms", C.c_double)]
 
 
 def _codec():

@@ -6,6 +6,7 @@
 // GOPs are independent, frames inside a GOP are not.
 #include "../../include/mptc_gpu.h"
 #include "mptc_kernels.h"
+#include "mptc_host.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -41,21 +42,28 @@ struct mptc_gpu_ctx {
   bool encoded = false;
   // GOP lanes: independent GOP ranges of one encode call run on their own streams, so the
   // latency-bound intra wavefront of one lane overlaps the throughput-bound inter search of
-  // the others (and, end to end, the H2D / D2H copies of the neighbours).
+  // the others.  Inside a lane the work is enqueued frame by frame (frame k of every GOP of the
+  // lane): search kernels on `s`, compaction + endpoint planes on the side stream `t`, and -- end
+  // to end -- the H2D copy of frame k+1 and the D2H copy of frame k-1 overlap the kernels of k.
   struct Lane {
-    cudaStream_t s = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    cudaStream_t s = nullptr, t = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_k, ev_side, ev_down;   // per frame index k inside the GOP
     int *d_tickets = nullptr;
     int tickets_cap = 0;
+    int f0 = 0, n = 0, n_gops = 0;   // frame range of the current call
     std::vector<StageEvent> stage_events;
     size_t stage_events_used = 0;
   };
   std::vector<Lane> lanes;
   int lanes_wanted = 0;          // 0 = automatic
   int lanes_used = 0;
+  int enc_first = 0, enc_count = 0, enc_gop = 1;   // the last encode call
+  bool enc_host_out = false;
   int sparse_ctas = 48;          // K3s CTAs per frame
   int wave_rows_intra = 0, wave_rows_inter = 0;   // CTAs per frame of the intra wavefront; 0 = default
   uint64_t launches = 0;
+  void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // result staging of mptc_encode_stream
+  size_t pinned_bytes[4] = {0, 0, 0, 0};
   char err[512] = {0};
 };
 
@@ -121,7 +129,7 @@ SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
 
 typedef mptc_gpu_ctx::Lane Lane;
 
-StageEvent &stage_begin(Lane &L, int stage) {
+StageEvent &stage_begin(Lane &L, int stage, cudaStream_t st) {
   if (L.stage_events_used == L.stage_events.size()) {
     StageEvent e;
     e.stage = stage;
@@ -131,13 +139,13 @@ StageEvent &stage_begin(Lane &L, int stage) {
   }
   StageEvent &e = L.stage_events[L.stage_events_used++];
   e.stage = stage;
-  cudaEventRecord(e.a, L.s);
+  cudaEventRecord(e.a, st);
   return e;
 }
 
-void stage_end(mptc_gpu_ctx *c, Lane &L, StageEvent &e) {
-  cudaEventRecord(e.b, L.s);
-  ++c->launches;
+void stage_end(mptc_gpu_ctx *c, StageEvent &e, cudaStream_t st, int n_launches = 1) {
+  cudaEventRecord(e.b, st);
+  c->launches += n_launches;
 }
 
 int check_params(mptc_gpu_ctx *c, int sa, int gop) {
@@ -146,14 +154,20 @@ int check_params(mptc_gpu_ctx *c, int sa, int gop) {
   return MPTC_OK;
 }
 
-int ensure_lanes(mptc_gpu_ctx *c, int n) {
+int ensure_lanes(mptc_gpu_ctx *c, int n, int gop) {
   while ((int)c->lanes.size() < n) {
     Lane L;
     CU(c, cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
-    CU(c, cudaEventCreateWithFlags(&L.ev_in, cudaEventDisableTiming));
-    CU(c, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
-    CU(c, cudaEventCreateWithFlags(&L.ev_out, cudaEventDisableTiming));
+    CU(c, cudaStreamCreateWithFlags(&L.t, cudaStreamNonBlocking));
     c->lanes.push_back(L);
+  }
+  for (int i = 0; i < n; ++i) {
+    Lane &L = c->lanes[i];
+    while ((int)L.ev_up.size() < gop) {
+      cudaEvent_t e[4];
+      for (int q = 0; q < 4; ++q) CU(c, cudaEventCreateWithFlags(&e[q], cudaEventDisableTiming));
+      L.ev_up.push_back(e[0]); L.ev_k.push_back(e[1]); L.ev_side.push_back(e[2]); L.ev_down.push_back(e[3]);
+    }
   }
   return MPTC_OK;
 }
@@ -173,65 +187,103 @@ struct HostIO {
   bool any_out() const { return blocks || motion || unique || n_unique || planes; }
 };
 
-// Enqueues on lane L: search + compaction + planes over frames [first, first+count) (a whole
-// number of GOPs except possibly the last one).  If fit == true also runs K1 over the range.
-// k_begin lets single-frame calls start at an inter frame whose predecessor's final blocks were
-// supplied by the caller.
-int enqueue_range(mptc_gpu_ctx *c, Lane &L, int first, int count, int gop, int sa, int thr, bool fit, int k_begin,
-                  bool planes) {
-  cudaStream_t s = L.s;
-  const int n_gops = (count + gop - 1) / gop;
+// Copies `rows` chunks of `width` bytes that lie `pitch` bytes apart in both src and dst (frame k of
+// consecutive GOPs).  One 2D copy when the pitch allows it, otherwise one copy per chunk.
+cudaError_t copy_strided(void *dst, const void *src, size_t width, size_t pitch, int rows, cudaMemcpyKind kind,
+                         cudaStream_t st) {
+  if (rows == 1 || width == pitch) return cudaMemcpyAsync(dst, src, width * (size_t)rows, kind, st);
+  if (pitch < ((size_t)1 << 31)) return cudaMemcpy2DAsync(dst, pitch, src, pitch, width, (size_t)rows, kind, st);
+  for (int r = 0; r < rows; ++r) {
+    cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst) + pitch * r, static_cast<const char *>(src) + pitch * r,
+                                    width, kind, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// Start of a lane's range [f0, f0 + n): reset the wavefront state of its frames.
+int lane_prologue(mptc_gpu_ctx *c, Lane &L, int gop) {
+  const int n_tickets = gop * (1 + L.n_gops);
   // tickets: [k] for the row wavefront of frame k of every GOP, then [gop + k*n_gops + g] for K3s
-  const int n_tickets = gop * (1 + n_gops);
   if (n_tickets > L.tickets_cap) {
     if (L.d_tickets) CU(c, cudaFree(L.d_tickets));   // implicit sync; only on the first calls
     CU(c, cudaMalloc(&L.d_tickets, sizeof(int) * n_tickets));
     L.tickets_cap = n_tickets;
   }
-  SeqView v = view_of(c, first, count, gop);
+  cudaStream_t s = L.s;
   CU(c, cudaMemsetAsync(L.d_tickets, 0, sizeof(int) * n_tickets, s));
-  CU(c, cudaMemsetAsync(c->d_progress + (size_t)first * c->bh, 0, sizeof(int) * (size_t)count * c->bh, s));
-  CU(c, cudaMemsetAsync(c->d_flags + (size_t)first * c->nb, 0, (size_t)count * c->nb, s));
-  CU(c, cudaMemsetAsync(c->d_row_todo + (size_t)first * c->bh, 0, (size_t)count * c->bh, s));
-  if (fit) {
-    StageEvent &e = stage_begin(L, 1);
-    launch_dxt1_fit(v, s);
-    stage_end(c, L, e);
+  CU(c, cudaMemsetAsync(c->d_progress + (size_t)L.f0 * c->bh, 0, sizeof(int) * (size_t)L.n * c->bh, s));
+  CU(c, cudaMemsetAsync(c->d_flags + (size_t)L.f0 * c->nb, 0, (size_t)L.n * c->nb, s));
+  CU(c, cudaMemsetAsync(c->d_row_todo + (size_t)L.f0 * c->bh, 0, (size_t)L.n * c->bh, s));
+  return MPTC_OK;
+}
+
+// Enqueues frame k of every GOP of lane L: [H2D] -> K1 -> K2 -> K3s/K3 on L.s, then K4 + K5 on the
+// side stream L.t, then [D2H] on the download stream.
+int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool fit, bool planes, int wave_rows,
+                 const HostIO *io, int call_first) {
+  const int nf = (L.n - k + gop - 1) / gop;       // GOPs of the lane that have a frame k
+  if (nf <= 0) return MPTC_OK;
+  const int fk = L.f0 + k;
+  const size_t nb = (size_t)c->nb;
+  SeqView v = view_of(c, L.f0, L.n, gop);
+  cudaStream_t s = L.s, t = L.t;
+  if (io && io->frames) {
+    CU(c, copy_strided(c->d_rgb + c->frame_bytes * fk, io->frames + c->frame_bytes * (size_t)(fk - call_first),
+                       c->frame_bytes, c->frame_bytes * gop, nf, cudaMemcpyHostToDevice, c->s_h2d));
+    CU(c, cudaEventRecord(L.ev_up[k], c->s_h2d));
+    CU(c, cudaStreamWaitEvent(s, L.ev_up[k], 0));
   }
-  const int k_end = count < gop ? count : gop;
-  for (int k = k_begin; k < k_end; ++k) {
-    if (k > 0) {
-      StageEvent &e = stage_begin(L, 2);
-      launch_inter_search(v, k, n_gops, sa, thr, s);
-      stage_end(c, L, e);
-    }
-    StageEvent &e = stage_begin(L, 3);
-    const int rows = k == 0 ? c->wave_rows_intra : c->wave_rows_inter;
-    if (k > 0) {
-      launch_intra_sparse(v, k, n_gops, sa, thr, L.d_tickets + gop + k * n_gops, c->sparse_ctas, s);
-      ++c->launches;
-    }
-    launch_intra_wavefront(v, k, n_gops, sa, thr, L.d_tickets + k, c->max_wave_ctas, rows * n_gops, s);
-    stage_end(c, L, e);
+  if (fit) {
+    StageEvent &e = stage_begin(L, 1, s);
+    launch_dxt1_fit(v, fk, gop, nf, s);
+    stage_end(c, e, s);
+  }
+  if (k > 0) {
+    StageEvent &e = stage_begin(L, 2, s);
+    launch_inter_search(v, k, L.n_gops, sa, thr, s);
+    stage_end(c, e, s);
   }
   {
-    StageEvent &e = stage_begin(L, 4);
-    launch_compact_unique(v, sa, c->d_cand, s);
-    stage_end(c, L, e);
+    StageEvent &e = stage_begin(L, 3, s);
+    if (k > 0) launch_intra_sparse(v, k, L.n_gops, sa, thr, L.d_tickets + gop + k * L.n_gops, c->sparse_ctas, s);
+    launch_intra_wavefront(v, k, L.n_gops, sa, thr, L.d_tickets + k, c->max_wave_ctas, wave_rows * L.n_gops, s);
+    stage_end(c, e, s, k > 0 ? 2 : 1);
+  }
+  CU(c, cudaEventRecord(L.ev_k[k], s));
+  CU(c, cudaStreamWaitEvent(t, L.ev_k[k], 0));
+  {
+    StageEvent &e = stage_begin(L, 4, t);
+    launch_compact_unique(v, sa, c->d_cand, fk, gop, nf, t);
+    stage_end(c, e, t);
   }
   if (planes) {
-    StageEvent &e = stage_begin(L, 5);
-    launch_endpoint_planes(v, c->pbw, c->pbh, s);
-    stage_end(c, L, e);
+    StageEvent &e = stage_begin(L, 5, t);
+    launch_endpoint_planes(v, c->pbw, c->pbh, fk, gop, nf, t);
+    stage_end(c, e, t);
+  }
+  CU(c, cudaEventRecord(L.ev_side[k], t));
+  if (io && io->any_out()) {
+    cudaStream_t d = c->s_d2h;
+    const size_t o = (size_t)(fk - call_first), f = (size_t)fk, g = (size_t)gop;
+    const cudaMemcpyKind D2H = cudaMemcpyDeviceToHost;
+    CU(c, cudaStreamWaitEvent(d, L.ev_side[k], 0));
+    if (io->blocks) CU(c, copy_strided(io->blocks + o * nb, c->d_final + f * nb, nb * 8, g * nb * 8, nf, D2H, d));
+    if (io->motion) CU(c, copy_strided(io->motion + o * nb * 2, c->d_motion + f * nb * 2, nb * 2, g * nb * 2, nf, D2H, d));
+    if (io->unique) CU(c, copy_strided(io->unique + o * nb, c->d_unique + f * nb, nb * 4, g * nb * 4, nf, D2H, d));
+    if (io->n_unique) CU(c, copy_strided(io->n_unique + o, c->d_nunique + f, 4, g * 4, nf, D2H, d));
+    if (io->planes) CU(c, copy_strided(io->planes + o * c->plane_bytes, c->d_planes + f * c->plane_bytes, c->plane_bytes,
+                                       g * c->plane_bytes, nf, D2H, d));
+    CU(c, cudaEventRecord(L.ev_down[k], d));
   }
   return MPTC_OK;
 }
 
 // One encode call over frames [first, first+count): the GOPs are split into contiguous ranges,
-// one per lane.  With host buffers (io) each lane's frames are uploaded on the H2D stream in
-// lane order and its results downloaded on the D2H stream as soon as the lane is done, so the
-// copies of one lane overlap the kernels of the others.  ev_begin .. ev_end on s_compute
-// bracket everything (including the copies when io is given).
+// one per lane, and enqueued frame-index-major (frame k of every lane, then k+1, ...), which is
+// also the order of the H2D and D2H copies.  ev_begin .. ev_end on s_compute bracket everything
+// (including the copies when io is given).  k_begin lets single-frame calls start at an inter
+// frame whose predecessor's final blocks were supplied by the caller.
 int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, bool fit, int k_begin,
                bool planes, const HostIO *io = nullptr) {
   const int n_gops = (count + gop - 1) / gop;
@@ -239,45 +291,40 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
   if (nl > n_gops) nl = n_gops;
   if (k_begin != 0) nl = 1;
   if (nl > 16) nl = 16;
-  if (int r = ensure_lanes(c, nl)) return r;
+  if (int r = ensure_lanes(c, nl, gop)) return r;
+  // CTAs per frame of the intra wavefront: with several lanes a full grid of (mostly waiting)
+  // wavefront CTAs would keep the other lanes' kernels off the SMs
+  const int rows_intra = c->wave_rows_intra > 0 ? c->wave_rows_intra : (nl > 1 ? 32 : 0);
+  const int rows_inter = c->wave_rows_inter;
   cudaStream_t s0 = c->s_compute;
   CU(c, cudaMemsetAsync(c->d_cand, 0, 2 * sizeof(unsigned long long), s0));
   CU(c, cudaEventRecord(c->ev_begin, s0));
   if (io && io->frames) CU(c, cudaStreamWaitEvent(c->s_h2d, c->ev_begin, 0));
-  const size_t nb = (size_t)c->nb;
   for (int i = 0; i < nl; ++i) {
     Lane &L = c->lanes[i];
     L.stage_events_used = 0;
     const int g0 = (int)((long long)n_gops * i / nl), g1 = (int)((long long)n_gops * (i + 1) / nl);
-    const int f0 = first + g0 * gop;
-    int n = (g1 - g0) * gop;
-    if (f0 + n > first + count) n = first + count - f0;
-    if (io && io->frames) {
-      CU(c, cudaMemcpyAsync(c->d_rgb + c->frame_bytes * f0, io->frames + c->frame_bytes * (size_t)(f0 - first),
-                            c->frame_bytes * n, cudaMemcpyHostToDevice, c->s_h2d));
-      CU(c, cudaEventRecord(L.ev_in, c->s_h2d));
-      CU(c, cudaStreamWaitEvent(L.s, L.ev_in, 0));
-    } else {
-      CU(c, cudaStreamWaitEvent(L.s, c->ev_begin, 0));
-    }
-    if (int r = enqueue_range(c, L, f0, n, gop, sa, thr, fit, k_begin, planes)) return r;
-    CU(c, cudaEventRecord(L.ev_done, L.s));
-    if (io && io->any_out()) {
-      cudaStream_t d = c->s_d2h;
-      const size_t o = (size_t)(f0 - first), m = (size_t)n, f = (size_t)f0;
-      CU(c, cudaStreamWaitEvent(d, L.ev_done, 0));
-      if (io->blocks) CU(c, cudaMemcpyAsync(io->blocks + o * nb, c->d_final + f * nb, m * nb * 8, cudaMemcpyDeviceToHost, d));
-      if (io->motion) CU(c, cudaMemcpyAsync(io->motion + o * nb * 2, c->d_motion + f * nb * 2, m * nb * 2, cudaMemcpyDeviceToHost, d));
-      if (io->unique) CU(c, cudaMemcpyAsync(io->unique + o * nb, c->d_unique + f * nb, m * nb * 4, cudaMemcpyDeviceToHost, d));
-      if (io->n_unique) CU(c, cudaMemcpyAsync(io->n_unique + o, c->d_nunique + f, m * 4, cudaMemcpyDeviceToHost, d));
-      if (io->planes) CU(c, cudaMemcpyAsync(io->planes + o * c->plane_bytes, c->d_planes + f * c->plane_bytes, m * c->plane_bytes, cudaMemcpyDeviceToHost, d));
-      CU(c, cudaEventRecord(L.ev_out, d));
-      CU(c, cudaStreamWaitEvent(s0, L.ev_out, 0));
-    } else {
-      CU(c, cudaStreamWaitEvent(s0, L.ev_done, 0));
-    }
+    L.f0 = first + g0 * gop;
+    L.n = (g1 - g0) * gop;
+    if (L.f0 + L.n > first + count) L.n = first + count - L.f0;
+    L.n_gops = g1 - g0;
+    CU(c, cudaStreamWaitEvent(L.s, c->ev_begin, 0));
+    if (int r = lane_prologue(c, L, gop)) return r;
+  }
+  const int k_end = count < gop ? count : gop;
+  for (int k = k_begin; k < k_end; ++k)
+    for (int i = 0; i < nl; ++i)
+      if (int r = enqueue_step(c, c->lanes[i], k, gop, sa, thr, fit, planes, k == 0 ? rows_intra : rows_inter, io, first))
+        return r;
+  const bool host_out = io && io->any_out();
+  for (int i = 0; i < nl; ++i) {
+    Lane &L = c->lanes[i];
+    const int k_last = (L.n < gop ? L.n : gop) - 1;
+    if (k_last < k_begin) continue;
+    CU(c, cudaStreamWaitEvent(s0, host_out ? L.ev_down[k_last] : L.ev_side[k_last], 0));
   }
   c->lanes_used = nl;
+  c->enc_first = first; c->enc_count = count; c->enc_gop = gop; c->enc_host_out = host_out;
   CU(c, cudaEventRecord(c->ev_end, s0));
   CU(c, cudaGetLastError());
   c->encoded = true;
@@ -285,6 +332,21 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
 }
 
 }  // namespace
+
+void *mptc::ctx_pinned(mptc_gpu_ctx *c, int slot, size_t bytes) {
+  if (!c || slot < 0 || slot >= 4) return nullptr;
+  if (c->pinned_bytes[slot] >= bytes && c->pinned[slot]) return c->pinned[slot];
+  cudaSetDevice(c->device);
+  if (c->pinned[slot]) {
+    cudaDeviceSynchronize();   // nothing may still be copying into the old buffer
+    cudaFreeHost(c->pinned[slot]);
+  }
+  c->pinned[slot] = nullptr;
+  c->pinned_bytes[slot] = 0;
+  if (cudaHostAlloc(&c->pinned[slot], bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  c->pinned_bytes[slot] = bytes;
+  return c->pinned[slot];
+}
 
 extern "C" {
 
@@ -326,13 +388,14 @@ void mptc_gpu_destroy(mptc_gpu_ctx *c) {
   cudaDeviceSynchronize();
   free_seq(c);
   cudaFree(c->d_cand);
+  for (void *p : c->pinned) if (p) cudaFreeHost(p);
   for (auto &L : c->lanes) {
     for (auto &e : L.stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaFree(L.d_tickets);
-    if (L.ev_in) cudaEventDestroy(L.ev_in);
-    if (L.ev_done) cudaEventDestroy(L.ev_done);
-    if (L.ev_out) cudaEventDestroy(L.ev_out);
+    for (auto *ev : {&L.ev_up, &L.ev_k, &L.ev_side, &L.ev_down})
+      for (cudaEvent_t e : *ev) cudaEventDestroy(e);
     if (L.s) cudaStreamDestroy(L.s);
+    if (L.t) cudaStreamDestroy(L.t);
   }
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -464,7 +527,7 @@ int mptc_gpu_dxt1_fit(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, uint64_
   if (int r = mptc_gpu_seq_reserve(c, w, h, 2)) return r;
   if (int r = mptc_gpu_seq_upload(c, rgb, 0, 1)) return r;
   SeqView v = view_of(c, 0, 1, 1);
-  launch_dxt1_fit(v, c->s_compute);
+  launch_dxt1_fit(v, 0, 1, 1, c->s_compute);
   ++c->launches;
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(blocks_out, c->d_init, (size_t)c->nb * 8, cudaMemcpyDeviceToHost, c->s_compute));
@@ -486,7 +549,7 @@ int mptc_gpu_reencode(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, int is_
     CU(c, cudaMemcpyAsync(c->d_final, prev_blocks, (size_t)c->nb * 8, cudaMemcpyHostToDevice, c->s_compute));
   {
     SeqView v = view_of(c, slot, 1, 1);
-    launch_dxt1_fit(v, c->s_compute);
+    launch_dxt1_fit(v, slot, 1, 1, c->s_compute);
     ++c->launches;
   }
   int r = is_intra ? run_encode(c, 0, 1, 1, search_area, err_threshold, false, 0, false)
@@ -512,7 +575,7 @@ int mptc_gpu_endpoint_planes(mptc_gpu_ctx *c, const uint64_t *blocks, int bw, in
   cudaStream_t s = c->s_compute;
   CU(c, cudaMemcpyAsync(c->d_final, blocks, (size_t)c->nb * 8, cudaMemcpyHostToDevice, s));
   SeqView v = view_of(c, 0, 1, 1);
-  launch_endpoint_planes(v, c->pbw, c->pbh, s);
+  launch_endpoint_planes(v, c->pbw, c->pbh, 0, 1, 1, s);
   ++c->launches;
   CU(c, cudaGetLastError());
   CU(c, cudaMemcpyAsync(planes_out, c->d_planes, c->plane_bytes, cudaMemcpyDeviceToHost, s));
@@ -520,15 +583,45 @@ int mptc_gpu_endpoint_planes(mptc_gpu_ctx *c, const uint64_t *blocks, int bw, in
   return MPTC_OK;
 }
 
-int mptc_gpu_encode_sequence(mptc_gpu_ctx *c, const uint8_t *frames, int n_frames, int w, int h,
-                             const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion, uint32_t *unique,
-                             uint32_t *n_unique, uint8_t *planes) {
+int mptc_gpu_encode_sequence_async(mptc_gpu_ctx *c, const uint8_t *frames, int n_frames, int w, int h,
+                                   const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion, uint32_t *unique,
+                                   uint32_t *n_unique, uint8_t *planes) {
   if (!c || !frames || !p) return MPTC_E_ARG;
   if (int r = check_params(c, p->search_area, p->gop)) return r;
   if (int r = mptc_gpu_seq_reserve(c, w, h, n_frames)) return r;
   HostIO io;
   io.frames = frames; io.blocks = blocks; io.motion = motion; io.unique = unique; io.n_unique = n_unique; io.planes = planes;
-  if (int r = run_encode(c, 0, n_frames, p->gop, p->search_area, p->err_threshold, true, 0, planes != nullptr, &io)) return r;
+  return run_encode(c, 0, n_frames, p->gop, p->search_area, p->err_threshold, true, 0, planes != nullptr, &io);
+}
+
+int mptc_gpu_wait_frame(mptc_gpu_ctx *c, int frame) {
+  if (!c) return MPTC_E_ARG;
+  if (!c->encoded) return fail(c, MPTC_E_STATE, "no encode has run");
+  if (frame < c->enc_first || frame >= c->enc_first + c->enc_count)
+    return fail(c, MPTC_E_ARG, "frame %d outside the last encode [%d,%d)", frame, c->enc_first, c->enc_first + c->enc_count);
+  CU(c, cudaSetDevice(c->device));
+  for (int i = 0; i < c->lanes_used; ++i) {
+    const Lane &L = c->lanes[i];
+    if (frame < L.f0 || frame >= L.f0 + L.n) continue;
+    const int k = (frame - L.f0) % c->enc_gop;
+    CU(c, cudaEventSynchronize(c->enc_host_out ? L.ev_down[k] : L.ev_side[k]));
+    return MPTC_OK;
+  }
+  return fail(c, MPTC_E_STATE, "frame %d not found in any lane", frame);
+}
+
+int mptc_gpu_wait(mptc_gpu_ctx *c) {
+  if (!c) return MPTC_E_ARG;
+  if (!c->encoded) return fail(c, MPTC_E_STATE, "no encode has run");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventSynchronize(c->ev_end));
+  return MPTC_OK;
+}
+
+int mptc_gpu_encode_sequence(mptc_gpu_ctx *c, const uint8_t *frames, int n_frames, int w, int h,
+                             const mptc_gpu_params *p, uint64_t *blocks, uint8_t *motion, uint32_t *unique,
+                             uint32_t *n_unique, uint8_t *planes) {
+  if (int r = mptc_gpu_encode_sequence_async(c, frames, n_frames, w, h, p, blocks, motion, unique, n_unique, planes)) return r;
   CU(c, cudaStreamSynchronize(c->s_compute));
   return MPTC_OK;
 }

@@ -153,6 +153,82 @@ void append_frame_payload(std::vector<uint8_t> &out, uint32_t n_unique, StreamJo
   }
 }
 
+// parallel_for whose tasks are handed out strictly in index order (task i may block until its
+// input has arrived; later inputs never arrive before earlier ones).
+template <typename F>
+void parallel_for_ordered(int n_tasks, int threads, F &&fn) { parallel_for(n_tasks, threads, fn); }
+
+// Everything mptc_assemble_stream / mptc_encode_stream share: the independent arithmetic-coder
+// jobs of a sequence (five per frame + one palette per group) and the final byte layout.
+struct StreamPlan {
+  int n_frames, w, h, n_groups, n_used;
+  mptc_gpu_params p;
+  size_t nb, ps;
+  const uint32_t *unique, *n_unique;
+  std::vector<StreamJob> jobs;                  // [n_used * 5] frame streams, then [n_groups] palettes
+  std::vector<std::vector<uint8_t>> palettes;   // combined palette per group (codec.cpp:1473-1479)
+
+  StreamPlan(int n_frames_, int w_, int h_, const mptc_gpu_params &p_, const uint8_t *motion, const uint32_t *unique_,
+             const uint32_t *n_unique_, const uint8_t *planes)
+      : n_frames(n_frames_), w(w_), h(h_), p(p_), unique(unique_), n_unique(n_unique_) {
+    nb = (size_t)(w / 4) * (h / 4);
+    ps = (size_t)((w / 4 + 63) / 64 * 64) * ((h / 4 + 63) / 64 * 64);
+    n_groups = n_frames / p.gop;                // a trailing partial group is never written
+    n_used = n_groups * p.gop;
+    jobs.resize((size_t)n_used * 5 + n_groups);
+    palettes.resize(n_groups);
+    for (int f = 0; f < n_used; ++f)
+      frame_jobs(motion + (size_t)f * 2 * nb, nb, planes + (size_t)f * 6 * ps, ps, &jobs[(size_t)f * 5]);
+  }
+
+  void build_palette(int g) {                   // needs n_unique / unique of the group's frames
+    std::vector<uint8_t> &pal = palettes[g];
+    pal.clear();
+    for (int f = g * p.gop; f < (g + 1) * p.gop; ++f) {
+      const uint8_t *src = reinterpret_cast<const uint8_t *>(unique + (size_t)f * nb);
+      pal.insert(pal.end(), src, src + (size_t)n_unique[f] * 4);
+    }
+    jobs[(size_t)n_used * 5 + g] = {pal.data(), pal.size(), {}};
+  }
+
+  void encode_job(int i) {
+    RangeEncoder enc;
+    enc.encode_all(jobs[i].sym, jobs[i].n, jobs[i].out);
+  }
+
+  void write(std::vector<uint8_t> &bytes, mptc_stream_stats &st) {
+    memset(&st, 0, sizeof st);
+    st.n_groups = (uint32_t)n_groups;
+    bytes.reserve(64 + (size_t)n_used * nb);
+    put_u32(bytes, (uint32_t)h);                     // header (codec.cpp:1358-1367)
+    put_u32(bytes, (uint32_t)w);
+    bytes.push_back((uint8_t)p.gop);
+    bytes.push_back((uint8_t)p.search_area);
+    put_u32(bytes, (uint32_t)n_groups);
+    const size_t patch_at = bytes.size();            // == 14
+    for (int k = 0; k < 5; ++k) put_u32(bytes, 0);
+    for (int g = 0; g < n_groups; ++g) {
+      const std::vector<uint8_t> &cpal = jobs[(size_t)n_used * 5 + g].out;
+      put_u32(bytes, (uint32_t)cpal.size());
+      bytes.insert(bytes.end(), cpal.begin(), cpal.end());
+      put_u32(bytes, (uint32_t)palettes[g].size());
+      if ((uint32_t)cpal.size() > st.max_comp_palette) st.max_comp_palette = (uint32_t)cpal.size();
+      if ((uint32_t)palettes[g].size() > st.max_unique_bytes) st.max_unique_bytes = (uint32_t)palettes[g].size();
+      for (int f = g * p.gop; f < (g + 1) * p.gop; ++f) {
+        StreamJob *fj = &jobs[(size_t)f * 5];
+        append_frame_payload(bytes, n_unique[f], fj);
+        const uint32_t m = (uint32_t)fj[0].out.size();
+        if (m > st.max_comp_motion) st.max_comp_motion = m;
+        for (int s : {1, 3}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_y) st.max_comp_ep_y = (uint32_t)fj[s].out.size();
+        for (int s : {2, 4}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_c) st.max_comp_ep_c = (uint32_t)fj[s].out.size();
+      }
+    }
+    const uint32_t patch[5] = {st.max_unique_bytes, st.max_comp_palette, st.max_comp_motion, st.max_comp_ep_y,
+                               st.max_comp_ep_c};   // codec.cpp:1514-1520
+    memcpy(bytes.data() + patch_at, patch, sizeof patch);
+  }
+};
+
 }  // namespace
 }  // namespace mptc
 
@@ -192,97 +268,87 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
   if (!p || !motion || !unique || !n_unique || !planes || n_frames < 1) return MPTC_E_ARG;
   if (p->gop < 1 || p->gop > 255 || p->search_area < 1 || p->search_area > 63) return MPTC_E_ARG;
   const auto t0 = std::chrono::steady_clock::now();
-  const size_t nb = (size_t)(w / 4) * (h / 4);
-  const size_t ps = (size_t)((w / 4 + 63) / 64 * 64) * ((h / 4 + 63) / 64 * 64);
-  const int n_groups = n_frames / p->gop;          // a trailing partial group is never written
-  const int n_used = n_groups * p->gop;
-
-  // every stream of every written frame + one palette stream per group, all independent
-  std::vector<StreamJob> jobs((size_t)n_used * 5 + n_groups);
-  std::vector<std::vector<uint8_t>> palettes(n_groups);
-  for (int f = 0; f < n_used; ++f)
-    frame_jobs(motion + (size_t)f * 2 * nb, nb, planes + (size_t)f * 6 * ps, ps, &jobs[(size_t)f * 5]);
-  for (int g = 0; g < n_groups; ++g) {             // combined palette (codec.cpp:1473-1479)
-    std::vector<uint8_t> &pal = palettes[g];
-    for (int f = g * p->gop; f < (g + 1) * p->gop; ++f) {
-      const uint8_t *src = reinterpret_cast<const uint8_t *>(unique + (size_t)f * nb);
-      pal.insert(pal.end(), src, src + (size_t)n_unique[f] * 4);
-    }
-    jobs[(size_t)n_used * 5 + g] = {pal.data(), pal.size(), {}};
-  }
-  parallel_for((int)jobs.size(), threads, [&](int i) {
-    RangeEncoder enc;
-    enc.encode_all(jobs[i].sym, jobs[i].n, jobs[i].out);
-  });
-
+  StreamPlan plan(n_frames, w, h, *p, motion, unique, n_unique, planes);
+  for (int g = 0; g < plan.n_groups; ++g) plan.build_palette(g);
+  parallel_for((int)plan.jobs.size(), threads, [&](int i) { plan.encode_job(i); });
   mptc_stream_stats st;
-  memset(&st, 0, sizeof st);
-  st.n_groups = (uint32_t)n_groups;
   std::vector<uint8_t> bytes;
-  bytes.reserve(64 + (size_t)n_used * nb);
-  put_u32(bytes, (uint32_t)h);                     // header (codec.cpp:1358-1367)
-  put_u32(bytes, (uint32_t)w);
-  bytes.push_back((uint8_t)p->gop);
-  bytes.push_back((uint8_t)p->search_area);
-  put_u32(bytes, (uint32_t)n_groups);
-  const size_t patch_at = bytes.size();            // == 14
-  for (int k = 0; k < 5; ++k) put_u32(bytes, 0);
-  for (int g = 0; g < n_groups; ++g) {
-    const std::vector<uint8_t> &cpal = jobs[(size_t)n_used * 5 + g].out;
-    put_u32(bytes, (uint32_t)cpal.size());
-    bytes.insert(bytes.end(), cpal.begin(), cpal.end());
-    put_u32(bytes, (uint32_t)palettes[g].size());
-    if ((uint32_t)cpal.size() > st.max_comp_palette) st.max_comp_palette = (uint32_t)cpal.size();
-    if ((uint32_t)palettes[g].size() > st.max_unique_bytes) st.max_unique_bytes = (uint32_t)palettes[g].size();
-    for (int f = g * p->gop; f < (g + 1) * p->gop; ++f) {
-      StreamJob *fj = &jobs[(size_t)f * 5];
-      append_frame_payload(bytes, n_unique[f], fj);
-      const uint32_t m = (uint32_t)fj[0].out.size();
-      if (m > st.max_comp_motion) st.max_comp_motion = m;
-      for (int s : {1, 3}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_y) st.max_comp_ep_y = (uint32_t)fj[s].out.size();
-      for (int s : {2, 4}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_c) st.max_comp_ep_c = (uint32_t)fj[s].out.size();
-    }
-  }
-  const uint32_t patch[5] = {st.max_unique_bytes, st.max_comp_palette, st.max_comp_motion, st.max_comp_ep_y,
-                             st.max_comp_ep_c};   // codec.cpp:1514-1520
-  memcpy(bytes.data() + patch_at, patch, sizeof patch);
-  st.entropy_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  plan.write(bytes, st);
+  st.entropy_ms = st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (stats) {
-    const double gpu_ms = stats->gpu_ms;
+    st.gpu_ms = stats->gpu_ms;
     *stats = st;
-    stats->gpu_ms = gpu_ms;
   }
   return copy_out(bytes, out, cap, out_bytes);
 }
 
+// GPU hot path and host arithmetic coding OVERLAPPED (BASELINE.json north_star): the encode is
+// enqueued asynchronously, results come back frame by frame in pinned buffers, and a pool of
+// host threads codes the five streams of every frame as soon as that frame's D2H copy has
+// completed (mptc_gpu_wait_frame), while the GPU is still searching the later frames.
 int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
                        const mptc_gpu_params *p, int threads, uint8_t *out, size_t cap,
                        size_t *out_bytes, mptc_stream_stats *stats) {
   if (!ctx || !frames || !p || n_frames < 1) return MPTC_E_ARG;
   if (w < 4 || h < 4 || (w & 3) || (h & 3)) return MPTC_E_ARG;
+  if (p->gop < 1 || p->gop > 255 || p->search_area < 1 || p->search_area > 63) return MPTC_E_ARG;
+  const auto t0 = std::chrono::steady_clock::now();
   const size_t nb = (size_t)(w / 4) * (h / 4);
   const size_t ps = (size_t)((w / 4 + 63) / 64 * 64) * ((h / 4 + 63) / 64 * 64);
   const size_t n = (size_t)n_frames;
-  // pinned staging for the results (freed on every exit path below)
-  uint64_t *blocks = static_cast<uint64_t *>(mptc_gpu_host_alloc(n * nb * 8));
-  uint8_t *motion = static_cast<uint8_t *>(mptc_gpu_host_alloc(n * nb * 2));
-  uint32_t *unique = static_cast<uint32_t *>(mptc_gpu_host_alloc(n * nb * 4));
-  uint32_t *n_unique = static_cast<uint32_t *>(mptc_gpu_host_alloc(n * 4));
-  uint8_t *planes = static_cast<uint8_t *>(mptc_gpu_host_alloc(n * 6 * ps));
+  // pinned staging (owned by the context, kept across calls) for the results the stream needs;
+  // the 8-byte blocks are not part of the stream
+  uint8_t *motion = static_cast<uint8_t *>(ctx_pinned(ctx, 0, n * nb * 2));
+  uint32_t *unique = static_cast<uint32_t *>(ctx_pinned(ctx, 1, n * nb * 4));
+  uint32_t *n_unique = static_cast<uint32_t *>(ctx_pinned(ctx, 2, n * 4));
+  uint8_t *planes = static_cast<uint8_t *>(ctx_pinned(ctx, 3, n * 6 * ps));
   int r = MPTC_E_NOMEM;
-  if (blocks && motion && unique && n_unique && planes) {
-    r = mptc_gpu_encode_sequence(ctx, frames, n_frames, w, h, p, blocks, motion, unique, n_unique, planes);
+  if (motion && unique && n_unique && planes) {
+    r = mptc_gpu_encode_sequence_async(ctx, frames, n_frames, w, h, p, nullptr, motion, unique, n_unique, planes);
     if (r == MPTC_OK) {
-      mptc_stream_stats st;
-      memset(&st, 0, sizeof st);
-      float ms = 0.f;
-      if (mptc_gpu_last_encode_ms(ctx, 0, &ms) == MPTC_OK) st.gpu_ms = ms;
-      r = mptc_assemble_stream(n_frames, w, h, p, motion, unique, n_unique, planes, threads, out, cap, out_bytes, &st);
-      if (stats) *stats = st;
+      StreamPlan plan(n_frames, w, h, *p, motion, unique, n_unique, planes);
+      // jobs in the order their inputs arrive: frame k of every group, then k+1, ...; a group's
+      // palette right after its last frame
+      std::vector<int> order;
+      order.reserve(plan.jobs.size());
+      for (int k = 0; k < p->gop; ++k)
+        for (int g = 0; g < plan.n_groups; ++g) {
+          const int f = g * p->gop + k;
+          for (int s = 0; s < 5; ++s) order.push_back(f * 5 + s);
+          if (k == p->gop - 1) order.push_back(plan.n_used * 5 + g);
+        }
+      std::atomic<int> failed(MPTC_OK);
+      const auto t1 = std::chrono::steady_clock::now();
+      parallel_for_ordered((int)order.size(), threads, [&](int i) {
+        const int j = order[i];
+        int wr = MPTC_OK;
+        if (j < plan.n_used * 5) {
+          wr = mptc_gpu_wait_frame(ctx, j / 5);
+        } else {
+          const int g = j - plan.n_used * 5;
+          for (int f = g * p->gop; f < (g + 1) * p->gop && wr == MPTC_OK; ++f) wr = mptc_gpu_wait_frame(ctx, f);
+          if (wr == MPTC_OK) plan.build_palette(g);
+        }
+        if (wr != MPTC_OK) { failed.store(wr); return; }
+        plan.encode_job(j);
+      });
+      r = failed.load();
+      const int wr = mptc_gpu_wait(ctx);   // also frames beyond the last full group
+      if (r == MPTC_OK) r = wr;
+      if (r == MPTC_OK) {
+        mptc_stream_stats st;
+        std::vector<uint8_t> bytes;
+        plan.write(bytes, st);
+        const auto t2 = std::chrono::steady_clock::now();
+        float ms = 0.f;
+        if (mptc_gpu_last_encode_ms(ctx, 0, &ms) == MPTC_OK) st.gpu_ms = ms;
+        st.entropy_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+        st.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
+        if (stats) *stats = st;
+        r = copy_out(bytes, out, cap, out_bytes);
+      }
     }
   }
-  mptc_gpu_host_free(blocks); mptc_gpu_host_free(motion); mptc_gpu_host_free(unique);
-  mptc_gpu_host_free(n_unique); mptc_gpu_host_free(planes);
   return r;
 }
 

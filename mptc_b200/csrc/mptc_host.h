@@ -23,3 +23,11 @@ class RangeEncoder {
 };
 
 }  // namespace mptc
+
+struct mptc_gpu_ctx;
+namespace mptc {
+// Page-locked staging buffer owned by the context (grow-only, freed with it): slot 0..3.
+// Internal to the library (not part of the C ABI): mptc_encode_stream keeps its result staging
+// across calls instead of pinning ~2 MB per frame every time.
+void *ctx_pinned(mptc_gpu_ctx *ctx, int slot, size_t bytes);
+}  // namespace mptc

@@ -196,9 +196,9 @@ __device__ __forceinline__ uint64_t fit_block(const uint32_t *px) {
 
 __global__ void __launch_bounds__(128) k_dxt1_fit(const uint8_t *__restrict__ rgb, size_t frame_bytes, int w, int bw,
                                                    int nb, uint64_t *__restrict__ init_blocks,
-                                                   uint64_t *__restrict__ final_blocks) {
+                                                   uint64_t *__restrict__ final_blocks, int fstride) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  int f = blockIdx.y;
+  int f = blockIdx.y * fstride;
   if (b >= nb) return;
   uint32_t px[16];
   load_block_rgbx(rgb + frame_bytes * f, w, b % bw, b / bw, px);
@@ -359,10 +359,10 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
 // "(255,255)" motion entries; emits the interp words in raster order.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-k_compact_unique(SeqView v, int sa, unsigned long long *__restrict__ cand_counts) {
+k_compact_unique(SeqView v, int sa, unsigned long long *__restrict__ cand_counts, int f0, int fstride) {
   __shared__ int warp_sums[32];
   __shared__ int s_base;
-  const int f = v.first + blockIdx.x;
+  const int f = f0 + blockIdx.x * fstride;
   const uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
   const uint64_t *blocks = v.final_blocks + (size_t)f * v.nb;
   uint32_t *out = v.unique + (size_t)f * v.nb;
@@ -419,14 +419,14 @@ k_compact_unique(SeqView v, int sa, unsigned long long *__restrict__ cand_counts
 __device__ __forceinline__ int mirror_hi(int i, int n) { return i < n ? i : 2 * n - 2 - i; }
 
 __global__ void __launch_bounds__(1024)
-k_endpoint_planes(SeqView v, int pbw, int pbh) {
+k_endpoint_planes(SeqView v, int pbw, int pbh, int f0, int fstride) {
   __shared__ int16_t a[64][65];
   __shared__ int16_t d[64][65];
   const int tiles_x = pbw / 64;
   const int tx = (blockIdx.x % tiles_x) * 64, ty = (blockIdx.x / tiles_x) * 64;
   const int plane = blockIdx.y;            // ep*3 + ch
   const int ep = plane / 3, ch = plane % 3;
-  const int f = v.first + blockIdx.z;
+  const int f = f0 + blockIdx.z * fstride;
   const uint64_t *blocks = v.final_blocks + (size_t)f * v.nb;
   for (int e = threadIdx.x; e < 4096; e += 1024) {
     int y = e >> 6, x = e & 63;
@@ -495,10 +495,12 @@ k_endpoint_planes(SeqView v, int pbw, int pbh) {
 // ------------------------------------------------------------------------------------------
 // Launch wrappers
 // ------------------------------------------------------------------------------------------
-void launch_dxt1_fit(const SeqView &v, cudaStream_t s) {
-  dim3 grid((v.nb + 127) / 128, v.count);
-  k_dxt1_fit<<<grid, 128, 0, s>>>(v.rgb + v.frame_bytes * v.first, v.frame_bytes, v.w, v.bw, v.nb,
-                                  v.init_blocks + (size_t)v.first * v.nb, v.final_blocks + (size_t)v.first * v.nb);
+// K1/K4/K5 run over frames f0, f0 + fstride, ... (nf of them): a contiguous range (fstride 1) or
+// frame k of every GOP of a lane (fstride = gop).
+void launch_dxt1_fit(const SeqView &v, int f0, int fstride, int nf, cudaStream_t s) {
+  dim3 grid((v.nb + 127) / 128, nf);
+  k_dxt1_fit<<<grid, 128, 0, s>>>(v.rgb + v.frame_bytes * f0, v.frame_bytes, v.w, v.bw, v.nb,
+                                  v.init_blocks + (size_t)f0 * v.nb, v.final_blocks + (size_t)f0 * v.nb, fstride);
 }
 
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
@@ -516,13 +518,14 @@ void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, 
   k_intra_wavefront<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, n_gops, sa, thr, ticket);
 }
 
-void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, cudaStream_t s) {
-  k_compact_unique<<<v.count, 1024, 0, s>>>(v, sa, cand_counts);
+void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, int f0, int fstride, int nf,
+                           cudaStream_t s) {
+  k_compact_unique<<<nf, 1024, 0, s>>>(v, sa, cand_counts, f0, fstride);
 }
 
-void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, cudaStream_t s) {
-  dim3 grid((pbw / 64) * (pbh / 64), 6, v.count);
-  k_endpoint_planes<<<grid, 1024, 0, s>>>(v, pbw, pbh);
+void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s) {
+  dim3 grid((pbw / 64) * (pbh / 64), 6, nf);
+  k_endpoint_planes<<<grid, 1024, 0, s>>>(v, pbw, pbh, f0, fstride);
 }
 
 int intra_wavefront_max_ctas(int device) {

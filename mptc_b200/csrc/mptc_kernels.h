@@ -32,7 +32,8 @@ void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int
                          cudaStream_t s);
 
 cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
-void launch_dxt1_fit(const SeqView &v, cudaStream_t s);
+// K1/K4/K5 run over frames f0, f0 + fstride, ... (nf of them).
+void launch_dxt1_fit(const SeqView &v, int f0, int fstride, int nf, cudaStream_t s);
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
 bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                                   int grid_cap, cudaStream_t s);
@@ -41,8 +42,9 @@ bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int s
 // frame busy, and idle CTAs would block the SMs for kernels of other lanes.
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                             int max_ctas, int grid_cap, cudaStream_t s);
-void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, cudaStream_t s);
-void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, cudaStream_t s);
+void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, int f0, int fstride, int nf,
+                           cudaStream_t s);
+void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s);
 int intra_wavefront_max_ctas(int device);
 
 }  // namespace mptc

@@ -37,7 +37,51 @@ KEYS = [
 ]
 
 
+JSON_KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "launch__grid_size", "launch__block_size",
+             "launch__registers_per_thread", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+             "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+             "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+             "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
+UNIT_SCALE = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+
+
+def to_json(rep, frames_per_launch, source):
+    """--json: counters of the longest launch of each search kernel -> profiles/ncu_counters.json
+    (bench.py's roofline.traffic / roofline.ncu)."""
+    import json
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    name_col = hdr.index("Kernel Name")
+    best = {}
+    for r in rows[2:]:
+        d = {h: (u, v) for h, u, v in zip(hdr, units, r)}
+        stage = "inter" if "k_inter_search" in r[name_col] else ("intra" if "k_intra_wavefront" in r[name_col] else None)
+        if stage is None:
+            continue
+        t = float(d["gpu__time_duration.sum"][1].replace(",", ""))
+        if stage in best and best[stage][0] >= t:
+            continue
+        o = {"kernel": r[name_col].split("(")[0], "frames_per_launch": frames_per_launch, "source": source}
+        for k in JSON_KEYS:
+            if k in d:
+                u, v = d[k]
+                x = float(v.replace(",", ""))
+                if k.startswith("dram__bytes"):
+                    x *= UNIT_SCALE.get(u, 1.0)
+                    u = "byte"
+                o[k] = x
+                o[k + ".unit"] = u
+        o["dram_bytes_per_frame"] = (o.get("dram__bytes_read.sum", 0.0) + o.get("dram__bytes_write.sum", 0.0)) / frames_per_launch
+        best[stage] = (t, o)
+    print(json.dumps({k: v[1] for k, v in best.items()}, indent=1))
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[2] == "--json":
+        to_json(sys.argv[1], int(sys.argv[3]) if len(sys.argv) > 3 else 2, sys.argv[4] if len(sys.argv) > 4 else sys.argv[1])
+        return
     rep = sys.argv[1]
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
