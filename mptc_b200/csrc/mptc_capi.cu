@@ -227,7 +227,8 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
   const int fk = L.f0 + k;
   const size_t nb = (size_t)c->nb;
   SeqView v = view_of(c, L.f0, L.n, gop);
-  cudaStream_t s = L.s, t = L.t;
+  // an explicitly requested single lane serialises everything (profiling: no kernel overlaps another)
+  cudaStream_t s = L.s, t = c->lanes_wanted == 1 ? L.s : L.t;
   if (io && io->frames) {
     CU(c, copy_strided(c->d_rgb + c->frame_bytes * fk, io->frames + c->frame_bytes * (size_t)(fk - call_first),
                        c->frame_bytes, c->frame_bytes * gop, nf, cudaMemcpyHostToDevice, c->s_h2d));

@@ -65,24 +65,40 @@ void RangeEncoder::encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t>
       base <<= 8;
     } while ((length <<= 8) < kMinLength);
   };
+  const uint32_t *const dist = dist_.data();
+  uint32_t *const count = count_.data();
+  uint32_t until = until_;                  // locals: the byte stores below may alias members
   for (size_t i = 0; i < n; ++i) {          // Arithmetic_Codec::encode (:360-387)
     const uint32_t s = sym[i], before = base;
     uint32_t x;
     if (s == last) {
-      x = dist_[s] * (length >> kLengthShift);
+      x = dist[s] * (length >> kLengthShift);
       base += x;
       length -= x;
     } else {
       length >>= kLengthShift;
-      x = dist_[s] * length;
+      x = dist[s] * length;
       base += x;
-      length = dist_[s + 1] * length - x;
+      length = dist[s + 1] * length - x;
     }
     if (before > base) carry();
-    if (length < kMinLength) renorm();
-    ++count_[s];
-    if (--until_ == 0) update_model();
+    // renorm_enc_interval without the data-dependent loop: every symbol keeps a range of at least
+    // one model unit, so length >= 2^9 here and at most two bytes leave; the byte count comes from
+    // the leading zeros, both candidate bytes are stored unconditionally (the buffer has slack and
+    // bytes past p are rewritten before they count).
+    const unsigned nsh = (unsigned)__builtin_clz(length) >> 3;
+    p[0] = (uint8_t)(base >> 24);
+    p[1] = (uint8_t)(base >> 16);
+    p += nsh;
+    base <<= 8 * nsh;
+    length <<= 8 * nsh;
+    ++count[s];
+    if (--until == 0) {
+      update_model();
+      until = until_;
+    }
   }
+  until_ = until;
   const uint32_t before = base;             // stop_encoder (:547-571)
   if (length > 2 * kMinLength) {
     base += kMinLength;
