@@ -40,7 +40,16 @@ sys.path.insert(0, ROOT)
 W, H, FRAMES, SA, THR, GOP = 1920, 1080, 60, 16, 50, 15
 ALGO_SLOTS_PER_CANDIDATE = 360
 SM_COUNT, SCHEDULERS, LANES = 148, 4, 32
-WORKLOAD = f"{W}x{H} synthetic x{FRAMES} frames/GPU, search_area={SA}, err_threshold={THR}, gop={GOP}"
+WORKLOAD = ""
+# BASELINE.json configs: [1] is the default (the headline); [2] = 4K x120 with the host coder overlapped
+WORKLOADS = {"1080p60": (1920, 1080, 60), "4k120": (3840, 2160, 120)}
+
+
+def set_workload(name: str, sa: int, thr: int):
+    global W, H, FRAMES, SA, THR, WORKLOAD
+    W, H, FRAMES = WORKLOADS[name]
+    SA, THR = sa, thr
+    WORKLOAD = f"{W}x{H} synthetic x{FRAMES} frames/GPU, search_area={SA}, err_threshold={THR}, gop={GOP}"
 METRIC = "mptc_encode_mpixel_per_s"
 UNIT = "Mpixel/s"
 
@@ -114,7 +123,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 def cpu_sample_frames(cores: int):
     """Bounded sample of the workload: per host core one 2-frame GOP (intra + inter) of a
-    512x512 crop of the 1080p sequence, each core a different crop / GOP."""
+    512x512 crop of the sequence, each core a different crop / GOP."""
     from mptc_b200.synth import make_frame
     crops = []
     for t in range(cores):
@@ -169,7 +178,7 @@ def cpu_baseline(steps: int = 1):
     times = [run_cpu_sample(crops, kind) for _ in range(steps)]
     t = float(np.mean(times))
     return {"value": pix / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{cores} threads x one 2-frame GOP (intra+inter) of a 512x512 crop of the 1080p sequence, "
+            "sample": f"{cores} threads x one 2-frame GOP (intra+inter) of a 512x512 crop of the {W}x{H} sequence, "
                       f"stages fit+search (DXTImage ctor + Reencode), sa={SA} thr={THR}; {t:.2f} s/step"}, times
 
 
@@ -374,7 +383,7 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "sharding": f"gop-sharded x{world}, no collective",
-                   "l2": "inputs (373 MB RGB per step) exceed the 126 MB L2; no explicit flush"},
+                   "l2": f"inputs ({frames.nbytes // 1000000} MB RGB per step) exceed the 126 MB L2; no explicit flush"},
         "wall_ms_per_step": wall_ms,
         "e2e": {"value": pixels_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
@@ -396,7 +405,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mptc_b200", choices=["mptc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="1080p60", choices=sorted(WORKLOADS),
+                    help="1080p60 = BASELINE.json configs[1] (default, the headline); 4k120 = configs[2]")
+    ap.add_argument("--search-area", type=int, default=SA)
+    ap.add_argument("--err-threshold", type=int, default=THR)
     args = ap.parse_args()
+    set_workload(args.workload, args.search_area, args.err_threshold)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
