@@ -59,7 +59,8 @@ struct mptc_gpu_ctx {
   int lanes_used = 0;
   int enc_first = 0, enc_count = 0, enc_gop = 1;   // the last encode call
   bool enc_host_out = false;
-  int sparse_ctas = 48;          // K3s CTAs per frame
+  int sparse_ctas = 0;           // K3s CTAs per frame; 0 = automatic
+  int sparse_max_pct = 50;       // K3s takes inter frames with up to this share of leftover blocks
   int wave_rows_intra = 0, wave_rows_inter = 0;   // CTAs per frame of the intra wavefront; 0 = default
   uint64_t launches = 0;
   void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // result staging of mptc_encode_stream
@@ -247,7 +248,12 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
   }
   {
     StageEvent &e = stage_begin(L, 3, s);
-    if (k > 0) launch_intra_sparse(v, k, L.n_gops, sa, thr, L.d_tickets + gop + k * L.n_gops, c->sparse_ctas, s);
+    if (k > 0) {
+      int ctas = c->sparse_ctas;
+      if (ctas <= 0) { ctas = 592 / L.n_gops; ctas = ctas < 16 ? 16 : (ctas > 148 ? 148 : ctas); }
+      const int max_items = (int)((long long)c->nb * c->sparse_max_pct / 100);
+      launch_intra_sparse(v, k, L.n_gops, sa, thr, L.d_tickets + gop + k * L.n_gops, ctas, max_items, s);
+    }
     launch_intra_wavefront(v, k, L.n_gops, sa, thr, L.d_tickets + k, c->max_wave_ctas, wave_rows * L.n_gops, s);
     stage_end(c, e, s, k > 0 ? 2 : 1);
   }
@@ -377,8 +383,9 @@ int mptc_gpu_create(int device, mptc_gpu_ctx **out) {
   c->lanes_wanted = env_int("MPTC_LANES", 0);
   c->wave_rows_intra = env_int("MPTC_WAVE_ROWS_INTRA", 0);
   c->wave_rows_inter = env_int("MPTC_WAVE_ROWS_INTER", 0);
-  c->sparse_ctas = env_int("MPTC_SPARSE_CTAS", 48);
-  if (c->sparse_ctas < 1) c->sparse_ctas = 1;
+  c->sparse_ctas = env_int("MPTC_SPARSE_CTAS", 0);
+  c->sparse_max_pct = env_int("MPTC_SPARSE_MAX_PCT", 50);
+  if (c->sparse_max_pct < 0) c->sparse_max_pct = 0;
   *out = c;
   return MPTC_OK;
 }

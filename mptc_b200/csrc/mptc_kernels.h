@@ -24,12 +24,11 @@ struct SeqView {
   int gop;
 };
 
-// Inter frames: K3s (mptc_sparse.cu) handles frames with at most kSparseMaxItems leftover blocks
-// and tells the row wavefront through n_unique[f] (0xFFFFFFFF = not handled, take the frame).
-constexpr int kSparseMaxItems = 2048;
+// Inter frames: K3s (mptc_sparse.cu) handles frames with at most max_items leftover blocks and
+// tells the row wavefront through n_unique[f] (0xFFFFFFFF = not handled, take the frame).
 constexpr uint32_t kSparseNotHandled = 0xFFFFFFFFu;
 void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
-                         cudaStream_t s);
+                         int max_items, cudaStream_t s);
 
 cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
 // K1/K4/K5 run over frames f0, f0 + fstride, ... (nf of them).

@@ -84,3 +84,30 @@ def test_overlapped_stream_equals_two_phase_assembly(ctx, threads):
     assert stream == two_phase
     assert st.n_groups == 2 and st.total_ms >= st.entropy_ms > 0 and st.gpu_ms > 0
     assert (st.max_comp_motion, st.max_comp_ep_y, st.max_comp_ep_c) == (st2.max_comp_motion, st2.max_comp_ep_y, st2.max_comp_ep_c)
+
+
+@pytest.mark.parametrize("max_pct", [0, 100])
+@pytest.mark.parametrize("sa,thr", [(4, 0), (16, 0), (2, 50), (20, 5)])
+def test_leftover_paths_bit_exact(max_pct, sa, thr, monkeypatch):
+    """Inter frames with MANY leftover blocks (thr 0 / tiny windows), forced through the per-block
+    kernel K3s (max_pct 100: never hands a frame to the wavefront; sa 20 takes its position-by-
+    position path) and through the row wavefront K3 (max_pct 0) -- both equal the oracle."""
+    monkeypatch.setenv("MPTC_SPARSE_MAX_PCT", str(max_pct))
+    c = capi.Context(0)
+    try:
+        w, h, n, gop = 256, 192, 6, 3
+        frames = make_sequence(w, h, n, seed=33)
+        ref = oracle_sequence(frames, sa, thr, gop)
+        out = c.encode_sequence(frames, sa, thr, gop)
+        left = 0
+        for i in range(n):
+            blocks, motion, unique = ref[i]
+            assert np.array_equal(out["blocks"][i], blocks), f"frame {i}"
+            assert np.array_equal(out["motion"][i], motion), f"frame {i}"
+            assert int(out["n_unique"][i]) == unique.size
+            if i % gop:
+                m = motion.reshape(-1, 2)
+                left += int(((m[:, 0] & 0x80) == 0).sum() + ((m[:, 0] == 255) & (m[:, 1] == 255)).sum())
+        assert left > 0, "the case must exercise the leftover path"
+    finally:
+        c.close()
