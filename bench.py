@@ -356,6 +356,12 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     algo_bytes = frames_k * nb * (72 + 20 + 14)
     # DRAM bytes per launch from the committed ncu --set full capture (per frame x frames per launch)
     ev = ncu_evidence(dominant)
+    if ev:   # keep the bench line readable: the counters DESIGN.md cites, not the whole capture
+        keep = ("kernel", "frames_per_launch", "source", "gpu__time_duration.sum", "dram_bytes_per_frame",
+                "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+                "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+        ev = {k: ev[k] for k in keep if k in ev}
     traffic = ev["dram_bytes_per_frame"] * n_gops if ev and "dram_bytes_per_frame" in ev else None
     roofline = {
         "kernel": "k_inter_search_tiled" if dominant == "inter" else "k_intra_wavefront_tiled",

@@ -17,7 +17,9 @@ constexpr uint32_t kMinLength = 0x01000000u;   // renormalisation threshold (AC_
 constexpr unsigned kLengthShift = 15;          // DM__LengthShift
 }  // namespace
 
-RangeEncoder::RangeEncoder(unsigned symbols) : n_(symbols), dist_(symbols), count_(symbols) {}
+// Byte symbols must never be the model's last symbol (step() codes the general branch only).
+RangeEncoder::RangeEncoder(unsigned symbols)
+    : n_(symbols < 257 ? 257 : symbols), dist_(n_), count_(n_) {}
 
 // Adaptive_Data_Model::reset (arithmetic_codec.cpp:818-829)
 void RangeEncoder::reset_model() {
@@ -46,70 +48,103 @@ void RangeEncoder::update_model() {
   until_ = cycle_;
 }
 
-void RangeEncoder::encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out) {
+// Coder state kept in locals while symbols are coded: the byte stores may alias the members.
+struct RangeEncoder::State {
+  uint32_t base, length, until;
+  uint8_t *p, *buf;
+  const uint32_t *dist;
+  uint32_t *count;
+};
+
+inline void RangeEncoder::begin(State &e, size_t n, std::vector<uint8_t> &out, size_t &start) {
   reset_model();
-  const size_t start = out.size();
+  start = out.size();
   out.resize(start + 2 * n + 16);   // an adaptive-model symbol never costs more than 15 bits
-  uint8_t *const buf = out.data() + start;
-  uint8_t *p = buf;
-  uint32_t base = 0, length = 0xFFFFFFFFu;
-  const uint32_t last = n_ - 1;
-  auto carry = [&]() {                      // propagate_carry (:81-86)
-    uint8_t *q = p - 1;
-    while (*q == 0xFFu) *q-- = 0;
-    ++*q;
-  };
-  auto renorm = [&]() {                     // renorm_enc_interval (:90-96)
-    do {
-      *p++ = (uint8_t)(base >> 24);
-      base <<= 8;
-    } while ((length <<= 8) < kMinLength);
-  };
-  const uint32_t *const dist = dist_.data();
-  uint32_t *const count = count_.data();
-  uint32_t until = until_;                  // locals: the byte stores below may alias members
-  for (size_t i = 0; i < n; ++i) {          // Arithmetic_Codec::encode (:360-387)
-    const uint32_t s = sym[i], before = base;
-    uint32_t x;
-    if (s == last) {
-      x = dist[s] * (length >> kLengthShift);
-      base += x;
-      length -= x;
-    } else {
-      length >>= kLengthShift;
-      x = dist[s] * length;
-      base += x;
-      length = dist[s + 1] * length - x;
-    }
-    if (before > base) carry();
-    // renorm_enc_interval without the data-dependent loop: every symbol keeps a range of at least
-    // one model unit, so length >= 2^9 here and at most two bytes leave; the byte count comes from
-    // the leading zeros, both candidate bytes are stored unconditionally (the buffer has slack and
-    // bytes past p are rewritten before they count).
-    const unsigned nsh = (unsigned)__builtin_clz(length) >> 3;
-    p[0] = (uint8_t)(base >> 24);
-    p[1] = (uint8_t)(base >> 16);
-    p += nsh;
-    base <<= 8 * nsh;
-    length <<= 8 * nsh;
-    ++count[s];
-    if (--until == 0) {
-      update_model();
-      until = until_;
-    }
+  e.buf = e.p = out.data() + start;
+  e.base = 0;
+  e.length = 0xFFFFFFFFu;
+  e.until = until_;
+  e.dist = dist_.data();
+  e.count = count_.data();
+}
+
+// propagate_carry (arithmetic_codec.cpp:81-86)
+static inline void carry(uint8_t *p) {
+  uint8_t *q = p - 1;
+  while (*q == 0xFFu) *q-- = 0;
+  ++*q;
+}
+
+// Arithmetic_Codec::encode (arithmetic_codec.cpp:360-387) for one byte symbol (never the model's
+// last symbol, 256, so only the general branch of :366-376 is needed).
+inline void RangeEncoder::step(State &e, uint32_t s) {
+  const uint32_t before = e.base;
+  const uint32_t len = e.length >> kLengthShift;
+  const uint32_t x = e.dist[s] * len;
+  e.base += x;
+  e.length = e.dist[s + 1] * len - x;
+  if (before > e.base) carry(e.p);
+  // renorm_enc_interval (:90-96) without the data-dependent loop: every symbol keeps a range of at
+  // least one model unit, so length >= 2^9 here and at most two bytes leave; the byte count comes
+  // from the leading zeros, both candidate bytes are stored unconditionally (the buffer has slack
+  // and bytes past p are rewritten before they count).
+  const unsigned nsh = (unsigned)__builtin_clz(e.length) >> 3;
+  e.p[0] = (uint8_t)(e.base >> 24);
+  e.p[1] = (uint8_t)(e.base >> 16);
+  e.p += nsh;
+  e.base <<= 8 * nsh;
+  e.length <<= 8 * nsh;
+  ++e.count[s];
+  if (--e.until == 0) {
+    update_model();
+    e.until = until_;
   }
-  until_ = until;
-  const uint32_t before = base;             // stop_encoder (:547-571)
-  if (length > 2 * kMinLength) {
-    base += kMinLength;
-    length = kMinLength >> 1;
+}
+
+// stop_encoder (arithmetic_codec.cpp:547-571)
+inline void RangeEncoder::finish(State &e, std::vector<uint8_t> &out, size_t start) {
+  until_ = e.until;
+  const uint32_t before = e.base;
+  if (e.length > 2 * kMinLength) {
+    e.base += kMinLength;
+    e.length = kMinLength >> 1;
   } else {
-    base += kMinLength >> 1;
-    length = kMinLength >> 9;
+    e.base += kMinLength >> 1;
+    e.length = kMinLength >> 9;
   }
-  if (before > base) carry();
-  renorm();
-  out.resize(start + (size_t)(p - buf));
+  if (before > e.base) carry(e.p);
+  do {                                      // renorm_enc_interval
+    *e.p++ = (uint8_t)(e.base >> 24);
+    e.base <<= 8;
+  } while ((e.length <<= 8) < kMinLength);
+  out.resize(start + (size_t)(e.p - e.buf));
+}
+
+void RangeEncoder::encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out) {
+  State e;
+  size_t start;
+  begin(e, n, out, start);
+  for (size_t i = 0; i < n; ++i) step(e, sym[i]);
+  finish(e, out, start);
+}
+
+// Two independent streams in one loop: the coder is a chain of dependent multiplies and shifts
+// (~10 cycles per symbol), so a second chain in flight nearly doubles a thread's throughput.
+void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, std::vector<uint8_t> &oa,
+                               RangeEncoder &mb, const uint8_t *sb, size_t nb, std::vector<uint8_t> &ob) {
+  State a, b;
+  size_t start_a, start_b;
+  ma.begin(a, na, oa, start_a);
+  mb.begin(b, nb, ob, start_b);
+  const size_t both = na < nb ? na : nb;
+  for (size_t i = 0; i < both; ++i) {
+    ma.step(a, sa[i]);
+    mb.step(b, sb[i]);
+  }
+  for (size_t i = both; i < na; ++i) ma.step(a, sa[i]);
+  for (size_t i = both; i < nb; ++i) mb.step(b, sb[i]);
+  ma.finish(a, oa, start_a);
+  mb.finish(b, ob, start_b);
 }
 
 namespace {
@@ -212,6 +247,42 @@ struct StreamPlan {
     enc.encode_all(jobs[i].sym, jobs[i].n, jobs[i].out);
   }
 
+  // One task = one or two jobs coded by one thread in an interleaved loop (RangeEncoder::encode_pair).
+  struct Task { int a, b; };                    // b < 0: single job
+  void encode_task(const Task &t) {
+    if (t.b < 0) { encode_job(t.a); return; }
+    RangeEncoder ea, eb;
+    RangeEncoder::encode_pair(ea, jobs[t.a].sym, jobs[t.a].n, jobs[t.a].out, eb, jobs[t.b].sym, jobs[t.b].n, jobs[t.b].out);
+  }
+  // Tasks in the order their inputs arrive from the GPU (frame k of every group, then k + 1, ...):
+  // per frame the two Y planes and the two Co|Cg planes pair up (equal lengths), motion streams
+  // pair across two groups; a group's palette follows its last frame.
+  std::vector<Task> tasks_in_arrival_order() const {
+    std::vector<Task> t;
+    t.reserve(jobs.size());
+    for (int k = 0; k < p.gop; ++k) {
+      int pending_motion = -1;
+      for (int g = 0; g < n_groups; ++g) {
+        const int f = g * p.gop + k;
+        if (pending_motion < 0) pending_motion = f * 5;
+        else { t.push_back({pending_motion, f * 5}); pending_motion = -1; }
+        t.push_back({f * 5 + 2, f * 5 + 4});
+        t.push_back({f * 5 + 1, f * 5 + 3});
+        if (k == p.gop - 1) t.push_back({n_used * 5 + g, -1});
+      }
+      if (pending_motion >= 0) t.push_back({pending_motion, -1});
+    }
+    return t;
+  }
+  // Frames a task's inputs come from: [first, last] of the jobs' frames (palette: the whole group).
+  void task_frames(const Task &t, int frames_out[2], int &n) const {
+    n = 0;
+    for (int j : {t.a, t.b}) {
+      if (j < 0) continue;
+      if (j < n_used * 5) frames_out[n++] = j / 5;
+    }
+  }
+
   void write(std::vector<uint8_t> &bytes, mptc_stream_stats &st) {
     memset(&st, 0, sizeof st);
     st.n_groups = (uint32_t)n_groups;
@@ -266,9 +337,14 @@ int mptc_frame_payload(const uint8_t *motion, size_t nb, const uint8_t *planes, 
   if (!motion || !planes) return MPTC_E_ARG;
   StreamJob jobs[5];
   frame_jobs(motion, nb, planes, plane_syms, jobs);
-  parallel_for(5, threads, [&](int s) {
-    RangeEncoder enc;
-    enc.encode_all(jobs[s].sym, jobs[s].n, jobs[s].out);
+  parallel_for(3, threads, [&](int t) {   // motion alone; the equal-length plane pairs interleaved
+    if (t == 0) {
+      RangeEncoder enc;
+      enc.encode_all(jobs[0].sym, jobs[0].n, jobs[0].out);
+    } else {
+      RangeEncoder ea, eb;
+      RangeEncoder::encode_pair(ea, jobs[t].sym, jobs[t].n, jobs[t].out, eb, jobs[t + 2].sym, jobs[t + 2].n, jobs[t + 2].out);
+    }
   });
   std::vector<uint8_t> bytes;
   append_frame_payload(bytes, n_unique, jobs);
@@ -286,7 +362,8 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
   const auto t0 = std::chrono::steady_clock::now();
   StreamPlan plan(n_frames, w, h, *p, motion, unique, n_unique, planes);
   for (int g = 0; g < plan.n_groups; ++g) plan.build_palette(g);
-  parallel_for((int)plan.jobs.size(), threads, [&](int i) { plan.encode_job(i); });
+  const std::vector<StreamPlan::Task> tasks = plan.tasks_in_arrival_order();
+  parallel_for((int)tasks.size(), threads, [&](int i) { plan.encode_task(tasks[i]); });
   mptc_stream_stats st;
   std::vector<uint8_t> bytes;
   plan.write(bytes, st);
@@ -323,30 +400,23 @@ int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, i
     r = mptc_gpu_encode_sequence_async(ctx, frames, n_frames, w, h, p, nullptr, motion, unique, n_unique, planes);
     if (r == MPTC_OK) {
       StreamPlan plan(n_frames, w, h, *p, motion, unique, n_unique, planes);
-      // jobs in the order their inputs arrive: frame k of every group, then k+1, ...; a group's
-      // palette right after its last frame
-      std::vector<int> order;
-      order.reserve(plan.jobs.size());
-      for (int k = 0; k < p->gop; ++k)
-        for (int g = 0; g < plan.n_groups; ++g) {
-          const int f = g * p->gop + k;
-          for (int s = 0; s < 5; ++s) order.push_back(f * 5 + s);
-          if (k == p->gop - 1) order.push_back(plan.n_used * 5 + g);
-        }
+      const std::vector<StreamPlan::Task> tasks = plan.tasks_in_arrival_order();
       std::atomic<int> failed(MPTC_OK);
       const auto t1 = std::chrono::steady_clock::now();
-      parallel_for_ordered((int)order.size(), threads, [&](int i) {
-        const int j = order[i];
+      parallel_for_ordered((int)tasks.size(), threads, [&](int i) {
+        const StreamPlan::Task &t = tasks[i];
         int wr = MPTC_OK;
-        if (j < plan.n_used * 5) {
-          wr = mptc_gpu_wait_frame(ctx, j / 5);
-        } else {
-          const int g = j - plan.n_used * 5;
+        if (t.a >= plan.n_used * 5) {          // palette: needs every frame of its group
+          const int g = t.a - plan.n_used * 5;
           for (int f = g * p->gop; f < (g + 1) * p->gop && wr == MPTC_OK; ++f) wr = mptc_gpu_wait_frame(ctx, f);
           if (wr == MPTC_OK) plan.build_palette(g);
+        } else {
+          int fr[2], nf;
+          plan.task_frames(t, fr, nf);
+          for (int q = 0; q < nf && wr == MPTC_OK; ++q) wr = mptc_gpu_wait_frame(ctx, fr[q]);
         }
         if (wr != MPTC_OK) { failed.store(wr); return; }
-        plan.encode_job(j);
+        plan.encode_task(t);
       });
       r = failed.load();
       const int wr = mptc_gpu_wait(ctx);   // also frames beyond the last full group

@@ -13,8 +13,15 @@ class RangeEncoder {
   explicit RangeEncoder(unsigned symbols = 257);
   // Appends the code bytes of `sym[0..n)` (fresh model, start .. stop) to `out`.
   void encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out);
+  // Two independent streams coded in one interleaved loop (each with its own model / encoder).
+  static void encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, std::vector<uint8_t> &oa,
+                          RangeEncoder &mb, const uint8_t *sb, size_t nb, std::vector<uint8_t> &ob);
 
  private:
+  struct State;
+  void begin(State &e, size_t n, std::vector<uint8_t> &out, size_t &start);
+  void step(State &e, uint32_t s);
+  void finish(State &e, std::vector<uint8_t> &out, size_t start);
   void reset_model();
   void update_model();
   unsigned n_;
