@@ -102,45 +102,62 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   if (tid == 0) { s_count = 0; s_special = 0; }
   __syncthreads();
 
-  // ---- phase 1: load the union window, insert its words -------------------------------------
+  // ---- phase 1: load the union window (all loads of a thread first, so their latencies overlap),
+  // this lane's target block, then insert the words --------------------------------------------
   const uint32_t hmask = (uint32_t)HT - 1u;
   const int hshift = 32 - __ffs(HT) + 1;   // HT = 2^(ffs-1)
-  for (int p = tid; p < NP; p += kThreads) {
-    const int ur = p / UW, uc = p - ur * UW;
-    const int i = ux0 + uc, j = uy0 + ur;
-    uint16_t slot = kNoPos;
-    if (i >= 0 && j >= 0 && i < v.bw && j < v.bh) {
-      const uint32_t word = (uint32_t)(__ldg(prev + (size_t)j * v.bw + i) >> 32);
-      sm.win[p] = word;
-      if (word == kEmpty) {
-        s_special = 1;
-        slot = (uint16_t)HT;
-      } else {
-        uint32_t h = (word * 0x9E3779B1u) >> hshift;
-        for (;;) {
-          const uint32_t old = atomicCAS(&sm.keys[h], kEmpty, word);
-          if (old == kEmpty || old == word) break;
-          h = (h + 1u) & hmask;
-        }
-        slot = (uint16_t)h;
-      }
-    }
-    sm.pos_uid[p] = slot;
-  }
+  const uint32_t uw_magic = 0xFFFFFFFFu / (uint32_t)UW + 1u;   // p / UW == umulhi(p, magic) for p < 2^16
 
   // this lane's target block (every warp holds the same 32 targets)
   const int tbx = tx0 + (lane & (kTileX - 1)), tby = ty0 + (lane >> 3);
   const bool t_valid = tbx < v.bw && tby < v.bh;
   const int tb = tby * v.bw + tbx;
   LaneTarget t;
-  if (t_valid) {
-    load_lane_target(t, v.rgb + v.frame_bytes * f, v.w, tbx, tby, v.init_blocks[(size_t)f * v.nb + tb]);
-  } else {
+  for (int p0 = 0; p0 < NP; p0 += 8 * kThreads) {
+    uint32_t wv[8];
+    bool ok[8];
 #pragma unroll
-    for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+    for (int q = 0; q < 8; ++q) {
+      const int p = p0 + q * kThreads + tid;
+      const int ur = (int)__umulhi((uint32_t)p, uw_magic), uc = p - ur * UW;
+      const int i = ux0 + uc, j = uy0 + ur;
+      ok[q] = p < NP && i >= 0 && j >= 0 && i < v.bw && j < v.bh;
+      wv[q] = ok[q] ? (uint32_t)(__ldg(prev + (size_t)j * v.bw + i) >> 32) : 0u;
+    }
+    if (p0 == 0) {   // the target's pixel loads go out behind the first batch of window loads
+      if (t_valid) {
+        load_lane_target(t, v.rgb + v.frame_bytes * f, v.w, tbx, tby, v.init_blocks[(size_t)f * v.nb + tb]);
+      } else {
 #pragma unroll
-    for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
-    t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+        for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
+        t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int p = p0 + q * kThreads + tid;
+      if (p >= NP) break;
+      uint16_t slot = kNoPos;
+      if (ok[q]) {
+        const uint32_t word = wv[q];
+        sm.win[p] = word;
+        if (word == kEmpty) {
+          s_special = 1;
+          slot = (uint16_t)HT;
+        } else {
+          uint32_t h = (word * 0x9E3779B1u) >> hshift;
+          for (;;) {
+            const uint32_t old = atomicCAS(&sm.keys[h], kEmpty, word);
+            if (old == kEmpty || old == word) break;
+            h = (h + 1u) & hmask;
+          }
+          slot = (uint16_t)h;
+        }
+      }
+      sm.pos_uid[p] = slot;
+    }
   }
   __syncthreads();
 
