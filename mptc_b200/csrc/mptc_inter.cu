@@ -143,14 +143,25 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
       if (ok[q]) {
         const uint32_t word = wv[q];
         sm.win[p] = word;
+        // the thread that claims a slot also hands out the word's dense id
         if (word == kEmpty) {
-          s_special = 1;
+          if (atomicExch(&s_special, 1) == 0) {
+            const int uid = atomicAdd(&s_count, 1);
+            sm.slot_uid[HT] = (uint16_t)uid;
+            sm.ulist[uid] = kEmpty;
+          }
           slot = (uint16_t)HT;
         } else {
           uint32_t h = (word * 0x9E3779B1u) >> hshift;
           for (;;) {
             const uint32_t old = atomicCAS(&sm.keys[h], kEmpty, word);
-            if (old == kEmpty || old == word) break;
+            if (old == kEmpty) {
+              const int uid = atomicAdd(&s_count, 1);
+              sm.slot_uid[h] = (uint16_t)uid;
+              sm.ulist[uid] = word;
+              break;
+            }
+            if (old == word) break;
             h = (h + 1u) & hmask;
           }
           slot = (uint16_t)h;
@@ -161,16 +172,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   }
   __syncthreads();
 
-  // ---- phase 2: dense ids for the distinct words ----------------------------------------------
-  for (int s = tid; s <= HT; s += kThreads) {
-    const bool occ = (s < HT) ? (sm.keys[s] != kEmpty) : (s_special != 0);
-    if (occ) {
-      const int uid = atomicAdd(&s_count, 1);
-      sm.slot_uid[s] = (uint16_t)uid;
-      sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;
-    }
-  }
-  __syncthreads();
+  // ---- phase 2: position -> dense word id ------------------------------------------------------
   const int U = s_count;
   for (int p = tid; p < NP; p += kThreads) {
     const uint16_t slot = sm.pos_uid[p];

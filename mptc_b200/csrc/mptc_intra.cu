@@ -80,16 +80,28 @@ __host__ __device__ inline size_t group_smem_bytes(int sa, int *np_out, int *ht_
   return (b + 15) & ~(size_t)15;
 }
 
+// Inserts `word` into the open-addressing set; the thread that claims a slot also hands out the
+// word's dense id (ids >= kMaxWords only count: the group then takes the direct path).
 __device__ __forceinline__ uint16_t wordset_insert(uint32_t *keys, uint32_t hmask, int hshift, int HT, int *special,
-                                                   uint32_t word) {
+                                                   int *count, uint16_t *slot_uid, uint32_t *ulist, uint32_t word) {
   if (word == kEmpty) {
-    *special = 1;
+    if (atomicExch(special, 1) == 0) {
+      const int uid = atomicAdd(count, 1);
+      slot_uid[HT] = (uint16_t)uid;
+      if (uid < kMaxWords) ulist[uid] = kEmpty;
+    }
     return (uint16_t)HT;
   }
   uint32_t h = (word * 0x9E3779B1u) >> hshift;
   for (;;) {
     const uint32_t old = atomicCAS(&keys[h], kEmpty, word);
-    if (old == kEmpty || old == word) break;
+    if (old == kEmpty) {
+      const int uid = atomicAdd(count, 1);
+      slot_uid[h] = (uint16_t)uid;
+      if (uid < kMaxWords) ulist[uid] = word;
+      break;
+    }
+    if (old == word) break;
     h = (h + 1u) & hmask;
   }
   return (uint16_t)h;
@@ -249,33 +261,25 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             ok[q] = valid;
             wv[q] = valid ? ldcg_word(cur, (size_t)j * v.bw + i) : 0u;
           }
+          if (p0 == 0) {   // the target's pixel loads go out behind the first batch of window loads
+            if (in_row) {
+              load_lane_target(t, frame, v.w, gx, by, init[(size_t)by * v.bw + gx]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
+              t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int p = p0 + q * kThreads + tid;
-            if (p < NP) sm.pos_uid[p] = ok[q] ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, wv[q]) : kNone;
+            if (p < NP) sm.pos_uid[p] = ok[q] ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, &s_count, sm.slot_uid, sm.ulist, wv[q]) : kNone;
           }
-        }
-        if (in_row) {
-          load_lane_target(t, frame, v.w, gx, by, init[(size_t)by * v.bw + gx]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
-          t.own_block = 0; t.own_word = 0; t.orig_err = 0;
         }
         __syncthreads();
 
-        // ---- dense ids ----------------------------------------------------------------------------
-        for (int s = tid; s <= HT; s += kThreads) {
-          const bool occ = (s < HT) ? (sm.keys[s] != kEmpty) : (s_special != 0);
-          if (occ) {
-            const int uid = atomicAdd(&s_count, 1);
-            sm.slot_uid[s] = (uint16_t)uid;
-            if (uid < kMaxWords) sm.ulist[uid] = (s < HT) ? sm.keys[s] : kEmpty;   // more: direct path
-          }
-        }
-        __syncthreads();
         U = s_count;
         PHASE_MARK(2);   // window load + hash + ids
       }
