@@ -446,6 +446,9 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         // 32 targets.  hslot = its free hash slot (lane `leader`'s value counts), HT for 0xFFFFFFFF.
         auto add_word = [&](uint32_t word, int hslot, int leader) {
           const int uid = U++;
+#ifdef MPTC_PHASE_TIMING
+          if (lane == 0) atomicAdd(&g_phase_cycles[12], 1ull);
+#endif
           if (lane == leader) {
             if (word == kEmpty) { s_special = 1; sm.slot_uid[HT] = (uint16_t)uid; }
             else { sm.keys[hslot] = word; sm.slot_uid[hslot] = (uint16_t)uid; }
@@ -479,16 +482,26 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         // Fetches what the near rows have published since, until target g's window is complete.
         // Returns false if the word table is full.
         auto near_update = [&](int g) -> bool {
+#ifdef MPTC_PHASE_TIMING
+          const long long nu_t0 = clock64();
+          struct NuTimer { long long t0; int lane; __device__ ~NuTimer() { if (lane == 0) { atomicAdd(&g_phase_cycles[13], (unsigned long long)(clock64() - t0)); atomicAdd(&g_phase_cycles[15], 1ull); } } } nu_timer{nu_t0, lane};
+#endif
 #pragma unroll
           for (int r = 0; r <= kNear; ++r) {
             const int need_g = r == 0 ? x0 : min(x0 + g + sa, v.bw);
             if (merged[r] >= need_g) continue;
             int p;
+#ifdef MPTC_PHASE_TIMING
+            const long long poll_t0 = clock64();
+#endif
             for (;;) {
               p = ld_acquire(progress + by - r);
               if (p >= need_g) break;
               __nanosleep(32);
             }
+#ifdef MPTC_PHASE_TIMING
+            if (lane == 0) atomicAdd(&g_phase_cycles[14], (unsigned long long)(clock64() - poll_t0));
+#endif
             p = min(p, r == 0 ? x0 : need);
             const int m0 = max(merged[r], max(x0 - sa, 0));
             const size_t rowbase = (size_t)(by - r) * v.bw;

@@ -29,3 +29,6 @@ groups = buf[11]
 print("intra ms", ctx.last_encode_ms("intra"), "groups", groups, "avg distinct words/group", buf[10] / max(groups, 1))
 for i, n in enumerate(names):
     print(f"{n:24s} {buf[i] / max(groups,1):10.0f} cycles/group  {100.0 * buf[i] / tot:5.1f}%")
+groups = max(groups, 1)
+print(f"decider detail per group: near_update calls {buf[15] / groups:.2f}, cycles in near_update {buf[13] / groups:.0f} "
+      f"(of which polling {buf[14] / groups:.0f}), words added late {buf[12] / groups:.2f}")
