@@ -566,6 +566,106 @@ int mptc_oracle_arith_encode(const uint8_t *sym, int n, uint8_t *out, int cap) {
   return nbytes <= cap ? nbytes : -nbytes;
 }
 
+/* Arithmetic_Codec::decode(Adaptive_Data_Model&) with start_decoder / renorm_dec_interval
+ * (entropy/arithmetic_codec.cpp:100-105, :391-444, :511-522), as driven by EntropyDecode
+ * (codec/codec.cpp:560-577).  The reference finds the symbol through its decoder table plus
+ * bisection (:399-414); any search for the s with dist[s] <= value/length < dist[s+1] gives the
+ * same symbol.  `code` must be readable up to code[nbytes + 3].  Returns 0, or -1 on overrun. */
+int mptc_oracle_arith_decode(const uint8_t *code, int nbytes, uint8_t *sym_out, int n) {
+  ac_model *m = (ac_model *)malloc(sizeof *m);
+  ac_model_init(m);
+  uint32_t length = 0xFFFFFFFFu;
+  const uint8_t *p = code + 3, *end = code + nbytes + 4;
+  uint32_t value = ((uint32_t)code[0] << 24) | ((uint32_t)code[1] << 16) | ((uint32_t)code[2] << 8) | code[3];
+  int rc = 0;
+  for (int i = 0; i < n; ++i) {
+    uint32_t y = length;
+    length >>= AC_SHIFT;
+    uint32_t dv = value / length, s = 0, hi = AC_SYMS;   /* largest s with dist[s] <= dv */
+    while (hi > s + 1) { uint32_t mid = (s + hi) >> 1; if (m->dist[mid] > dv) hi = mid; else s = mid; }
+    uint32_t x = m->dist[s] * length;
+    if (s != AC_SYMS - 1) y = m->dist[s + 1] * length;
+    value -= x;
+    length = y - x;
+    if (length < 0x01000000u)
+      do {
+        if (p + 1 >= end) { rc = -1; break; }
+        value = (value << 8) | *++p;
+      } while ((length <<= 8) < 0x01000000u);
+    if (rc) break;
+    ++m->count[s];
+    if (--m->until == 0) ac_model_update(m);
+    sym_out[i] = (uint8_t)s;
+  }
+  free(m);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Decoder side of the endpoint planes: ReconstructEndPoints (codec/codec.cpp:697-800) =
+ * MakeSigned (image_utils.h:243-266) -> IWavelet2D<.,64> (image_processing.h:337-399, levels
+ * dim = 2..64, InverseWavelet2D rows-then-columns wavelet.cpp:133-155, InverseWavelet1D :64-95)
+ * -> ycocg667_to_rgb565 (codec.cpp:46-63) -> 565 packing (:764-771).
+ * planes = 6 x pbw*pbh symbols as written by mptc_oracle_endpoint_planes; ep1/ep2 = bw*bh u16.
+ * ---------------------------------------------------------------------------------- */
+static void unlift53(const int16_t *src, int16_t *dst, int len) { /* InverseWavelet1D, even len >= 2 */
+  int mid = len - len / 2;
+  for (int i = 0; i < len; i += 2) {
+    int pv = (i == 0) ? 1 : i - 1;                        /* NormalizeIndex(-1) = 1 */
+    int nx = (i + 1 < len) ? i + 1 : 2 * len - 2 - (i + 1);
+    dst[i] = (int16_t)(src[i / 2] - (src[mid + pv / 2] + src[mid + nx / 2] + 2) / 4);
+  }
+  for (int i = 1; i < len; i += 2) {
+    int nx = (i + 1 < len) ? i + 1 : 2 * len - 2 - (i + 1);
+    dst[i] = (int16_t)(src[mid + i / 2] + (dst[i - 1] + dst[nx]) / 2);
+  }
+}
+
+static void inverse_wavelet_tile(int16_t t[64][64]) {
+  int16_t line[64], outl[64];
+  for (int dim = 2; dim <= 64; dim <<= 1) {
+    for (int r = 0; r < dim; ++r) { /* rows first (wavelet.cpp:141-144) */
+      memcpy(line, t[r], sizeof(int16_t) * dim);
+      unlift53(line, outl, dim);
+      memcpy(t[r], outl, sizeof(int16_t) * dim);
+    }
+    for (int c = 0; c < dim; ++c) { /* then columns (:148-152) */
+      for (int r = 0; r < dim; ++r) line[r] = t[r][c];
+      unlift53(line, outl, dim);
+      for (int r = 0; r < dim; ++r) t[r][c] = outl[r];
+    }
+  }
+}
+
+void mptc_oracle_inverse_planes(const uint8_t *planes, int bw, int bh, uint16_t *ep1, uint16_t *ep2) {
+  int pbw = (bw + 63) / 64 * 64, pbh = (bh + 63) / 64 * 64;
+  size_t pn = (size_t)pbw * pbh;
+  int16_t tile[3][64][64];
+  for (int ep = 0; ep < 2; ++ep) {
+    uint16_t *out = ep ? ep2 : ep1;
+    for (int ty = 0; ty < pbh; ty += 64)
+      for (int tx = 0; tx < pbw; tx += 64) {
+        for (int ch = 0; ch < 3; ++ch) {
+          const uint8_t *src = planes + (size_t)(ep * 3 + ch) * pn;
+          for (int y = 0; y < 64; ++y)
+            for (int x = 0; x < 64; ++x)
+              tile[ch][y][x] = (int16_t)(int8_t)(uint8_t)(src[(size_t)(ty + y) * pbw + tx + x] - 128);
+          inverse_wavelet_tile(tile[ch]);
+        }
+        for (int y = 0; y < 64 && ty + y < bh; ++y)
+          for (int x = 0; x < 64 && tx + x < bw; ++x) {
+            int8_t yy = (int8_t)tile[0][y][x], co = (int8_t)tile[1][y][x], cg = (int8_t)tile[2][y][x];
+            int8_t t = (int8_t)(yy - cg / 2);
+            int8_t g = (int8_t)(cg + t), b = (int8_t)((t - co) / 2), r = (int8_t)(b + co);
+            uint16_t v = (uint16_t)r;                      /* codec.cpp:764-771, as written */
+            v = (uint16_t)(v << 6); v |= (uint16_t)g;
+            v = (uint16_t)(v << 5); v |= (uint16_t)b;
+            out[(size_t)(ty + y) * bw + tx + x] = v;
+          }
+      }
+  }
+}
+
 /* ------------------------------------------------------------------------------------
  * PSNR of the decoded blocks (dxt_image.cpp:363-383 over PhysicalToLogical(blocks))
  * ---------------------------------------------------------------------------------- */

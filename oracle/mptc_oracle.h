@@ -54,6 +54,14 @@ void mptc_oracle_endpoint_planes(const uint64_t *blocks, int bw, int bh, uint8_t
  * (Adaptive_Data_Model(257), start_encoder .. stop_encoder).  Returns bytes written. */
 int mptc_oracle_arith_encode(const uint8_t *sym, int n, uint8_t *out, int out_cap);
 
+/* Decoder side.  Arithmetic_Codec::decode with Adaptive_Data_Model(257)
+ * (arithmetic_codec.cpp:391-444, codec.cpp:560-577): n symbols from nbytes of code (the buffer
+ * must be readable 4 bytes past the end).  Returns 0, -1 if the code runs out. */
+int mptc_oracle_arith_decode(const uint8_t *code, int nbytes, uint8_t *sym_out, int n);
+
+/* ReconstructEndPoints (codec.cpp:697-800): 6 symbol planes -> ep1 / ep2 (bw*bh RGB565 each). */
+void mptc_oracle_inverse_planes(const uint8_t *planes, int bw, int bh, uint16_t *ep1, uint16_t *ep2);
+
 /* PSNR of the decoded physical blocks against the source (dxt_image.cpp:363-383 applied
  * to PhysicalToLogical of the emitted blocks). */
 double mptc_oracle_psnr(const uint8_t *rgb, int w, int h, const uint64_t *blocks);

@@ -31,6 +31,8 @@ def lib():
         L.mptc_oracle_eval_candidate.argtypes = [vp, C.c_uint64, C.c_uint32, vp, vp]
         L.mptc_oracle_endpoint_planes.argtypes = [vp, ci, ci, vp]
         L.mptc_oracle_arith_encode.argtypes = [vp, ci, vp, ci]
+        L.mptc_oracle_arith_decode.argtypes = [vp, ci, vp, ci]
+        L.mptc_oracle_inverse_planes.argtypes = [vp, ci, ci, vp, vp]
         L.mptc_oracle_psnr.restype = C.c_double
         L.mptc_oracle_psnr.argtypes = [vp, ci, ci, vp]
         L.mptc_oracle_tables.argtypes = [vp, vp]
@@ -140,3 +142,74 @@ def check_blocks(rgb, is_intra, search_area, err_threshold, init_blocks, cur_fin
     return lib().mptc_oracle_check_blocks(rgb.ctypes.data, w, h, int(is_intra), search_area, err_threshold,
                                           init_blocks.ctypes.data, cur_final.ctypes.data, pf, motion.ctypes.data,
                                           which.ctypes.data, which.size)
+
+
+def arith_decode(code: bytes, n: int) -> np.ndarray:
+    """Arithmetic_Codec::decode x n with a fresh Adaptive_Data_Model(257) (codec.cpp:560-577)."""
+    buf = np.zeros(len(code) + 8, dtype=np.uint8)   # the decoder reads ahead of the code
+    buf[: len(code)] = np.frombuffer(code, dtype=np.uint8)
+    out = np.empty(n, dtype=np.uint8)
+    r = lib().mptc_oracle_arith_decode(buf.ctypes.data, len(code), out.ctypes.data, n)
+    if r != 0:
+        raise ValueError("arithmetic code ran out")
+    return out
+
+
+def inverse_planes(planes: np.ndarray, bw: int, bh: int):
+    """ReconstructEndPoints (codec.cpp:697-800): 6 symbol planes -> (ep1, ep2) RGB565 per block."""
+    planes = np.ascontiguousarray(planes, dtype=np.uint8)
+    ep1 = np.empty(bw * bh, dtype=np.uint16)
+    ep2 = np.empty(bw * bh, dtype=np.uint16)
+    lib().mptc_oracle_inverse_planes(planes.ctypes.data, bw, bh, ep1.ctypes.data, ep2.ctypes.data)
+    return ep1, ep2
+
+
+def parse_stream(stream: bytes):
+    """Splits an MPTC stream (reader codec.cpp:1172-1184 + :1201-1290) into
+    its header fields and per-frame compressed records.  Test helper, pure Python."""
+    import struct
+    h, w, gop, sa, n_groups = struct.unpack_from("<IIBBI", stream, 0)
+    maxes = struct.unpack_from("<5I", stream, 14)
+    off = 34
+    groups = []
+    for _ in range(n_groups):
+        (cpal,) = struct.unpack_from("<I", stream, off); off += 4
+        pal_code = stream[off:off + cpal]; off += cpal
+        (unique_bytes,) = struct.unpack_from("<I", stream, off); off += 4
+        frames = []
+        for _ in range(gop):
+            (n_unique,) = struct.unpack_from("<I", stream, off); off += 4
+            recs = []
+            for _ in range(5):
+                (nb,) = struct.unpack_from("<I", stream, off); off += 4
+                recs.append(stream[off:off + nb]); off += nb
+            frames.append((n_unique, recs))
+        groups.append((pal_code, unique_bytes, frames))
+    assert off == len(stream)
+    return {"h": h, "w": w, "gop": gop, "sa": sa, "n_groups": n_groups, "maxes": maxes, "groups": groups}
+
+
+def decode_stream(stream: bytes) -> np.ndarray:
+    """Whole-stream CPU decode built from the restated pieces (DecompressMultiUnique,
+    codec.cpp:1161-1305): -> final 8-byte blocks [n_frames][nb]."""
+    st = parse_stream(stream)
+    w, h, gop, sa = st["w"], st["h"], st["gop"], st["sa"]
+    bw, bh = w // 4, h // 4
+    nb = bw * bh
+    ps = ((bw + 63) // 64 * 64) * ((bh + 63) // 64 * 64)
+    out = []
+    for pal_code, unique_bytes, frames in st["groups"]:
+        palette = arith_decode(pal_code, unique_bytes).view(np.uint32)
+        at = 0
+        prev_words = None
+        for k, (n_unique, recs) in enumerate(frames):
+            motion = arith_decode(recs[0], 2 * nb)
+            planes = np.concatenate([arith_decode(recs[1], ps), arith_decode(recs[2], 2 * ps),
+                                     arith_decode(recs[3], ps), arith_decode(recs[4], 2 * ps)])
+            words, used = reconstruct_words(motion, palette[at:at + n_unique], prev_words if k else None, bw, bh, sa)
+            assert used == n_unique
+            at += n_unique
+            ep1, ep2 = inverse_planes(planes, bw, bh)
+            out.append(ep1.astype(np.uint64) | (ep2.astype(np.uint64) << np.uint64(16)) | (words.astype(np.uint64) << np.uint64(32)))
+            prev_words = words
+    return np.stack(out)

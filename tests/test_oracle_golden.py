@@ -85,3 +85,51 @@ def test_endpoint_planes_padding_extension():
     b2 = blocks.reshape(bh, bw)
     padded[:] = b2[np.minimum(np.arange(128), bh - 1)[:, None], np.minimum(np.arange(128), bw - 1)[None, :]]
     assert np.array_equal(got, port.endpoint_planes(padded.reshape(-1), 128, 128))
+
+
+# ---- decoder side, pinned on outputs of the reference itself --------------------
+def test_arith_decoder_inverts_reference_encodings():
+    g = load("arith")
+    for k in [k[4:] for k in g.files if k.startswith("sym_")]:
+        sym = g["sym_" + k]
+        assert np.array_equal(port.arith_decode(g["enc_" + k].tobytes(), sym.size), sym), k
+
+
+def test_inverse_planes_recover_reference_endpoints():
+    """The reference's own symbol planes -> the endpoints of the reference's own final blocks."""
+    g = load("seq_256x256_sa8")
+    for i in range(2):
+        ep1, ep2 = port.inverse_planes(g[f"planes_{i}"], 64, 64)
+        final = g[f"final_{i}"]
+        assert np.array_equal(ep1, (final & np.uint64(0xFFFF)).astype(np.uint16))
+        assert np.array_equal(ep2, ((final >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.uint16))
+
+
+def test_reference_payload_decodes_to_reference_symbols():
+    g = load("seq_256x256_sa8")
+    import struct
+    for i in range(2):
+        payload = g[f"payload_{i}"].tobytes()
+        off = 4
+        want = [g[f"motion_{i}"], g[f"planes_{i}"][0], np.concatenate([g[f"planes_{i}"][1], g[f"planes_{i}"][2]]),
+                g[f"planes_{i}"][3], np.concatenate([g[f"planes_{i}"][4], g[f"planes_{i}"][5]])]
+        for s in range(5):
+            (n,) = struct.unpack_from("<I", payload, off)
+            off += 4
+            assert np.array_equal(port.arith_decode(payload[off:off + n], want[s].size), want[s].reshape(-1)), (i, s)
+            off += n
+        assert off == len(payload)
+
+
+def test_reference_stream_decodes_to_reference_blocks():
+    """The stream CompressMultiUnique wrote (fixture) -> the blocks the encoder produced."""
+    g = load("stream_256x256_sa4_gop2")
+    w, h, n, seed, sa, thr, gop = [int(x) for x in g["params"]]
+    frames = make_sequence(w, h, n, seed=seed)
+    decoded = port.decode_stream(g["stream"].tobytes())
+    prev = None
+    for i in range(n // gop * gop):
+        init = port.dxt1_fit(frames[i])
+        blocks, motion, unique = port.reencode(frames[i], i % gop == 0, sa, thr, init, prev)
+        assert np.array_equal(decoded[i], blocks), f"frame {i}"
+        prev = blocks
