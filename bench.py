@@ -318,6 +318,29 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     barrier()
     stream_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
 
+    # ---- decoder side: the stream just written back to DXT1 blocks ----------------
+    stream = capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)[0]
+    ctx.seq_encode(0, FRAMES, SA, THR, GOP)           # leaves motion / unique / planes on the device
+    ctx.sync()
+    dec_ms = {k: 0.0 for k in ("total", "words", "planes", "rgb")}
+    for it in range(2 + args.steps):
+        ctx.seq_decode(0, FRAMES, SA, GOP, rgb=True)  # device-resident symbols -> blocks + RGB
+        if it >= 2:
+            for k in dec_ms:
+                dec_ms[k] += ctx.last_decode_ms(k) / args.steps
+    ctx.sync()
+    dec_stats = None
+    capi.decode_stream(ctx, stream, threads=host_threads)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec_blocks, _, dec_stats = capi.decode_stream(ctx, stream, threads=host_threads)
+    barrier()
+    dec_stream_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    dec_ok = bool(np.array_equal(dec_blocks, out["blocks"]))
+    for k in dec_ms:
+        dec_ms[k] = max_over_ranks(dec_ms[k])
+
     # ---- kernel attribution pass: one GOP lane, so that kernels do not overlap and the CUDA events
     # around each launch measure that kernel alone (in the timed region above, kernels of different
     # lanes share the GPU and their event intervals include each other's time) ---------------------
@@ -398,6 +421,21 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
                        "note": "e2e + the host arithmetic coder and stream assembly (mptc_encode_stream), coder overlapped with the GPU"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "checksum_n_unique": checksum,
+        "decode": {
+            "note": "decoder side (SURVEY.md 8f-2), same frames: device = symbols resident in HBM -> DXT1 blocks + RGB "
+                    "pictures (CUDA events); stream = mptc_decode_stream from the stream bytes to host DXT1 blocks, host "
+                    "arithmetic decoder included",
+            "device": {"value": pixels_total / (dec_ms["total"] * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dec_ms["total"],
+                       "stage_ms": dec_ms},
+            "rgb_kernel_hbm": {"kernel": "k_dxt1_to_rgb", "bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                               "achieved": FRAMES * nb * 56 / (dec_ms["rgb"] * 1e-3) / 1e9,
+                               "frac": FRAMES * nb * 56 / (dec_ms["rgb"] * 1e-3) / 1e9 / hbm_peak,
+                               "algo_bytes_per_block": 56},
+            "stream": {"value": pixels_total / (dec_stream_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dec_stream_ms,
+                       "host_threads": host_threads, "entropy_ms": dec_stats.entropy_ms if dec_stats else None,
+                       "symbols": int(dec_stats.symbols) if dec_stats else None},
+            "round_trip_equal": dec_ok,
+        },
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MPTC_E_SPACE (-5) /* output buffer too small; *out_bytes holds the size needed */
+/* MPTC_E_SPACE (mptc_gpu.h): output buffer too small; *out_bytes holds the size needed */
 
 /* Adaptive arithmetic coding of n byte symbols with a fresh 257-symbol model. */
 int mptc_arith_encode(const uint8_t *sym, size_t n, uint8_t *out, size_t cap, size_t *out_bytes);
@@ -63,6 +63,37 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
                          const uint32_t *unique, const uint32_t *n_unique, const uint8_t *planes,
                          int threads, uint8_t *out, size_t cap, size_t *out_bytes,
                          mptc_stream_stats *stats);
+
+/* ---- decoder side --------------------------------------------------- */
+
+/* EntropyDecode (codec/codec.cpp:560-577): n byte symbols from nbytes of code, fresh
+ * Adaptive_Data_Model(257), Arithmetic_Codec::decode (arithmetic_codec.cpp:391-444).
+ * MPTC_E_DATA if the code runs out or decodes a symbol outside 0..255. */
+int mptc_arith_decode(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n);
+
+/* The 34-byte stream header (reader: codec.cpp:1172-1184). */
+typedef struct mptc_stream_header {
+  int width, height, gop /* unique_interval */, search_area, n_groups, n_frames /* n_groups*gop */;
+  uint32_t max_unique_bytes, max_comp_palette, max_comp_motion, max_comp_ep_y, max_comp_ep_c;
+} mptc_stream_header;
+int mptc_stream_info(const uint8_t *stream, size_t bytes, mptc_stream_header *hdr);
+
+typedef struct mptc_decode_stats {
+  mptc_stream_header header;
+  double entropy_ms;  /* wall time of the arithmetic decoding on `threads` host threads (the GPU
+                         reconstructs finished groups meanwhile) */
+  double total_ms;    /* wall time of the whole call */
+  uint64_t symbols;   /* symbols decoded */
+} mptc_decode_stats;
+
+/* Whole-stream decode, replaces DecompressMultiUnique (codec.cpp:1161-1305; the library flavour
+ * GetFrame / GetFrameMultiThread, codec/decoder.cpp:256-470): stream bytes in, the DXT1 blocks
+ * (PhysicalDXTBlock, ready for texture upload) of all header.n_frames frames out, optionally the
+ * decoded RGB frames as well.  Arithmetic decoding on `threads` host threads (one job per stream
+ * record), reconstruction on the GPU, group by group as the host finishes them.
+ * blocks_out: n_frames*nb u64 (may be NULL); rgb_out: n_frames*w*h*3 bytes (may be NULL). */
+int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, int threads,
+                       uint64_t *blocks_out, uint8_t *rgb_out, mptc_decode_stats *stats);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,8 @@ extern "C" {
 #define MPTC_E_CUDA (-2)    /* CUDA runtime error; see mptc_gpu_last_error */
 #define MPTC_E_NOMEM (-3)   /* device or pinned allocation failed */
 #define MPTC_E_STATE (-4)   /* call order violated (e.g. encode before reserve/upload) */
+#define MPTC_E_SPACE (-5)   /* output buffer too small (mptc_codec.h) */
+#define MPTC_E_DATA (-6)    /* corrupt input: a stream / motion vector no encoder emits */
 
 typedef struct mptc_gpu_ctx mptc_gpu_ctx;
 
@@ -125,6 +127,38 @@ int mptc_gpu_encode_sequence_async(mptc_gpu_ctx *ctx, const uint8_t *frames, int
                                    uint32_t *unique, uint32_t *n_unique, uint8_t *planes);
 int mptc_gpu_wait_frame(mptc_gpu_ctx *ctx, int frame);
 int mptc_gpu_wait(mptc_gpu_ctx *ctx);
+
+/* ---- decoder side --------------------------------------------------- */
+/* From the symbols the arithmetic decoder produced to ready-to-upload DXT1 blocks.  Replaces
+ * ReconstructDXTData + ReconstructEndPoints (codec/codec.cpp:393-500, :697-800; the library
+ * flavour ReconstructDXTFrame / ReconstructEndpoints, codec/decoder.cpp:68-254) and, with RGB
+ * output, DXTImage::DecompressedImage (dxt_image.cpp:463-479).  The reference walks the blocks
+ * of every frame in raster order, frame after frame; here all frames of all GOPs are resolved in
+ * the same launches (pointer jumping over the copy chains).
+ *   motion   n*2*nb bytes;  planes  n*6*pbw*pbh symbols (layout as above)
+ *   unique   the index words of the unique blocks: unique_stride == 0 -> packed, frame after frame
+ *            (the group palettes of the stream back to back, codec.cpp:1473-1479); otherwise frame
+ *            i's words start at unique + i*unique_stride (the encoder's output layout, stride nb)
+ * Returns MPTC_E_DATA if a motion vector points outside the frame / forward in raster order /
+ * to a previous frame that does not exist (the reference would read out of bounds). */
+int mptc_gpu_decode_sequence(mptc_gpu_ctx *ctx, const uint8_t *motion, const uint32_t *unique,
+                             const uint32_t *n_unique, size_t unique_stride, const uint8_t *planes,
+                             int n_frames, int w, int h, int search_area, int gop,
+                             uint64_t *blocks_out, uint8_t *rgb_out /* may be NULL */);
+
+/* The same in three asynchronous steps on the device-resident sequence (mptc_gpu_seq_reserve):
+ * upload the symbols of frames [first, first+count), decode them (first = a GOP boundary), fetch
+ * the results.  mptc_gpu_seq_decode without an upload decodes what the encoder left on the
+ * device (motion / unique / planes of mptc_gpu_seq_encode): the device-resident round trip.
+ * Decoded blocks live in their own buffer; the encoder's final blocks stay untouched. */
+int mptc_gpu_seq_decode_upload(mptc_gpu_ctx *ctx, int first, int count, const uint8_t *motion,
+                               const uint32_t *unique, const uint32_t *n_unique, size_t unique_stride,
+                               const uint8_t *planes);
+int mptc_gpu_seq_decode(mptc_gpu_ctx *ctx, int first, int count, int search_area, int gop, int want_rgb);
+int mptc_gpu_seq_decode_download(mptc_gpu_ctx *ctx, int first, int count, uint64_t *blocks, uint8_t *rgb);
+/* Device time (ms) of the last mptc_gpu_seq_decode: stage 0 whole, 1 index words (count, links,
+ * pointer jumping), 2 inverse endpoint planes + block assembly, 3 DXT1 -> RGB. */
+int mptc_gpu_last_decode_ms(mptc_gpu_ctx *ctx, int stage, float *ms);
 
 /* Page-locked host memory for the buffers above. */
 void *mptc_gpu_host_alloc(size_t bytes);

@@ -22,7 +22,10 @@ EXPORTS = [
     "mptc_gpu_sync", "mptc_gpu_last_encode_ms", "mptc_gpu_encode_sequence",
     "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count", "mptc_gpu_set_schedule",
     "mptc_gpu_encode_sequence_async", "mptc_gpu_wait_frame", "mptc_gpu_wait",
+    "mptc_gpu_decode_sequence", "mptc_gpu_seq_decode_upload", "mptc_gpu_seq_decode",
+    "mptc_gpu_seq_decode_download", "mptc_gpu_last_decode_ms",
 ]
+DECODE_STAGES = {"total": 0, "words": 1, "planes": 2, "rgb": 3}
 
 
 class Params(C.Structure):
@@ -74,6 +77,11 @@ def load():
     L.mptc_gpu_host_free.argtypes = [vp]
     L.mptc_gpu_last_candidate_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.mptc_gpu_set_schedule.argtypes = [vp, ci, ci, ci]
+    L.mptc_gpu_decode_sequence.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, ci, ci, ci, ci, ci, vp, vp]
+    L.mptc_gpu_seq_decode_upload.argtypes = [vp, ci, ci, vp, vp, vp, C.c_size_t, vp]
+    L.mptc_gpu_seq_decode.argtypes = [vp, ci, ci, ci, ci, ci]
+    L.mptc_gpu_seq_decode_download.argtypes = [vp, ci, ci, vp, vp]
+    L.mptc_gpu_last_decode_ms.argtypes = [vp, ci, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -250,9 +258,57 @@ class Context:
         self.w, self.h, self.nb, self.pbw, self.pbh = w, h, nb, pbw, pbh
         return out
 
+    # ---- decoder side ----------------------------------------------------------------------
+    def decode_sequence(self, motion, unique, n_unique, planes, w, h, search_area, gop, packed=False, rgb=False):
+        """Symbols -> DXT1 blocks [n, nb] (and RGB frames [n, h, w, 3] with rgb=True).  `unique` is
+        [n, nb] in the encoder's layout, or with packed=True the unique words of all frames back to
+        back."""
+        motion = np.ascontiguousarray(motion, dtype=np.uint8)
+        unique = np.ascontiguousarray(unique, dtype=np.uint32)
+        n_unique = np.ascontiguousarray(n_unique, dtype=np.uint32)
+        planes = np.ascontiguousarray(planes, dtype=np.uint8)
+        n = n_unique.size
+        nb = (h // 4) * (w // 4)
+        blocks = np.empty((n, nb), dtype=np.uint64)
+        pix = np.empty((n, h, w, 3), dtype=np.uint8) if rgb else None
+        self._check(self._L.mptc_gpu_decode_sequence(self._p, motion.ctypes.data, unique.ctypes.data,
+                                                     n_unique.ctypes.data, 0 if packed else nb, planes.ctypes.data,
+                                                     n, w, h, search_area, gop, blocks.ctypes.data, _ptr(pix)))
+        self.w, self.h, self.nb = w, h, nb
+        self.pbw, self.pbh = (w // 4 + 63) // 64 * 64, (h // 4 + 63) // 64 * 64
+        return (blocks, pix) if rgb else blocks
+
+    def seq_decode(self, first, count, search_area, gop, rgb=False):
+        """Decodes what is on the device (after seq_encode: the device-resident round trip)."""
+        self._check(self._L.mptc_gpu_seq_decode(self._p, first, count, search_area, gop, int(rgb)))
+
+    def seq_decode_download(self, first, count, rgb=False):
+        blocks = np.empty((count, self.nb), dtype=np.uint64)
+        pix = np.empty((count, self.h, self.w, 3), dtype=np.uint8) if rgb else None
+        self._check(self._L.mptc_gpu_seq_decode_download(self._p, first, count, blocks.ctypes.data, _ptr(pix)))
+        return (blocks, pix) if rgb else blocks
+
+    def last_decode_ms(self, stage="total") -> float:
+        ms = C.c_float(0)
+        self._check(self._L.mptc_gpu_last_decode_ms(self._p, DECODE_STAGES[stage], C.byref(ms)))
+        return float(ms.value)
+
 
 # ---- host codec (include/mptc_codec.h) -----------------------------------------------------------
-CODEC_EXPORTS = ["mptc_arith_encode", "mptc_frame_payload", "mptc_encode_stream", "mptc_assemble_stream"]
+CODEC_EXPORTS = ["mptc_arith_encode", "mptc_frame_payload", "mptc_encode_stream", "mptc_assemble_stream",
+                 "mptc_arith_decode", "mptc_stream_info", "mptc_decode_stream"]
+
+
+class StreamHeader(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("gop", C.c_int), ("search_area", C.c_int),
+                ("n_groups", C.c_int), ("n_frames", C.c_int), ("max_unique_bytes", C.c_uint32),
+                ("max_comp_palette", C.c_uint32), ("max_comp_motion", C.c_uint32), ("max_comp_ep_y", C.c_uint32),
+                ("max_comp_ep_c", C.c_uint32)]
+
+
+class DecodeStats(C.Structure):
+    _fields_ = [("header", StreamHeader), ("entropy_ms", C.c_double), ("total_ms", C.c_double),
+                ("symbols", C.c_uint64)]
 
 
 class StreamStats(C.Structure):
@@ -271,8 +327,47 @@ def _codec():
                                          C.POINTER(StreamStats)]
         L.mptc_assemble_stream.argtypes = [ci, ci, ci, C.POINTER(Params), vp, vp, vp, vp, ci, vp, sz, C.POINTER(sz),
                                            C.POINTER(StreamStats)]
+        L.mptc_arith_decode.argtypes = [vp, sz, vp, sz]
+        L.mptc_stream_info.argtypes = [vp, sz, C.POINTER(StreamHeader)]
+        L.mptc_decode_stream.argtypes = [vp, vp, sz, ci, vp, vp, C.POINTER(DecodeStats)]
         L._codec_ready = True
     return L
+
+
+def arith_decode(code: bytes, n: int) -> np.ndarray:
+    """EntropyDecode (codec.cpp:560-577): n byte symbols from an arithmetic-coded stream."""
+    buf = np.frombuffer(code, dtype=np.uint8)
+    out = np.empty(n, dtype=np.uint8)
+    r = _codec().mptc_arith_decode(buf.ctypes.data if buf.size else None, buf.size, out.ctypes.data, n)
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_arith_decode failed: {r}")
+    return out
+
+
+def stream_info(stream: bytes) -> StreamHeader:
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    hdr = StreamHeader()
+    r = _codec().mptc_stream_info(buf.ctypes.data, buf.size, C.byref(hdr))
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_stream_info failed: {r}")
+    return hdr
+
+
+def decode_stream(ctx: "Context", stream, threads=1, rgb=False):
+    """Stream bytes -> (blocks [n, nb], rgb [n, h, w, 3] or None, DecodeStats)."""
+    buf = np.frombuffer(stream, dtype=np.uint8) if not isinstance(stream, np.ndarray) else stream
+    hdr = stream_info(buf)
+    n, w, h = hdr.n_frames, hdr.width, hdr.height
+    nb = (w // 4) * (h // 4)
+    blocks = np.empty((n, nb), dtype=np.uint64)
+    pix = np.empty((n, h, w, 3), dtype=np.uint8) if rgb else None
+    st = DecodeStats()
+    r = _codec().mptc_decode_stream(ctx._p, buf.ctypes.data, buf.size, threads, blocks.ctypes.data, _ptr(pix),
+                                    C.byref(st))
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_decode_stream failed: {r}: {ctx._L.mptc_gpu_last_error(ctx._p).decode()}")
+    ctx.w, ctx.h, ctx.nb = w, h, nb
+    return blocks, pix, st
 
 
 def arith_encode(sym: np.ndarray) -> bytes:

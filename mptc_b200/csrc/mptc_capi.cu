@@ -65,6 +65,14 @@ struct mptc_gpu_ctx {
   uint64_t launches = 0;
   void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // result staging of mptc_encode_stream
   size_t pinned_bytes[4] = {0, 0, 0, 0};
+  // decoder side (mptc_decode.cu): allocated by the first decode call for the reserved sequence
+  uint32_t *d_dec_words = nullptr, *d_dec_chunks = nullptr, *d_dec_uoff = nullptr;
+  int *d_dec_link = nullptr, *d_dec_status = nullptr;     // status: [0] errors, then 40 ints per frame
+  uint64_t *d_dec_blocks = nullptr;
+  uint8_t *d_dec_rgb = nullptr;
+  std::vector<uint32_t> h_uoff;   // word offset of every frame's unique words inside d_unique
+  cudaEvent_t ev_dec[4] = {nullptr, nullptr, nullptr, nullptr};   // begin, words, planes, rgb/end
+  bool decoded = false, dec_pending = false, dec_rgb = false;
   char err[512] = {0};
 };
 
@@ -114,8 +122,43 @@ void free_seq(mptc_gpu_ctx *c) {
   cudaFree(c->d_progress); cudaFree(c->d_row_todo);
   c->d_rgb = nullptr; c->d_init = c->d_final = nullptr; c->d_motion = c->d_flags = c->d_planes = nullptr;
   c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr; c->d_row_todo = nullptr;
+  cudaFree(c->d_dec_words); cudaFree(c->d_dec_chunks); cudaFree(c->d_dec_uoff); cudaFree(c->d_dec_link);
+  cudaFree(c->d_dec_status); cudaFree(c->d_dec_blocks); cudaFree(c->d_dec_rgb);
+  c->d_dec_words = c->d_dec_chunks = c->d_dec_uoff = nullptr; c->d_dec_link = c->d_dec_status = nullptr;
+  c->d_dec_blocks = nullptr; c->d_dec_rgb = nullptr;
   c->cap_frames = 0; c->w = c->h = 0;
-  c->encoded = false;
+  c->encoded = c->decoded = c->dec_pending = false;
+}
+
+constexpr int kDecStatusStride = 40;   // pass flags per decode call, indexed by its first frame
+
+// Decoder-side buffers for the reserved sequence (lazy: encode-only users never pay for them).
+int ensure_decode(mptc_gpu_ctx *c, bool want_rgb) {
+  const size_t F = (size_t)c->cap_frames, nb = (size_t)c->nb;
+  if (!c->d_dec_link) {
+    CU(c, cudaMalloc(&c->d_dec_words, F * nb * 4));
+    CU(c, cudaMalloc(&c->d_dec_link, F * nb * sizeof(int)));
+    CU(c, cudaMalloc(&c->d_dec_chunks, F * dec_chunks(c->nb) * 4));
+    CU(c, cudaMalloc(&c->d_dec_uoff, F * 4));
+    CU(c, cudaMalloc(&c->d_dec_status, (1 + F * kDecStatusStride) * sizeof(int)));
+    CU(c, cudaMalloc(&c->d_dec_blocks, F * nb * 8));
+    CU(c, cudaMemset(c->d_dec_status, 0, sizeof(int)));
+  }
+  if (want_rgb && !c->d_dec_rgb) CU(c, cudaMalloc(&c->d_dec_rgb, F * c->frame_bytes));
+  for (auto &e : c->ev_dec)
+    if (!e) CU(c, cudaEventCreate(&e));
+  return MPTC_OK;
+}
+
+DecView dec_view_of(const mptc_gpu_ctx *c, int first, int count, int gop, int sa) {
+  DecView v;
+  v.motion = c->d_motion; v.unique = c->d_unique; v.unique_off = c->d_dec_uoff; v.n_unique = c->d_nunique;
+  v.planes = c->d_planes; v.words = c->d_dec_words; v.link = c->d_dec_link; v.chunk_counts = c->d_dec_chunks;
+  v.errors = c->d_dec_status; v.status = c->d_dec_status + 1 + (size_t)first * kDecStatusStride;
+  v.blocks = c->d_dec_blocks; v.rgb = c->d_dec_rgb;
+  v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb; v.pbw = c->pbw; v.pbh = c->pbh;
+  v.first = first; v.count = count; v.gop = gop; v.sa = sa;
+  return v;
 }
 
 SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
@@ -330,6 +373,7 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
     if (k_last < k_begin) continue;
     CU(c, cudaStreamWaitEvent(s0, host_out ? L.ev_down[k_last] : L.ev_side[k_last], 0));
   }
+  for (int f = first; f < first + count; ++f) c->h_uoff[f] = (uint32_t)((size_t)f * c->nb);   // K4's unique layout
   c->lanes_used = nl;
   c->enc_first = first; c->enc_count = count; c->enc_gop = gop; c->enc_host_out = host_out;
   CU(c, cudaEventRecord(c->ev_end, s0));
@@ -376,7 +420,7 @@ int mptc_gpu_create(int device, mptc_gpu_ctx **out) {
     uint8_t t5[512], t6[512];
     build_match_table(t5, 5);
     build_match_table(t6, 6);
-    ok = upload_tables(t5, t6) == cudaSuccess;
+    ok = upload_tables(t5, t6) == cudaSuccess && decode_kernels_init() == cudaSuccess;
   }
   if (!ok) { mptc_gpu_destroy(c); return MPTC_E_CUDA; }
   c->max_wave_ctas = intra_wavefront_max_ctas(device);
@@ -405,6 +449,7 @@ void mptc_gpu_destroy(mptc_gpu_ctx *c) {
     if (L.s) cudaStreamDestroy(L.s);
     if (L.t) cudaStreamDestroy(L.t);
   }
+  for (cudaEvent_t e : c->ev_dec) if (e) cudaEventDestroy(e);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
   if (c->ev_uploaded) cudaEventDestroy(c->ev_uploaded);
@@ -450,6 +495,8 @@ int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
   CU(c, cudaMalloc(&c->d_planes, F * c->plane_bytes));
   CU(c, cudaMalloc(&c->d_progress, F * c->bh * sizeof(int)));
   c->cap_frames = n_frames;
+  c->h_uoff.resize(F);
+  for (size_t f = 0; f < F; ++f) c->h_uoff[f] = (uint32_t)(f * nb);   // the encoder's layout
   return MPTC_OK;
 }
 
@@ -631,6 +678,101 @@ int mptc_gpu_encode_sequence(mptc_gpu_ctx *c, const uint8_t *frames, int n_frame
                              uint32_t *n_unique, uint8_t *planes) {
   if (int r = mptc_gpu_encode_sequence_async(c, frames, n_frames, w, h, p, blocks, motion, unique, n_unique, planes)) return r;
   CU(c, cudaStreamSynchronize(c->s_compute));
+  return MPTC_OK;
+}
+
+// ---- decoder side -------------------------------------------------------------------------
+
+int mptc_gpu_seq_decode_upload(mptc_gpu_ctx *c, int first, int count, const uint8_t *motion, const uint32_t *unique,
+                               const uint32_t *n_unique, size_t unique_stride, const uint8_t *planes) {
+  if (!c || !motion || !n_unique || !planes) return MPTC_E_ARG;
+  if (first < 0 || count < 1 || first + count > c->cap_frames) return fail(c, MPTC_E_STATE, "decode upload range [%d,%d) outside reserved %d frames", first, first + count, c->cap_frames);
+  CU(c, cudaSetDevice(c->device));
+  if (int r = ensure_decode(c, false)) return r;
+  cudaStream_t s = c->s_compute;
+  const size_t nb = (size_t)c->nb, f0 = (size_t)first, n = (size_t)count;
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+  CU(c, cudaMemcpyAsync(c->d_motion + f0 * nb * 2, motion, n * nb * 2, H2D, s));
+  CU(c, cudaMemcpyAsync(c->d_planes + f0 * c->plane_bytes, planes, n * c->plane_bytes, H2D, s));
+  CU(c, cudaMemcpyAsync(c->d_nunique + f0, n_unique, n * 4, H2D, s));
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (n_unique[i] > nb) return fail(c, MPTC_E_DATA, "frame %zu: %u unique words for %zu blocks", f0 + i, n_unique[i], nb);
+    c->h_uoff[f0 + i] = (uint32_t)(unique_stride ? (f0 + i) * nb : f0 * nb + total);
+    total += n_unique[i];
+  }
+  if (total && !unique) return MPTC_E_ARG;
+  if (unique_stride == 0) {          // packed: the group palettes back to back (codec.cpp:1473-1479)
+    if (total) CU(c, cudaMemcpyAsync(c->d_unique + f0 * nb, unique, total * 4, H2D, s));
+  } else {                           // the encoder's layout: frame i's words at unique + i*stride
+    for (size_t i = 0; i < n; ++i)
+      if (n_unique[i]) CU(c, cudaMemcpyAsync(c->d_unique + (f0 + i) * nb, unique + i * unique_stride, (size_t)n_unique[i] * 4, H2D, s));
+  }
+  return MPTC_OK;
+}
+
+int mptc_gpu_seq_decode(mptc_gpu_ctx *c, int first, int count, int search_area, int gop, int want_rgb) {
+  if (!c) return MPTC_E_ARG;
+  if (int r = check_params(c, search_area, gop)) return r;
+  if (first < 0 || count < 1 || first + count > c->cap_frames) return fail(c, MPTC_E_STATE, "decode range [%d,%d) outside reserved %d frames", first, first + count, c->cap_frames);
+  CU(c, cudaSetDevice(c->device));
+  if (int r = ensure_decode(c, want_rgb != 0)) return r;
+  cudaStream_t s = c->s_compute;
+  const int passes = dec_jump_passes(gop, c->nb);
+  if (passes + 2 > kDecStatusStride) return fail(c, MPTC_E_ARG, "gop %d x %d blocks: chains too long", gop, c->nb);
+  DecView v = dec_view_of(c, first, count, gop, search_area);
+  CU(c, cudaMemcpyAsync(c->d_dec_uoff + first, c->h_uoff.data() + first, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+  if (!c->dec_pending) CU(c, cudaMemsetAsync(c->d_dec_status, 0, sizeof(int), s));
+  CU(c, cudaMemsetAsync(v.status, 0, kDecStatusStride * sizeof(int), s));
+  CU(c, cudaEventRecord(c->ev_dec[0], s));
+  c->launches += launch_decode_words(v, s);
+  CU(c, cudaEventRecord(c->ev_dec[1], s));
+  c->launches += launch_inverse_planes(v, s);
+  CU(c, cudaEventRecord(c->ev_dec[2], s));
+  if (want_rgb) c->launches += launch_dxt1_to_rgb(v, s);
+  CU(c, cudaEventRecord(c->ev_dec[3], s));
+  CU(c, cudaGetLastError());
+  c->decoded = c->dec_pending = true;
+  c->dec_rgb = want_rgb != 0;
+  return MPTC_OK;
+}
+
+int mptc_gpu_seq_decode_download(mptc_gpu_ctx *c, int first, int count, uint64_t *blocks, uint8_t *rgb) {
+  if (!c) return MPTC_E_ARG;
+  if (!c->decoded) return fail(c, MPTC_E_STATE, "no decode has run");
+  if (first < 0 || count < 1 || first + count > c->cap_frames) return fail(c, MPTC_E_STATE, "download range [%d,%d) outside reserved %d frames", first, first + count, c->cap_frames);
+  if (rgb && !c->d_dec_rgb) return fail(c, MPTC_E_STATE, "the decode did not produce RGB");
+  CU(c, cudaSetDevice(c->device));
+  cudaStream_t s = c->s_compute;
+  const size_t nb = (size_t)c->nb;
+  if (blocks) CU(c, cudaMemcpyAsync(blocks, c->d_dec_blocks + (size_t)first * nb, (size_t)count * nb * 8, cudaMemcpyDeviceToHost, s));
+  if (rgb) CU(c, cudaMemcpyAsync(rgb, c->d_dec_rgb + (size_t)first * c->frame_bytes, (size_t)count * c->frame_bytes, cudaMemcpyDeviceToHost, s));
+  int bad = 0;
+  CU(c, cudaMemcpyAsync(&bad, c->d_dec_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  c->dec_pending = false;
+  if (bad) return fail(c, MPTC_E_DATA, "corrupt stream: %d blocks with a motion vector no encoder emits", bad);
+  return MPTC_OK;
+}
+
+int mptc_gpu_decode_sequence(mptc_gpu_ctx *c, const uint8_t *motion, const uint32_t *unique, const uint32_t *n_unique,
+                             size_t unique_stride, const uint8_t *planes, int n_frames, int w, int h,
+                             int search_area, int gop, uint64_t *blocks_out, uint8_t *rgb_out) {
+  if (!c) return MPTC_E_ARG;
+  if (int r = check_params(c, search_area, gop)) return r;
+  if (int r = mptc_gpu_seq_reserve(c, w, h, n_frames)) return r;
+  if (int r = mptc_gpu_seq_decode_upload(c, 0, n_frames, motion, unique, n_unique, unique_stride, planes)) return r;
+  if (int r = mptc_gpu_seq_decode(c, 0, n_frames, search_area, gop, rgb_out != nullptr)) return r;
+  return mptc_gpu_seq_decode_download(c, 0, n_frames, blocks_out, rgb_out);
+}
+
+int mptc_gpu_last_decode_ms(mptc_gpu_ctx *c, int stage, float *ms) {
+  if (!c || !ms || stage < 0 || stage > 3) return MPTC_E_ARG;
+  if (!c->decoded) return fail(c, MPTC_E_STATE, "no decode has run");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventSynchronize(c->ev_dec[3]));
+  if (stage == 0) CU(c, cudaEventElapsedTime(ms, c->ev_dec[0], c->ev_dec[3]));
+  else CU(c, cudaEventElapsedTime(ms, c->ev_dec[stage - 1], c->ev_dec[stage]));
   return MPTC_OK;
 }
 

@@ -1,0 +1,287 @@
+// mptc_decode.cu -- decoder-side kernels for sm_100a: from the symbols the
+// arithmetic decoder produced to ready-to-upload DXT1 blocks (and, optionally, RGB pixels).
+//
+//   D1 k_dec_count / k_dec_links / k_dec_jump   ReconstructDXTData / ReconstructDXTFrame
+//        (codec/codec.cpp:393-500, codec/decoder.cpp:198-254): every block's index word is a unique
+//        word, a copy from the previous frame (inter) or a copy from an earlier block of its own
+//        frame (intra).  The reference resolves that sequentially, block after block, frame after
+//        frame.  It is pure copying, so here every block of a GOP becomes a node with one parent
+//        link and the chains are collapsed by pointer jumping: O(log depth) data-parallel passes
+//        over ALL frames of the GOP at once, no raster or frame order left.
+//   D2 k_inverse_planes    ReconstructEndPoints (codec.cpp:697-800; decoder.cpp:68-196): symbols ->
+//        MakeSigned -> inverse 5/3 wavelet on 64x64 tiles (image_processing.h:337-399, levels
+//        dim = 2..64, rows then columns wavelet.cpp:133-155, :64-95) -> ycocg667_to_rgb565
+//        (codec.cpp:46-63) -> 565 packing (:764-771), fused with the gather of the index word, so
+//        the 8-byte PhysicalDXTBlock is written once, coalesced.
+//   D3 k_dxt1_to_rgb       DXTImage::DecompressedImage (dxt_image.cpp:463-479) over
+//        PhysicalToLogical (:198-227): the decoded picture, 8 B in / 48 B out per block -- the one
+//        HBM-bound kernel of the codec.
+//
+// No tensor cores: integer copies and lifting steps only.
+#include "mptc_kernels.h"
+#include "mptc_device.cuh"
+
+namespace mptc {
+
+namespace {
+constexpr int kChunk = 1024;   // blocks per CTA of D1's count / link kernels
+}
+
+int dec_chunks(int nb) { return (nb + kChunk - 1) / kChunk; }
+
+// Unique blocks per chunk of 1024 raster-ordered blocks.
+__global__ void __launch_bounds__(kChunk)
+k_dec_count(DecView v) {
+  __shared__ int warp_cnt[kChunk / 32];
+  const int f = v.first + blockIdx.y;
+  const int b = blockIdx.x * kChunk + threadIdx.x;
+  bool uniq = false;
+  if (b < v.nb) {
+    const uchar2 m = reinterpret_cast<const uchar2 *>(v.motion)[(size_t)f * v.nb + b];
+    uniq = m.x == 255 && m.y == 255;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, uniq);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int c = warp_cnt[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (threadIdx.x == 0) v.chunk_counts[(size_t)f * gridDim.x + blockIdx.x] = (uint32_t)c;
+  }
+}
+
+// One node per block: link = the node its index word is copied from (itself for unique blocks,
+// whose word is fetched from the palette right here).
+__global__ void __launch_bounds__(kChunk)
+k_dec_links(DecView v) {
+  __shared__ int warp_cnt[kChunk / 32];
+  __shared__ int chunk_base;
+  const int f = v.first + blockIdx.y;
+  const int b = blockIdx.x * kChunk + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uchar2 m = make_uchar2(0, 0);
+  if (b < v.nb) m = reinterpret_cast<const uchar2 *>(v.motion)[(size_t)f * v.nb + b];
+  const bool uniq = b < v.nb && m.x == 255 && m.y == 255;
+  const unsigned bal = __ballot_sync(0xffffffffu, uniq);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  if (warp == 0) {   // uniques of the chunks before this one
+    int c = 0;
+    for (int i = lane; i < (int)blockIdx.x; i += 32) c += (int)v.chunk_counts[(size_t)f * gridDim.x + i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) chunk_base = c;
+  }
+  __syncthreads();
+  if (b >= v.nb) return;
+  int rank = chunk_base + __popc(bal & ((1u << lane) - 1u));
+  for (int i = 0; i < warp; ++i) rank += warp_cnt[i];
+  const size_t n = (size_t)f * v.nb + b;
+  const int bx = b % v.bw, by = b / v.bw;
+  int parent = -1;
+  if (uniq) {
+    if ((uint32_t)rank < v.n_unique[f]) {                      // codec.cpp:451-455
+      v.words[n] = v.unique[(size_t)v.unique_off[f] + rank];
+      parent = (int)n;
+    }
+  } else if ((m.x & 0x80) && (m.y & 0x80)) {                   // inter (:456-471)
+    const int rx = bx + (m.x & 0x7F) - v.sa, ry = by + (m.y & 0x7F) - v.sa;
+    if ((f - v.first) % v.gop != 0 && rx >= 0 && ry >= 0 && rx < v.bw && ry < v.bh)
+      parent = (int)(n - v.nb) - b + ry * v.bw + rx;
+  } else {                                                     // intra (:472-489)
+    const int rx = bx + m.x - v.sa, ry = by + m.y - (2 * v.sa - 1);
+    if (rx >= 0 && ry >= 0 && rx < v.bw && ry * v.bw + rx < b)
+      parent = (int)n - b + ry * v.bw + rx;
+  }
+  if (parent < 0) {           // a vector the encoder cannot emit: corrupt stream
+    atomicAdd(v.errors, 1);
+    v.words[n] = 0;
+    parent = (int)n;
+  }
+  v.link[n] = parent;
+}
+
+// One pointer-jumping pass, in place: link[n] <- link[link[n]].  Any value a racing thread reads
+// is an ancestor of its node, so stale reads only cost passes, never correctness.  status[1+pass]
+// is raised while some node still is more than one hop from its root; later passes return at once
+// when the previous one did not raise it.
+__global__ void __launch_bounds__(256)
+k_dec_jump(DecView v, int pass) {
+  if (pass > 0 && v.status[pass] == 0) return;
+  const size_t total = (size_t)v.count * v.nb, base = (size_t)v.first * v.nb;
+  bool more = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = base + i;
+    const int p = __ldcg(v.link + n);
+    const int q = __ldcg(v.link + p);
+    if (q != p) {
+      v.link[n] = q;
+      more |= __ldcg(v.link + q) != q;
+    }
+  }
+  if (__any_sync(0xffffffffu, more) && (threadIdx.x & 31) == 0) v.status[1 + pass] = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// D2: inverse endpoint planes + final block assembly.  One CTA per (64x64 tile, frame), all six
+// planes of the tile in shared memory (6 x 2 x 8 KB), ping-pong per lifting direction.
+// ------------------------------------------------------------------------------------------
+constexpr int kTile = 64, kTileElems = kTile * kTile;
+
+__device__ __forceinline__ uint32_t ycocg_to_565(int y16, int co16, int cg16) {
+  // codec.cpp:46-63 and :764-771 as written (int8 arithmetic, sign-extending uint16 casts)
+  const int8_t y = (int8_t)y16, co = (int8_t)co16, cg = (int8_t)cg16;
+  const int8_t t = (int8_t)(y - cg / 2);
+  const int8_t g = (int8_t)(cg + t), b = (int8_t)((t - co) / 2), r = (int8_t)(b + co);
+  uint16_t x = (uint16_t)r;
+  x = (uint16_t)(x << 6); x |= (uint16_t)g;
+  x = (uint16_t)(x << 5); x |= (uint16_t)b;
+  return x;
+}
+
+__global__ void __launch_bounds__(1024)
+k_inverse_planes(DecView v) {
+  extern __shared__ int16_t sm[];
+  int16_t *A = sm, *B = sm + 6 * kTileElems;     // [plane][y][x]
+  const int tiles_x = v.pbw / kTile;
+  const int tx = (blockIdx.x % tiles_x) * kTile, ty = (blockIdx.x / tiles_x) * kTile;
+  const int f = v.first + blockIdx.y;
+  const size_t pn = (size_t)v.pbw * v.pbh;
+  // MakeSigned (image_utils.h:243-266): symbol - 128 as int8
+  for (int e = threadIdx.x; e < 6 * kTileElems / 4; e += 1024) {
+    const int pl = e >> 10, idx = (e & 1023) * 4, y = idx >> 6, x = idx & 63;
+    const uint32_t s4 = *reinterpret_cast<const uint32_t *>(v.planes + ((size_t)f * 6 + pl) * pn + (size_t)(ty + y) * v.pbw + tx + x);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      A[pl * kTileElems + idx + q] = (int16_t)(int8_t)(uint8_t)(((s4 >> (8 * q)) & 0xFFu) - 128u);
+  }
+  __syncthreads();
+  for (int dim = 2; dim <= kTile; dim <<= 1) {
+    const int half = dim >> 1, items = 6 * half * dim;
+    const int sh = 31 - __clz(half);                       // half is a power of two
+    // rows (wavelet.cpp:141-144): even samples ...
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int k = e & (half - 1), r = (e >> sh) & (dim - 1), pl = e >> (2 * sh + 1);
+      const int16_t *a = A + pl * kTileElems + r * kTile;
+      B[pl * kTileElems + r * kTile + 2 * k] = (int16_t)(a[k] - (a[half + max(k - 1, 0)] + a[half + k] + 2) / 4);
+    }
+    __syncthreads();
+    // ... odd samples
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int k = e & (half - 1), r = (e >> sh) & (dim - 1), pl = e >> (2 * sh + 1);
+      int16_t *b = B + pl * kTileElems + r * kTile;
+      b[2 * k + 1] = (int16_t)(A[pl * kTileElems + r * kTile + half + k] + (b[2 * k] + b[min(2 * k + 2, dim - 2)]) / 2);
+    }
+    __syncthreads();
+    // columns (:148-152): even samples ...
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int c = e & (dim - 1), k = (e >> (sh + 1)) & (half - 1), pl = e >> (2 * sh + 1);
+      const int16_t *b = B + pl * kTileElems + c;
+      A[pl * kTileElems + 2 * k * kTile + c] =
+          (int16_t)(b[k * kTile] - (b[(half + max(k - 1, 0)) * kTile] + b[(half + k) * kTile] + 2) / 4);
+    }
+    __syncthreads();
+    // ... odd samples
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int c = e & (dim - 1), k = (e >> (sh + 1)) & (half - 1), pl = e >> (2 * sh + 1);
+      int16_t *a = A + pl * kTileElems + c;
+      a[(2 * k + 1) * kTile] =
+          (int16_t)(B[pl * kTileElems + (half + k) * kTile + c] + (a[2 * k * kTile] + a[min(2 * k + 2, dim - 2) * kTile]) / 2);
+    }
+    __syncthreads();
+  }
+  // endpoints + the index word gathered through the collapsed link -> PhysicalDXTBlock
+  for (int e = threadIdx.x; e < kTileElems; e += 1024) {
+    const int y = e >> 6, x = e & 63;
+    if (ty + y >= v.bh || tx + x >= v.bw) continue;
+    const uint32_t ep1 = ycocg_to_565(A[e], A[kTileElems + e], A[2 * kTileElems + e]);
+    const uint32_t ep2 = ycocg_to_565(A[3 * kTileElems + e], A[4 * kTileElems + e], A[5 * kTileElems + e]);
+    const size_t n = (size_t)f * v.nb + (size_t)(ty + y) * v.bw + tx + x;
+    const uint32_t word = v.words[v.link[n]];
+    v.blocks[n] = (uint64_t)(ep1 | (ep2 << 16)) | ((uint64_t)word << 32);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// D3: DXT1 blocks -> RGB8 rows.  One CTA per run of 128 blocks of a block row: palettes in
+// registers, the four pixel rows staged in shared memory, written back as coalesced 32-bit words
+// (a row of a run is 1536 contiguous bytes of the frame).
+// ------------------------------------------------------------------------------------------
+constexpr int kRun = 128;
+
+__global__ void __launch_bounds__(kRun)
+k_dxt1_to_rgb(DecView v) {
+  __shared__ uint32_t rows[4][kRun * 3];
+  const int runs_x = (v.bw + kRun - 1) / kRun;
+  const int by = blockIdx.x / runs_x, bx0 = (blockIdx.x % runs_x) * kRun;
+  const int f = v.first + blockIdx.y;
+  const int bx = bx0 + threadIdx.x;
+  const int nrun = min(kRun, v.bw - bx0);
+  if (bx < v.bw) {
+    const uint64_t blk = v.blocks[(size_t)f * v.nb + (size_t)by * v.bw + bx];
+    uint32_t pal[4];
+    palette_of_block(blk, pal);
+    const uint32_t word = (uint32_t)(blk >> 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t c[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t s = (word >> (2 * (4 * j + i))) & 3u;
+        c[i] = (s & 2u) ? ((s & 1u) ? pal[3] : pal[2]) : ((s & 1u) ? pal[1] : pal[0]);
+      }
+      // four RGBX pixels -> 12 bytes R G B R | G B R G | B R G B
+      rows[j][3 * threadIdx.x + 0] = c[0] | (c[1] << 24);
+      rows[j][3 * threadIdx.x + 1] = (c[1] >> 8) | (c[2] << 16);
+      rows[j][3 * threadIdx.x + 2] = (c[2] >> 16) | (c[3] << 8);
+    }
+  }
+  __syncthreads();
+  uint8_t *frame = v.rgb + (size_t)f * v.w * v.h * 3;
+  for (int j = 0; j < 4; ++j) {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(frame + ((size_t)(4 * by + j) * v.w + 4 * bx0) * 3);
+    for (int i = threadIdx.x; i < 3 * nrun; i += kRun) dst[i] = rows[j][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Launch wrappers
+// ------------------------------------------------------------------------------------------
+int dec_jump_passes(int gop, int nb) {
+  // a chain is at most gop * nb links long and every pass at least halves the longest one
+  long long depth = (long long)gop * nb;
+  int p = 1;
+  while ((1ll << p) < depth) ++p;
+  return p + 1;
+}
+
+int launch_decode_words(const DecView &v, cudaStream_t s) {
+  dim3 grid(dec_chunks(v.nb), v.count);
+  k_dec_count<<<grid, kChunk, 0, s>>>(v);
+  k_dec_links<<<grid, kChunk, 0, s>>>(v);
+  const int passes = dec_jump_passes(v.gop, v.nb);
+  const size_t total = (size_t)v.count * v.nb;
+  int ctas = (int)((total + 1023) / 1024);
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  for (int p = 0; p < passes; ++p) k_dec_jump<<<ctas, 256, 0, s>>>(v, p);
+  return 2 + passes;
+}
+
+cudaError_t decode_kernels_init() {
+  return cudaFuncSetAttribute(k_inverse_planes, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(12 * kTileElems * sizeof(int16_t)));
+}
+
+int launch_inverse_planes(const DecView &v, cudaStream_t s) {
+  dim3 grid((v.pbw / kTile) * (v.pbh / kTile), v.count);
+  k_inverse_planes<<<grid, 1024, 12 * kTileElems * sizeof(int16_t), s>>>(v);
+  return 1;
+}
+
+int launch_dxt1_to_rgb(const DecView &v, cudaStream_t s) {
+  dim3 grid(((v.bw + kRun - 1) / kRun) * v.bh, v.count);
+  k_dxt1_to_rgb<<<grid, kRun, 0, s>>>(v);
+  return 1;
+}
+
+}  // namespace mptc

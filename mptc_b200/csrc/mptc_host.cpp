@@ -147,6 +147,83 @@ void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, s
   mb.finish(b, ob, start_b);
 }
 
+// ---- decoder ---------------------------------------------------------------------------------
+namespace {
+constexpr unsigned kTableShift = 8;                            // 128 buckets over the 15-bit range
+constexpr unsigned kTableSize = (1u << kLengthShift) >> kTableShift;
+}  // namespace
+
+RangeDecoder::RangeDecoder(unsigned symbols)
+    : n_(symbols < 257 ? 257 : symbols), dist_(n_ + 1), count_(n_), start_(kTableSize) {}
+
+void RangeDecoder::reset_model() {     // Adaptive_Data_Model::reset (arithmetic_codec.cpp:818-829)
+  total_ = 0;
+  cycle_ = n_;
+  for (unsigned k = 0; k < n_; ++k) count_[k] = 1;
+  update_model();
+  until_ = cycle_ = (n_ + 6) >> 1;
+}
+
+void RangeDecoder::update_model() {    // Adaptive_Data_Model::update(false) (:781-816)
+  if ((total_ += cycle_) > (1u << kLengthShift)) {
+    total_ = 0;
+    for (unsigned k = 0; k < n_; ++k) total_ += (count_[k] = (count_[k] + 1) >> 1);
+  }
+  const uint32_t scale = 0x80000000u / total_;
+  uint32_t sum = 0;
+  unsigned t = 0;
+  for (unsigned k = 0; k < n_; ++k) {
+    dist_[k] = (scale * sum) >> (31 - kLengthShift);
+    sum += count_[k];
+    for (; t < kTableSize && (t << kTableShift) < dist_[k]; ++t) start_[t] = (uint16_t)(k - 1);
+  }
+  for (; t < kTableSize; ++t) start_[t] = (uint16_t)(n_ - 1);
+  dist_[n_] = 1u << kLengthShift;      // sentinel: the scan below stops at the last symbol
+  cycle_ = (5 * cycle_) >> 2;
+  const uint32_t max_cycle = (n_ + 6) << 3;
+  if (cycle_ > max_cycle) cycle_ = max_cycle;
+  until_ = cycle_;
+}
+
+bool RangeDecoder::decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n) {
+  reset_model();
+  const uint8_t *p = code, *const end = code + nbytes;
+  size_t overrun = 0;
+  auto next = [&]() -> uint32_t {
+    if (p < end) return *p++;
+    ++overrun;
+    return 0;
+  };
+  uint32_t value = 0, length = 0xFFFFFFFFu;
+  for (int i = 0; i < 4; ++i) value = (value << 8) | next();   // start_decoder
+  uint32_t until = until_;
+  const uint32_t *dist = dist_.data();
+  bool ok = true;
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t len = length >> kLengthShift;
+    uint32_t dv = value / len;
+    if (dv >= (1u << kLengthShift)) dv = (1u << kLengthShift) - 1;   // only on corrupt input
+    uint32_t s = start_[dv >> kTableShift];
+    while (dist[s + 1] <= dv) ++s;
+    const uint32_t x = dist[s] * len;
+    const uint32_t y = s + 1 == n_ ? length : dist[s + 1] * len;     // last symbol: y = old length
+    value -= x;
+    length = y - x;
+    while (length < kMinLength) {                                    // renorm_dec_interval
+      value = (value << 8) | next();
+      length <<= 8;
+    }
+    ok &= s < 256;
+    sym[i] = (uint8_t)s;
+    ++count_[s];
+    if (--until == 0) {
+      update_model();
+      until = until_;
+    }
+  }
+  return ok && overrun <= 4;
+}
+
 namespace {
 
 void put_u32(std::vector<uint8_t> &v, uint32_t x) {
@@ -434,6 +511,147 @@ int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, i
         r = copy_out(bytes, out, cap, out_bytes);
       }
     }
+  }
+  return r;
+}
+
+// ---- decoder side ------------------------------------------------------------------------------
+
+int mptc_arith_decode(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n) {
+  if ((!code && nbytes) || (!sym && n)) return MPTC_E_ARG;
+  RangeDecoder dec;
+  return dec.decode_all(code, nbytes, sym, n) ? MPTC_OK : MPTC_E_DATA;
+}
+
+int mptc_stream_info(const uint8_t *stream, size_t bytes, mptc_stream_header *hdr) {
+  if (!stream || !hdr) return MPTC_E_ARG;
+  if (bytes < 34) return MPTC_E_DATA;
+  uint32_t v[2], g, mx[5];
+  memcpy(v, stream, 8);                 // reader: codec.cpp:1172-1184
+  memcpy(&g, stream + 10, 4);
+  memcpy(mx, stream + 14, 20);
+  hdr->height = (int)v[0]; hdr->width = (int)v[1];
+  hdr->gop = stream[8]; hdr->search_area = stream[9];
+  hdr->n_groups = (int)g;
+  hdr->n_frames = (int)g * hdr->gop;
+  hdr->max_unique_bytes = mx[0]; hdr->max_comp_palette = mx[1]; hdr->max_comp_motion = mx[2];
+  hdr->max_comp_ep_y = mx[3]; hdr->max_comp_ep_c = mx[4];
+  if (hdr->width < 4 || hdr->height < 4 || (hdr->width & 3) || (hdr->height & 3) || hdr->width > 65536 ||
+      hdr->height > 65536 || hdr->gop < 1 || hdr->search_area < 1 || hdr->search_area > 63 || g < 1 || g > (1u << 24))
+    return MPTC_E_DATA;
+  return MPTC_OK;
+}
+
+// DecompressMultiUnique (codec.cpp:1161-1305) with the work re-cut for the machine: the stream is
+// walked once to find its records (sizes only), every record is an independent arithmetic-decoder
+// job for the host thread pool (a group's palette + five per frame, written straight into pinned
+// staging in the layout the kernels read), and as soon as all jobs of a group are done that
+// group's symbols go to the GPU and its frames are reconstructed there -- all frames of the group
+// in the same launches -- while the pool is already decoding the next groups.
+int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, int threads, uint64_t *blocks_out,
+                       uint8_t *rgb_out, mptc_decode_stats *stats) {
+  if (!ctx || !stream) return MPTC_E_ARG;
+  const auto t0 = std::chrono::steady_clock::now();
+  mptc_stream_header H;
+  if (int r = mptc_stream_info(stream, bytes, &H)) return r;
+  const int gop = H.gop, n_frames = H.n_frames, w = H.width, h = H.height;
+  const size_t nb = (size_t)(w / 4) * (h / 4);
+  const size_t ps = (size_t)((w / 4 + 63) / 64 * 64) * ((h / 4 + 63) / 64 * 64);
+  struct Rec { const uint8_t *code; size_t nbytes; uint8_t *dst; size_t n; int group; };
+  std::vector<Rec> recs;
+  recs.reserve((size_t)n_frames * 5 + H.n_groups);
+  std::vector<size_t> pal_off(H.n_groups + 1, 0);   // byte offset of every group's palette in `pal`
+  // pass 1: locate the records
+  size_t off = 34, pal_total = 0;
+  auto get_u32 = [&](uint32_t &x) {
+    if (off + 4 > bytes) return false;
+    memcpy(&x, stream + off, 4);
+    off += 4;
+    return true;
+  };
+  struct GroupHdr { size_t pal_code_off; uint32_t pal_code_bytes, unique_bytes; };
+  std::vector<GroupHdr> groups(H.n_groups);
+  std::vector<uint32_t> n_unique_v((size_t)n_frames);
+  struct FrameRec { size_t off[5]; uint32_t nbytes[5]; };
+  std::vector<FrameRec> frs((size_t)n_frames);
+  for (int g = 0; g < H.n_groups; ++g) {
+    uint32_t cpal, ub;
+    if (!get_u32(cpal) || off + cpal > bytes) return MPTC_E_DATA;
+    groups[g].pal_code_off = off; groups[g].pal_code_bytes = cpal;
+    off += cpal;
+    if (!get_u32(ub) || (ub & 3) || ub > (uint64_t)gop * nb * 4) return MPTC_E_DATA;
+    groups[g].unique_bytes = ub;
+    pal_off[g] = pal_total;
+    pal_total += ub;
+    uint64_t group_unique = 0;
+    for (int k = 0; k < gop; ++k) {
+      const int f = g * gop + k;
+      if (!get_u32(n_unique_v[f]) || n_unique_v[f] > nb) return MPTC_E_DATA;
+      group_unique += n_unique_v[f];
+      for (int q = 0; q < 5; ++q) {
+        uint32_t sz;
+        if (!get_u32(sz) || off + sz > bytes) return MPTC_E_DATA;
+        frs[f].off[q] = off; frs[f].nbytes[q] = sz;
+        off += sz;
+      }
+    }
+    if (group_unique * 4 != ub) return MPTC_E_DATA;
+  }
+  pal_off[H.n_groups] = pal_total;
+  // pinned staging in the layout the kernels read
+  const size_t n = (size_t)n_frames;
+  uint8_t *motion = static_cast<uint8_t *>(ctx_pinned(ctx, 0, n * nb * 2));
+  uint8_t *pal = static_cast<uint8_t *>(ctx_pinned(ctx, 1, pal_total + 4));
+  uint8_t *planes = static_cast<uint8_t *>(ctx_pinned(ctx, 3, n * 6 * ps));
+  if (!motion || !pal || !planes) return MPTC_E_NOMEM;
+  if (int r = mptc_gpu_seq_reserve(ctx, w, h, n_frames)) return r;
+  for (int g = 0; g < H.n_groups; ++g) {
+    recs.push_back({stream + groups[g].pal_code_off, groups[g].pal_code_bytes, pal + pal_off[g], groups[g].unique_bytes, g});
+    for (int k = 0; k < gop; ++k) {
+      const size_t f = (size_t)g * gop + k;
+      uint8_t *pl = planes + f * 6 * ps;
+      uint8_t *dst[5] = {motion + f * 2 * nb, pl, pl + ps, pl + 3 * ps, pl + 4 * ps};   // Y1, Co|Cg 1, Y2, Co|Cg 2
+      const size_t cnt[5] = {2 * nb, ps, 2 * ps, ps, 2 * ps};
+      for (int q = 0; q < 5; ++q) recs.push_back({stream + frs[f].off[q], frs[f].nbytes[q], dst[q], cnt[q], g});
+    }
+  }
+  std::vector<std::atomic<int>> left(H.n_groups);
+  for (int g = 0; g < H.n_groups; ++g) left[g].store(1 + 5 * gop);
+  std::atomic<int> next(0), corrupt(0);
+  const int n_recs = (int)recs.size();
+  auto worker = [&]() {
+    RangeDecoder dec;
+    for (int i = next.fetch_add(1); i < n_recs; i = next.fetch_add(1)) {
+      const Rec &r = recs[i];
+      if (!dec.decode_all(r.code, r.nbytes, r.dst, r.n)) corrupt.store(1);
+      left[r.group].fetch_sub(1, std::memory_order_release);
+    }
+  };
+  if (threads < 1) threads = 1;
+  if (threads > n_recs) threads = n_recs;
+  const auto t1 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) pool.emplace_back(worker);
+  // the calling thread feeds the GPU group by group
+  int r = MPTC_OK;
+  for (int g = 0; g < H.n_groups && r == MPTC_OK; ++g) {
+    while (left[g].load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    if (corrupt.load()) break;
+    const size_t f0 = (size_t)g * gop;
+    r = mptc_gpu_seq_decode_upload(ctx, (int)f0, gop, motion + f0 * 2 * nb, reinterpret_cast<const uint32_t *>(pal + pal_off[g]),
+                                   n_unique_v.data() + f0, 0, planes + f0 * 6 * ps);
+    if (r == MPTC_OK) r = mptc_gpu_seq_decode(ctx, (int)f0, gop, H.search_area, gop, rgb_out != nullptr);
+  }
+  for (auto &th : pool) th.join();
+  const auto t2 = std::chrono::steady_clock::now();
+  if (r == MPTC_OK && corrupt.load()) r = MPTC_E_DATA;
+  if (r == MPTC_OK) r = mptc_gpu_seq_decode_download(ctx, 0, n_frames, blocks_out, rgb_out);
+  const auto t3 = std::chrono::steady_clock::now();
+  if (stats) {
+    stats->header = H;
+    stats->entropy_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    stats->total_ms = std::chrono::duration<double, std::milli>(t3 - t0).count();
+    stats->symbols = (uint64_t)n * (2 * nb + 6 * ps) + pal_total;
   }
   return r;
 }

@@ -29,6 +29,28 @@ class RangeEncoder {
   uint32_t total_ = 0, cycle_ = 0, until_ = 0;
 };
 
+// The decoding side of the same coder (Arithmetic_Codec::decode, arithmetic_codec.cpp:391-444,
+// start_decoder :511-522, renorm_dec_interval :100-105) with the decoder flavour of the adaptive
+// model.  The symbol search is a coarse table plus a short linear scan instead of the reference's
+// table plus bisection: any search for the s with dist[s] <= value/length < dist[s+1] decodes the
+// same symbol.
+class RangeDecoder {
+ public:
+  explicit RangeDecoder(unsigned symbols = 257);
+  // Decodes n byte symbols from code[0..nbytes).  Reads past the end of the code see zeros (a
+  // valid stream never needs more than the coder's 4-byte look-ahead).  Returns false if the code
+  // ran out more than 4 bytes early or a symbol outside 0..255 appeared (corrupt stream).
+  bool decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n);
+
+ private:
+  void reset_model();
+  void update_model();
+  unsigned n_;
+  std::vector<uint32_t> dist_, count_;
+  std::vector<uint16_t> start_;   // start_[t] = largest s with dist[s] <= t << kTableShift
+  uint32_t total_ = 0, cycle_ = 0, until_ = 0;
+};
+
 }  // namespace mptc
 
 struct mptc_gpu_ctx;

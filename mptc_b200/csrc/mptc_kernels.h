@@ -46,4 +46,30 @@ void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_co
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s);
 int intra_wavefront_max_ctas(int device);
 
+// ---- decoder side (mptc_decode.cu) -------------------------------------------------------
+// Frames [first, first + count) of the device-resident sequence, every gop-th one intra.
+struct DecView {
+  const uint8_t *motion;        // [F][nb][2]   decoded motion bytes
+  const uint32_t *unique;       // unique index words; frame f's start at unique[unique_off[f]]
+  const uint32_t *unique_off;   // [F]
+  const uint32_t *n_unique;     // [F]
+  const uint8_t *planes;        // [F][6][pbh][pbw] decoded wavelet symbols
+  uint32_t *words;              // [F][nb]   index word of the unique blocks
+  int *link;                    // [F][nb]   node the block's index word comes from
+  uint32_t *chunk_counts;       // [F][dec_chunks(nb)]
+  int *errors;                  // [0] invalid motion vectors (cumulative until read)
+  int *status;                  // [1 + p] pass p of the pointer jumping left work ([0] unused)
+  uint64_t *blocks;             // [F][nb]   out: PhysicalDXTBlock
+  uint8_t *rgb;                 // [F][h][w][3] out (optional)
+  int w, h, bw, bh, nb, pbw, pbh;
+  int first, count, gop, sa;
+};
+int dec_chunks(int nb);
+int dec_jump_passes(int gop, int nb);
+cudaError_t decode_kernels_init();
+// Each returns the number of kernels it launched.
+int launch_decode_words(const DecView &v, cudaStream_t s);
+int launch_inverse_planes(const DecView &v, cudaStream_t s);
+int launch_dxt1_to_rgb(const DecView &v, cudaStream_t s);
+
 }  // namespace mptc

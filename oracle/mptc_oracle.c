@@ -667,6 +667,23 @@ void mptc_oracle_inverse_planes(const uint8_t *planes, int bw, int bh, uint16_t 
 }
 
 /* ------------------------------------------------------------------------------------
+ * The decoded picture: DXTImage::DecompressedImage (dxt_image.cpp:463-479) = GetColorAt over
+ * SetLogicalBlocks / PhysicalToLogical (:198-227); transparent black of the 3-colour mode
+ * reads as (0,0,0).  rgb_out: w*h*3 bytes, row-major.
+ * ---------------------------------------------------------------------------------- */
+void mptc_oracle_decode_rgb(const uint64_t *blocks, int w, int h, uint8_t *rgb_out) {
+  int bw = w >> 2;
+  pal4 p;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      uint64_t blk = blocks[(size_t)(y >> 2) * bw + (x >> 2)];
+      palette_from_physical(blk, &p);
+      const uint8_t *c = p.c[((uint32_t)(blk >> 32) >> (2 * ((y & 3) * 4 + (x & 3)))) & 3];
+      memcpy(rgb_out + ((size_t)y * w + x) * 3, c, 3);
+    }
+}
+
+/* ------------------------------------------------------------------------------------
  * PSNR of the decoded blocks (dxt_image.cpp:363-383 over PhysicalToLogical(blocks))
  * ---------------------------------------------------------------------------------- */
 double mptc_oracle_psnr(const uint8_t *rgb, int w, int h, const uint64_t *blocks) {

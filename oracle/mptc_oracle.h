@@ -62,6 +62,9 @@ int mptc_oracle_arith_decode(const uint8_t *code, int nbytes, uint8_t *sym_out, 
 /* ReconstructEndPoints (codec.cpp:697-800): 6 symbol planes -> ep1 / ep2 (bw*bh RGB565 each). */
 void mptc_oracle_inverse_planes(const uint8_t *planes, int bw, int bh, uint16_t *ep1, uint16_t *ep2);
 
+/* DXTImage::DecompressedImage (dxt_image.cpp:463-479) of decoded physical blocks: w*h*3 bytes. */
+void mptc_oracle_decode_rgb(const uint64_t *blocks, int w, int h, uint8_t *rgb_out);
+
 /* PSNR of the decoded physical blocks against the source (dxt_image.cpp:363-383 applied
  * to PhysicalToLogical of the emitted blocks). */
 double mptc_oracle_psnr(const uint8_t *rgb, int w, int h, const uint64_t *blocks);

@@ -33,6 +33,7 @@ def lib():
         L.mptc_oracle_arith_encode.argtypes = [vp, ci, vp, ci]
         L.mptc_oracle_arith_decode.argtypes = [vp, ci, vp, ci]
         L.mptc_oracle_inverse_planes.argtypes = [vp, ci, ci, vp, vp]
+        L.mptc_oracle_decode_rgb.argtypes = [vp, ci, ci, vp]
         L.mptc_oracle_psnr.restype = C.c_double
         L.mptc_oracle_psnr.argtypes = [vp, ci, ci, vp]
         L.mptc_oracle_tables.argtypes = [vp, vp]
@@ -162,6 +163,14 @@ def inverse_planes(planes: np.ndarray, bw: int, bh: int):
     ep2 = np.empty(bw * bh, dtype=np.uint16)
     lib().mptc_oracle_inverse_planes(planes.ctypes.data, bw, bh, ep1.ctypes.data, ep2.ctypes.data)
     return ep1, ep2
+
+
+def decode_rgb(blocks, w: int, h: int) -> np.ndarray:
+    """DXTImage::DecompressedImage of decoded physical blocks -> uint8 [h, w, 3]."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint64)
+    out = np.empty((h, w, 3), dtype=np.uint8)
+    lib().mptc_oracle_decode_rgb(blocks.ctypes.data, w, h, out.ctypes.data)
+    return out
 
 
 def parse_stream(stream: bytes):

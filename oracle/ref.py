@@ -145,3 +145,20 @@ def write_png(path: str, rgb: np.ndarray):
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
     if lib().mptc_ref_write_png(path.encode(), rgb.shape[1], rgb.shape[0], rgb.ctypes.data) != 0:
         raise RuntimeError("stbi_write_png failed")
+
+
+def decode_stream(stream: bytes):
+    """The reference's own decoder functions driven over a stream in memory (see
+    mptc_ref_decode_stream): -> (blocks u64 [n, nb], rgb u8 [n, h, w, 3])."""
+    import struct
+    h, w, gop, _sa, n_groups = struct.unpack_from("<IIBBI", stream, 0)
+    n = gop * n_groups
+    nb = (w // 4) * (h // 4)
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    blocks = np.empty((n, nb), dtype=np.uint64)
+    rgb = np.empty((n, h, w, 3), dtype=np.uint8)
+    lib().mptc_ref_decode_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    r = lib().mptc_ref_decode_stream(buf.ctypes.data, buf.size, blocks.ctypes.data, rgb.ctypes.data)
+    if r != n:
+        raise RuntimeError(f"reference decoder returned {r}")
+    return blocks, rgb

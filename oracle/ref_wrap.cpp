@@ -51,6 +51,20 @@ DXTImage::DXTImage(int width, int height, uint8_t *rgb) {
 }
 }  // namespace MPTC
 
+// Decoder functions the reference defines in codec.cpp (external linkage) but does not declare
+// in codec.h; declared here so the wrapper can drive them on a stream held in memory.
+namespace MPTC {
+void ReconstructDXTData(std::vector<uint32_t> &unique_indices,
+                        std::vector<std::tuple<uint8_t, uint8_t> > &motion_indices,
+                        std::unique_ptr<DXTImage> &curr_frame, std::unique_ptr<DXTImage> &prev_frame,
+                        uint8_t search_area, std::string ep_dir, uint32_t frame_number);
+void EntropyDecode(std::vector<uint8_t> &compressed_data, std::vector<uint8_t> &out_symbols, bool is_bit_model);
+void ReconstructEndPoints(std::unique_ptr<DXTImage> &dxt_image, std::unique_ptr<std::vector<uint8_t> > &wav_ep1_Y,
+                          std::unique_ptr<std::vector<uint8_t> > &wav_ep1_C,
+                          std::unique_ptr<std::vector<uint8_t> > &wav_ep2_Y,
+                          std::unique_ptr<std::vector<uint8_t> > &wav_ep2_C);
+}  // namespace MPTC
+
 using MPTC::DXTImage;
 
 struct RefFrame {
@@ -208,6 +222,74 @@ int mptc_ref_arith_encode(const uint8_t *sym, int n, uint8_t *out, int out_cap) 
 void mptc_ref_compress_multi_unique(const char *dir, const char *out_file, unsigned search_area,
                                     int thr, unsigned intra_interval, unsigned unique_interval) {
   MPTC::CompressMultiUnique(dir, out_file, search_area, thr, intra_interval, unique_interval, "");
+}
+
+// The reference's decoder on a stream held in memory: the loop of DecompressMultiUnique
+// (codec.cpp:1161-1305) with std::ifstream::read replaced by memcpy, every decoding step done by
+// the reference's own functions (EntropyDecode :560, the decoder-side DXTImage constructor
+// dxt_image.cpp:437, ReconstructDXTData :393, ReconstructEndPoints :697, SetLogicalBlocks,
+// DecompressedImage dxt_image.cpp:463).  DecompressMultiUnique itself only writes PNGs (and only
+// without NDEBUG); this returns the frames' physical blocks and decoded pixels.  Frame sizes must
+// be multiples of 256 (the reference's wavelet, image_processing.h:293-294).  Returns the frame
+// count, or -1 if the stream is truncated.
+int mptc_ref_decode_stream(const uint8_t *stream, int nbytes, uint64_t *blocks_out, uint8_t *rgb_out) {
+  size_t off = 0;
+  auto rd = [&](void *dst, size_t n) {
+    if (off + n > (size_t)nbytes) return false;
+    memcpy(dst, stream + off, n);
+    off += n;
+    return true;
+  };
+  uint32_t frame_height, frame_width, total_groups, mx[5];
+  uint8_t unique_interval, search_area;
+  if (!rd(&frame_height, 4) || !rd(&frame_width, 4) || !rd(&unique_interval, 1) || !rd(&search_area, 1) ||
+      !rd(&total_groups, 4) || !rd(mx, 20))
+    return -1;
+  const uint32_t num_blocks = (frame_height / 4 * frame_width / 4);
+  std::unique_ptr<DXTImage> prev_frame(nullptr), curr_frame(nullptr);
+  uint32_t frame_number = 0;
+  for (uint32_t g = 0; g < total_groups; ++g) {
+    uint32_t compressed_palette_size, unique_count, unique_idx_offset = 0;
+    if (!rd(&compressed_palette_size, 4)) return -1;
+    std::vector<uint8_t> compressed_combined_palette(compressed_palette_size);
+    if (!rd(compressed_combined_palette.data(), compressed_palette_size) || !rd(&unique_count, 4)) return -1;
+    std::vector<uint8_t> combined_8bit_palette(unique_count);
+    MPTC::EntropyDecode(compressed_combined_palette, combined_8bit_palette, false);
+    for (uint8_t k = 0; k < unique_interval; ++k) {
+      uint32_t num_unique, sz;
+      if (!rd(&num_unique, 4) || !rd(&sz, 4)) return -1;
+      std::vector<uint32_t> unique_indices(num_unique, 0);
+      memcpy(unique_indices.data(), combined_8bit_palette.data() + unique_idx_offset, 4 * (size_t)num_unique);
+      unique_idx_offset += 4 * num_unique;
+      std::vector<uint8_t> comp(sz), motion(2 * (size_t)num_blocks, 0);
+      if (!rd(comp.data(), sz)) return -1;
+      MPTC::EntropyDecode(comp, motion, false);
+      std::vector<std::tuple<uint8_t, uint8_t> > out_motion_indices;
+      for (size_t i = 0; i < motion.size(); i += 2) out_motion_indices.push_back(std::make_tuple(motion[i], motion[i + 1]));
+      std::unique_ptr<std::vector<uint8_t> > wav[4];
+      for (int q = 0; q < 4; ++q) {
+        wav[q].reset(new std::vector<uint8_t>((q & 1) ? 2 * (size_t)num_blocks : num_blocks));
+        if (!rd(&sz, 4)) return -1;
+        comp.resize(sz);
+        if (!rd(comp.data(), sz)) return -1;
+        MPTC::EntropyDecode(comp, *wav[q], false);
+      }
+      curr_frame.reset(new DXTImage(frame_width, frame_height, false, unique_indices));
+      MPTC::ReconstructDXTData(unique_indices, out_motion_indices, curr_frame, prev_frame, search_area, "/nonexistent",
+                               frame_number + 1);
+      MPTC::ReconstructEndPoints(curr_frame, wav[0], wav[1], wav[2], wav[3]);
+      curr_frame->SetLogicalBlocks();
+      if (blocks_out)
+        for (uint32_t i = 0; i < num_blocks; ++i) blocks_out[(size_t)frame_number * num_blocks + i] = curr_frame->_physical_blocks[i].dxt_block;
+      if (rgb_out) {
+        std::vector<uint8_t> px = curr_frame->DecompressedImage()->Pack();
+        memcpy(rgb_out + (size_t)frame_number * frame_width * frame_height * 3, px.data(), (size_t)frame_width * frame_height * 3);
+      }
+      prev_frame = std::move(curr_frame);
+      ++frame_number;
+    }
+  }
+  return (int)frame_number;
 }
 
 // Proves the supplied raw constructor == the reference's PNG constructor

@@ -77,7 +77,21 @@ def reference_stream(frames, sa, thr, gop):
         return open(out, "rb").read()
 
 
+def decode_fixture():
+    """The reference's own decoder (mptc_ref_decode_stream: the loop of DecompressMultiUnique over
+    the reference's EntropyDecode / ReconstructDXTData / ReconstructEndPoints / DecompressedImage)
+    run on the stream fixture: decoded blocks of every frame, hashes of the decoded pictures and
+    the first 16 pixel rows of the last one."""
+    g = np.load(os.path.join(HERE, "stream_256x256_sa4_gop2.npz"))
+    blocks, rgb = ref.decode_stream(g["stream"].tobytes())
+    np.savez_compressed(os.path.join(HERE, "decode_256x256_sa4_gop2.npz"), blocks=blocks,
+                        rgb_sha=np.array([sha(f) for f in rgb]), rgb_last_rows=rgb[-1, :16].copy())
+    print("wrote decode fixture", blocks.shape)
+
+
 def main():
+    if "--decode-only" in sys.argv:
+        return decode_fixture()
     assert ref.available(), "build oracle/_ref first: make -C oracle ref"
     assert ref.selfcheck_png(make_sequence(64, 64, 1)[0]) == 0
     for name, cfg in CASES.items():
@@ -105,6 +119,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "stream_256x256_sa4_gop2.npz"), params=np.array([256, 256, 4, 77, 4, 50, 2]),
                         frames_sha=np.array(sha(frames)), stream=np.frombuffer(stream, dtype=np.uint8))
     print("wrote stream", len(stream), "bytes")
+    decode_fixture()
 
 
 if __name__ == "__main__":

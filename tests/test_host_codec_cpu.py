@@ -72,3 +72,40 @@ def test_trailing_partial_group_is_dropped_like_the_reference():
     s3, st3 = capi.assemble_stream(w, h, 2, 50, 2, motion, unique, n_unique, planes)
     s2, st2 = capi.assemble_stream(w, h, 2, 50, 2, motion[:2], unique[:2], n_unique[:2], planes[:2])
     assert s3 == s2 and st3.n_groups == 1
+
+
+# ---- decoder side --------------------------------------------------------------------------------
+def test_arith_decode_inverts_reference_encodings():
+    """mptc_arith_decode (EntropyDecode, codec.cpp:560-577) on the reference's own encodings."""
+    g = load("arith")
+    for k in [k[4:] for k in g.files if k.startswith("sym_")]:
+        sym = g["sym_" + k]
+        assert np.array_equal(capi.arith_decode(g["enc_" + k].tobytes(), sym.size), sym), k
+
+
+def test_arith_decode_matches_oracle_and_round_trips():
+    rng = np.random.default_rng(6)
+    for n in (1, 2, 257, 4096, 150000):
+        s = np.clip(rng.normal(128, rng.uniform(0.5, 80), n), 0, 255).astype(np.uint8)
+        code = capi.arith_encode(s)
+        got = capi.arith_decode(code, n)
+        assert np.array_equal(got, s)
+        assert np.array_equal(got, port.arith_decode(code, n))
+
+
+def test_arith_decode_rejects_truncated_code():
+    s = np.random.default_rng(7).integers(0, 256, 5000, dtype=np.uint8)
+    code = capi.arith_encode(s)
+    with pytest.raises(capi.MptcError):
+        capi.arith_decode(code[: len(code) // 2], s.size)
+
+
+def test_stream_info_reads_the_reference_header():
+    g = load("stream_256x256_sa4_gop2")
+    w, h, n, _seed, sa, _thr, gop = [int(x) for x in g["params"]]
+    hdr = capi.stream_info(g["stream"].tobytes())
+    assert (hdr.width, hdr.height, hdr.gop, hdr.search_area, hdr.n_groups, hdr.n_frames) == (w, h, gop, sa, n // gop, n)
+    want = port.parse_stream(g["stream"].tobytes())["maxes"]
+    assert (hdr.max_unique_bytes, hdr.max_comp_palette, hdr.max_comp_motion, hdr.max_comp_ep_y, hdr.max_comp_ep_c) == tuple(want)
+    with pytest.raises(capi.MptcError):
+        capi.stream_info(g["stream"].tobytes()[:20])

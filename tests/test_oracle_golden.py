@@ -133,3 +133,17 @@ def test_reference_stream_decodes_to_reference_blocks():
         blocks, motion, unique = port.reencode(frames[i], i % gop == 0, sa, thr, init, prev)
         assert np.array_equal(decoded[i], blocks), f"frame {i}"
         prev = blocks
+
+
+def test_decoded_pictures_match_the_reference_decoder():
+    """Fixture from the reference's own decoder functions (gen_golden.decode_fixture): its decoded
+    blocks equal the restated stream decode, and its DecompressedImage equals decode_rgb."""
+    g = load("stream_256x256_sa4_gop2")
+    d = load("decode_256x256_sa4_gop2")
+    w, h = int(g["params"][0]), int(g["params"][1])
+    decoded = port.decode_stream(g["stream"].tobytes())
+    assert np.array_equal(decoded, d["blocks"])
+    for i in range(decoded.shape[0]):
+        rgb = port.decode_rgb(decoded[i], w, h)
+        assert sha(rgb) == str(d["rgb_sha"][i]), f"frame {i}"
+    assert np.array_equal(port.decode_rgb(decoded[-1], w, h)[:16], d["rgb_last_rows"])

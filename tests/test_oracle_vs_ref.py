@@ -54,3 +54,25 @@ def test_planes_and_payload():
     assert np.array_equal(mine, planes)
     assert port.arith_encode(planes[0]) == ref.arith_encode(planes[0])
     assert len(port.arith_encode(motion)) == int(sizes[0])
+
+
+def test_decoder_restatement_equals_reference_decoder():
+    """Encode with the product's host coder from reference results, decode with the reference's own
+    decoder functions and with the restatement: same blocks, same pictures."""
+    from mptc_b200 import capi
+    w, h, n, sa, thr, gop = 256, 256, 4, 6, 30, 2
+    frames = make_sequence(w, h, n, seed=31)
+    seq = ref.encode_sequence(frames, sa, thr, gop)
+    nb = (w // 4) * (h // 4)
+    motion = np.stack([fr.motion() for fr in seq])
+    n_unique = np.array([fr.unique().size for fr in seq], dtype=np.uint32)
+    unique = np.zeros((n, nb), dtype=np.uint32)
+    for i, fr in enumerate(seq):
+        unique[i, : n_unique[i]] = fr.unique()
+    planes = np.stack([port.endpoint_planes(fr.blocks(), w // 4, h // 4) for fr in seq])
+    stream, _ = capi.assemble_stream(w, h, sa, thr, gop, motion, unique, n_unique, planes)
+    blocks, rgb = ref.decode_stream(stream)
+    assert np.array_equal(blocks, np.stack([fr.blocks() for fr in seq]))
+    assert np.array_equal(port.decode_stream(stream), blocks)
+    for i in range(n):
+        assert np.array_equal(port.decode_rgb(blocks[i], w, h), rgb[i])
