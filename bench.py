@@ -136,9 +136,13 @@ def cpu_sample_frames(cores: int):
     return crops
 
 
-def run_cpu_sample(crops, kind: str):
+def run_cpu_sample(crops, kind: str, stages=None):
     """One GOP per thread (ThreadedCompressMultiUnique, codec.cpp:1781-1793, without its
-    5-thread cap).  Returns seconds of wall time."""
+    5-thread cap).  Returns seconds of wall time of stages A+B (DXT1 fit + index search).  With a
+    dict in `stages` (reference kind only) the wavelet + arithmetic-coding stage C
+    (EntropyEncode, codec.cpp:1115-1158) is then run and timed the same way, and the dict
+    receives the wall time of C and the per-stage CPU seconds summed over the threads."""
+    kept = []
     if kind == "reference":
         from oracle import ref
 
@@ -148,6 +152,8 @@ def run_cpu_sample(crops, kind: str):
                 fr = ref.RefFrame(pair[i], i == 0, SA, THR)   # DXTImage ctor (stb fit)
                 fr.reencode(prev)                             # DXTImage::Reencode
                 prev = fr
+                if stages is not None:
+                    kept.append(fr)
         ref.lib()  # load + silence before threading
         ref.RefFrame(crops[0][0][:16, :16], True, 1, THR)     # stb table init is not thread safe
     else:
@@ -162,7 +168,21 @@ def run_cpu_sample(crops, kind: str):
         t.start()
     for t in threads:
         t.join()
-    return time.perf_counter() - t0
+    t_ab = time.perf_counter() - t0
+    if stages is not None and kept:
+        per = (len(kept) + len(crops) - 1) // len(crops)
+        chunks = [kept[i:i + per] for i in range(0, len(kept), per)]
+        threads = [threading.Thread(target=lambda fs: [f.entropy_payload() for f in fs], args=(c,)) for c in chunks]
+        t0 = time.perf_counter()
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        stages["wall_c_s"] = time.perf_counter() - t0
+        tt = [f.times() for f in kept]
+        stages["cpu_s"] = {"fit": float(sum(t["fit_s"] for t in tt)), "search": float(sum(t["search_s"] for t in tt)),
+                           "wavelet_entropy": float(sum(t["entropy_s"] for t in tt))}
+    return t_ab
 
 
 def cpu_kind():
@@ -175,11 +195,19 @@ def cpu_baseline(steps: int = 1):
     kind = cpu_kind()
     crops = cpu_sample_frames(cores)
     pix = sum(c.shape[0] * c.shape[1] * c.shape[2] for c in crops)
-    times = [run_cpu_sample(crops, kind) for _ in range(steps)]
+    stages = {} if kind == "reference" else None
+    times = [run_cpu_sample(crops, kind, stages if i == steps - 1 else None) for i in range(steps)]
     t = float(np.mean(times))
-    return {"value": pix / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{cores} threads x one 2-frame GOP (intra+inter) of a 512x512 crop of the {W}x{H} sequence, "
-                      f"stages fit+search (DXTImage ctor + Reencode), sa={SA} thr={THR}; {t:.2f} s/step"}, times
+    out = {"value": pix / t / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{cores} threads x one 2-frame GOP (intra+inter) of a 512x512 crop of the {W}x{H} sequence, "
+                     f"stages fit+search (DXTImage ctor + Reencode), sa={SA} thr={THR}; {t:.2f} s/step",
+           "per_core": pix / t / 1e6 / cores}
+    if stages and "cpu_s" in stages:   # stage A / B / C separately
+        cs = stages["cpu_s"]
+        out["stages_mpixel_per_s_per_core"] = {k: (pix / 1e6 / v if v > 0 else None) for k, v in cs.items()}
+        out["with_wavelet_entropy"] = {"value": pix / (t + stages["wall_c_s"]) / 1e6, "unit": UNIT,
+                                       "note": "stages A+B+C (EntropyEncode per frame, codec.cpp:1115-1158) on the same threads"}
+    return out, times
 
 
 def reference_arm(args, rank: int):

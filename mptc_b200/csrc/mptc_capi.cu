@@ -35,7 +35,7 @@ struct mptc_gpu_ctx {
   uint8_t *d_rgb = nullptr;
   uint64_t *d_init = nullptr, *d_final = nullptr;
   uint8_t *d_motion = nullptr, *d_flags = nullptr, *d_planes = nullptr, *d_row_todo = nullptr;
-  uint32_t *d_unique = nullptr, *d_nunique = nullptr;
+  uint32_t *d_unique = nullptr, *d_nunique = nullptr, *d_chunks = nullptr;
   int *d_progress = nullptr;
   unsigned long long *d_cand = nullptr;
   int max_wave_ctas = 0;
@@ -119,7 +119,8 @@ void build_match_table(uint8_t *table, int bits) {
 void free_seq(mptc_gpu_ctx *c) {
   cudaFree(c->d_rgb); cudaFree(c->d_init); cudaFree(c->d_final); cudaFree(c->d_motion);
   cudaFree(c->d_flags); cudaFree(c->d_planes); cudaFree(c->d_unique); cudaFree(c->d_nunique);
-  cudaFree(c->d_progress); cudaFree(c->d_row_todo);
+  cudaFree(c->d_progress); cudaFree(c->d_row_todo); cudaFree(c->d_chunks);
+  c->d_chunks = nullptr;
   c->d_rgb = nullptr; c->d_init = c->d_final = nullptr; c->d_motion = c->d_flags = c->d_planes = nullptr;
   c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr; c->d_row_todo = nullptr;
   cudaFree(c->d_dec_words); cudaFree(c->d_dec_chunks); cudaFree(c->d_dec_uoff); cudaFree(c->d_dec_link);
@@ -164,7 +165,7 @@ DecView dec_view_of(const mptc_gpu_ctx *c, int first, int count, int gop, int sa
 SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
   SeqView v;
   v.rgb = c->d_rgb; v.init_blocks = c->d_init; v.final_blocks = c->d_final; v.motion = c->d_motion;
-  v.flags = c->d_flags; v.row_todo = c->d_row_todo; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.planes = c->d_planes;
+  v.flags = c->d_flags; v.row_todo = c->d_row_todo; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.chunk_counts = c->d_chunks; v.planes = c->d_planes;
   v.progress = c->d_progress; v.frame_bytes = c->frame_bytes;
   v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb;
   v.first = first; v.count = count; v.gop = gop;
@@ -305,7 +306,7 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
   {
     StageEvent &e = stage_begin(L, 4, t);
     launch_compact_unique(v, sa, c->d_cand, fk, gop, nf, t);
-    stage_end(c, e, t);
+    stage_end(c, e, t, 2);
   }
   if (planes) {
     StageEvent &e = stage_begin(L, 5, t);
@@ -492,6 +493,7 @@ int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
   CU(c, cudaMalloc(&c->d_row_todo, F * c->bh));
   CU(c, cudaMalloc(&c->d_unique, F * nb * 4));
   CU(c, cudaMalloc(&c->d_nunique, F * 4));
+  CU(c, cudaMalloc(&c->d_chunks, F * ((nb + 1023) / 1024) * 4));
   CU(c, cudaMalloc(&c->d_planes, F * c->plane_bytes));
   CU(c, cudaMalloc(&c->d_progress, F * c->bh * sizeof(int)));
   c->cap_frames = n_frames;

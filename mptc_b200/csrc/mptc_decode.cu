@@ -101,10 +101,12 @@ k_dec_links(DecView v) {
   v.link[n] = parent;
 }
 
-// One pointer-jumping pass, in place: link[n] <- link[link[n]].  Any value a racing thread reads
-// is an ancestor of its node, so stale reads only cost passes, never correctness.  status[1+pass]
-// is raised while some node still is more than one hop from its root; later passes return at once
-// when the previous one did not raise it.
+// One pointer-jumping pass, in place: every node walks up to kHops links towards its root and
+// stores where it got to.  Any value a racing thread reads is an ancestor of its node, so stale
+// reads only cost passes, never correctness.  status[1+pass] is raised while some node still has
+// not reached a root; later passes return at once when the previous one did not raise it.
+constexpr int kHops = 16;
+
 __global__ void __launch_bounds__(256)
 k_dec_jump(DecView v, int pass) {
   if (pass > 0 && v.status[pass] == 0) return;
@@ -112,12 +114,14 @@ k_dec_jump(DecView v, int pass) {
   bool more = false;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = base + i;
-    const int p = __ldcg(v.link + n);
-    const int q = __ldcg(v.link + p);
-    if (q != p) {
-      v.link[n] = q;
-      more |= __ldcg(v.link + q) != q;
+    const int p0 = __ldcg(v.link + n);
+    int p = p0, q = __ldcg(v.link + p);
+    for (int hop = 1; q != p && hop < kHops; ++hop) {
+      p = q;
+      q = __ldcg(v.link + p);
     }
+    if (q != p0) v.link[n] = q;
+    more |= q != p && __ldcg(v.link + q) != q;
   }
   if (__any_sync(0xffffffffu, more) && (threadIdx.x & 31) == 0) v.status[1 + pass] = 1;
 }
@@ -203,44 +207,59 @@ k_inverse_planes(DecView v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// D3: DXT1 blocks -> RGB8 rows.  One CTA per run of 128 blocks of a block row: palettes in
-// registers, the four pixel rows staged in shared memory, written back as coalesced 32-bit words
-// (a row of a run is 1536 contiguous bytes of the frame).
+// D3: DXT1 blocks -> RGB8 rows.  A CTA takes a run of 128 blocks of a block row (the loop lets a
+// capped grid walk several): palettes in registers, the four pixel rows of the run staged in
+// shared memory (double buffered), written
+// back as coalesced 16-byte words when the frame rows allow it (a row of a run is 1536 contiguous
+// bytes of the frame), 4-byte words otherwise.
 // ------------------------------------------------------------------------------------------
 constexpr int kRun = 128;
 
+template <bool VEC16>
 __global__ void __launch_bounds__(kRun)
-k_dxt1_to_rgb(DecView v) {
-  __shared__ uint32_t rows[4][kRun * 3];
-  const int runs_x = (v.bw + kRun - 1) / kRun;
-  const int by = blockIdx.x / runs_x, bx0 = (blockIdx.x % runs_x) * kRun;
-  const int f = v.first + blockIdx.y;
-  const int bx = bx0 + threadIdx.x;
-  const int nrun = min(kRun, v.bw - bx0);
-  if (bx < v.bw) {
-    const uint64_t blk = v.blocks[(size_t)f * v.nb + (size_t)by * v.bw + bx];
-    uint32_t pal[4];
-    palette_of_block(blk, pal);
-    const uint32_t word = (uint32_t)(blk >> 32);
+k_dxt1_to_rgb(DecView v, int runs_x, int n_runs) {
+  __shared__ __align__(16) uint32_t rows[2][4][kRun * 3];
+  int buf = 0;
+  for (int run = blockIdx.x; run < n_runs; run += gridDim.x, buf ^= 1) {
+    const int fi = run / (runs_x * v.bh), rr = run - fi * runs_x * v.bh;
+    const int by = rr / runs_x, bx0 = (rr - by * runs_x) * kRun;
+    const int f = v.first + fi;
+    const int bx = bx0 + threadIdx.x;
+    const int nrun = min(kRun, v.bw - bx0);
+    if (bx < v.bw) {
+      const uint64_t blk = __ldcs(reinterpret_cast<const unsigned long long *>(v.blocks) + (size_t)f * v.nb + (size_t)by * v.bw + bx);
+      uint32_t pal[4];
+      palette_of_block(blk, pal);
+      const uint32_t word = (uint32_t)(blk >> 32);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t c[4];
+      for (int j = 0; j < 4; ++j) {
+        uint32_t c[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t s = (word >> (2 * (4 * j + i))) & 3u;
-        c[i] = (s & 2u) ? ((s & 1u) ? pal[3] : pal[2]) : ((s & 1u) ? pal[1] : pal[0]);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t s = (word >> (2 * (4 * j + i))) & 3u;
+          c[i] = (s & 2u) ? ((s & 1u) ? pal[3] : pal[2]) : ((s & 1u) ? pal[1] : pal[0]);
+        }
+        // four RGBX pixels -> 12 bytes R G B R | G B R G | B R G B
+        rows[buf][j][3 * threadIdx.x + 0] = c[0] | (c[1] << 24);
+        rows[buf][j][3 * threadIdx.x + 1] = (c[1] >> 8) | (c[2] << 16);
+        rows[buf][j][3 * threadIdx.x + 2] = (c[2] >> 16) | (c[3] << 8);
       }
-      // four RGBX pixels -> 12 bytes R G B R | G B R G | B R G B
-      rows[j][3 * threadIdx.x + 0] = c[0] | (c[1] << 24);
-      rows[j][3 * threadIdx.x + 1] = (c[1] >> 8) | (c[2] << 16);
-      rows[j][3 * threadIdx.x + 2] = (c[2] >> 16) | (c[3] << 8);
     }
-  }
-  __syncthreads();
-  uint8_t *frame = v.rgb + (size_t)f * v.w * v.h * 3;
-  for (int j = 0; j < 4; ++j) {
-    uint32_t *dst = reinterpret_cast<uint32_t *>(frame + ((size_t)(4 * by + j) * v.w + 4 * bx0) * 3);
-    for (int i = threadIdx.x; i < 3 * nrun; i += kRun) dst[i] = rows[j][i];
+    __syncthreads();   // one barrier per run: the next run fills the other buffer
+    uint8_t *frame = v.rgb + (size_t)f * v.w * v.h * 3;
+    if (VEC16) {       // w % 16 == 0: every run row starts 16-byte aligned, 3*nrun/4 uint4 per row
+      const int per_row = 3 * nrun / 4;
+      for (int i = threadIdx.x; i < 4 * per_row; i += kRun) {
+        const int j = i / per_row, c = i - j * per_row;
+        uint4 *dst = reinterpret_cast<uint4 *>(frame + ((size_t)(4 * by + j) * v.w + 4 * bx0) * 3);
+        __stcs(dst + c, reinterpret_cast<const uint4 *>(rows[buf][j])[c]);
+      }
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(frame + ((size_t)(4 * by + j) * v.w + 4 * bx0) * 3);
+        for (int i = threadIdx.x; i < 3 * nrun; i += kRun) dst[i] = rows[buf][j][i];
+      }
+    }
   }
 }
 
@@ -248,10 +267,10 @@ k_dxt1_to_rgb(DecView v) {
 // Launch wrappers
 // ------------------------------------------------------------------------------------------
 int dec_jump_passes(int gop, int nb) {
-  // a chain is at most gop * nb links long and every pass at least halves the longest one
-  long long depth = (long long)gop * nb;
+  // a chain is at most gop * nb links long and every pass shortens the longest one kHops times
+  const long long depth = (long long)gop * nb;
   int p = 1;
-  while ((1ll << p) < depth) ++p;
+  for (long long reach = kHops; reach < depth; reach *= kHops) ++p;
   return p + 1;
 }
 
@@ -279,8 +298,13 @@ int launch_inverse_planes(const DecView &v, cudaStream_t s) {
 }
 
 int launch_dxt1_to_rgb(const DecView &v, cudaStream_t s) {
-  dim3 grid(((v.bw + kRun - 1) / kRun) * v.bh, v.count);
-  k_dxt1_to_rgb<<<grid, kRun, 0, s>>>(v);
+  const int runs_x = (v.bw + kRun - 1) / kRun;
+  const long long n_runs = (long long)runs_x * v.bh * v.count;
+  // one run per CTA: measured 3.2 TB/s against 2.95 TB/s for 16 persistent CTAs per SM looping over
+  // runs and 3.1 TB/s with 4-byte stores (profiles/micro/rgb_ab.py; write-only fill peak 3.86 TB/s)
+  const int ctas = (int)(n_runs < 0x7fffffff ? n_runs : 0x7fffffff);
+  if (v.w % 16 == 0) k_dxt1_to_rgb<true><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
+  else k_dxt1_to_rgb<false><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
   return 1;
 }
 

@@ -185,43 +185,78 @@ void RangeDecoder::update_model() {    // Adaptive_Data_Model::update(false) (:7
   until_ = cycle_;
 }
 
-bool RangeDecoder::decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n) {
-  reset_model();
-  const uint8_t *p = code, *const end = code + nbytes;
-  size_t overrun = 0;
-  auto next = [&]() -> uint32_t {
+// Decoder state kept in locals while symbols are decoded.
+struct RangeDecoder::State {
+  uint32_t value, length, until;
+  const uint8_t *p, *end;
+  size_t overrun;
+  bool ok;
+  uint32_t next() {
     if (p < end) return *p++;
     ++overrun;
     return 0;
-  };
-  uint32_t value = 0, length = 0xFFFFFFFFu;
-  for (int i = 0; i < 4; ++i) value = (value << 8) | next();   // start_decoder
-  uint32_t until = until_;
-  const uint32_t *dist = dist_.data();
-  bool ok = true;
-  for (size_t i = 0; i < n; ++i) {
-    const uint32_t len = length >> kLengthShift;
-    uint32_t dv = value / len;
-    if (dv >= (1u << kLengthShift)) dv = (1u << kLengthShift) - 1;   // only on corrupt input
-    uint32_t s = start_[dv >> kTableShift];
-    while (dist[s + 1] <= dv) ++s;
-    const uint32_t x = dist[s] * len;
-    const uint32_t y = s + 1 == n_ ? length : dist[s + 1] * len;     // last symbol: y = old length
-    value -= x;
-    length = y - x;
-    while (length < kMinLength) {                                    // renorm_dec_interval
-      value = (value << 8) | next();
-      length <<= 8;
-    }
-    ok &= s < 256;
-    sym[i] = (uint8_t)s;
-    ++count_[s];
-    if (--until == 0) {
-      update_model();
-      until = until_;
-    }
   }
-  return ok && overrun <= 4;
+};
+
+inline void RangeDecoder::begin(State &d, const uint8_t *code, size_t nbytes) {
+  reset_model();
+  d.p = code;
+  d.end = code + nbytes;
+  d.overrun = 0;
+  d.ok = true;
+  d.value = 0;
+  d.length = 0xFFFFFFFFu;
+  for (int i = 0; i < 4; ++i) d.value = (d.value << 8) | d.next();   // start_decoder
+  d.until = until_;
+}
+
+// Arithmetic_Codec::decode(Adaptive_Data_Model &) (arithmetic_codec.cpp:391-444)
+inline uint8_t RangeDecoder::step(State &d) {
+  const uint32_t *dist = dist_.data();
+  const uint32_t len = d.length >> kLengthShift;
+  uint32_t dv = d.value / len;
+  if (dv >= (1u << kLengthShift)) dv = (1u << kLengthShift) - 1;   // only on corrupt input
+  uint32_t s = start_[dv >> kTableShift];
+  while (dist[s + 1] <= dv) ++s;
+  const uint32_t x = dist[s] * len;
+  const uint32_t y = s + 1 == n_ ? d.length : dist[s + 1] * len;   // last symbol: y = old length
+  d.value -= x;
+  d.length = y - x;
+  while (d.length < kMinLength) {                                  // renorm_dec_interval
+    d.value = (d.value << 8) | d.next();
+    d.length <<= 8;
+  }
+  d.ok &= s < 256;
+  ++count_[s];
+  if (--d.until == 0) {
+    update_model();
+    d.until = until_;
+  }
+  return (uint8_t)s;
+}
+
+bool RangeDecoder::decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n) {
+  State d;
+  begin(d, code, nbytes);
+  for (size_t i = 0; i < n; ++i) sym[i] = step(d);
+  return d.ok && d.overrun <= 4;
+}
+
+// Two independent streams in one loop: each symbol costs a 32-bit division and a dependent table
+// walk, a second chain in flight hides most of that latency.
+bool RangeDecoder::decode_pair(RangeDecoder &ma, const uint8_t *ca, size_t ba, uint8_t *sa, size_t na,
+                               RangeDecoder &mb, const uint8_t *cb, size_t bb, uint8_t *sb, size_t nb) {
+  State a, b;
+  ma.begin(a, ca, ba);
+  mb.begin(b, cb, bb);
+  const size_t both = na < nb ? na : nb;
+  for (size_t i = 0; i < both; ++i) {
+    sa[i] = ma.step(a);
+    sb[i] = mb.step(b);
+  }
+  for (size_t i = both; i < na; ++i) sa[i] = ma.step(a);
+  for (size_t i = both; i < nb; ++i) sb[i] = mb.step(b);
+  return a.ok && b.ok && a.overrun <= 4 && b.overrun <= 4;
 }
 
 namespace {
@@ -617,18 +652,39 @@ int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, i
   }
   std::vector<std::atomic<int>> left(H.n_groups);
   for (int g = 0; g < H.n_groups; ++g) left[g].store(1 + 5 * gop);
+  // tasks = one or two records decoded by one thread in an interleaved loop: per frame the two Y
+  // and the two Co|Cg planes (equal lengths), motion streams of two frames of a group
+  struct Task { int a, b; };
+  std::vector<Task> tasks;
+  tasks.reserve(recs.size());
+  for (int g = 0; g < H.n_groups; ++g) {
+    const int r0 = g * (1 + 5 * gop);
+    tasks.push_back({r0, -1});                                  // palette
+    for (int k = 0; k < gop; ++k) {
+      const int fr = r0 + 1 + 5 * k;
+      if ((k & 1) == 0) tasks.push_back({fr, k + 1 < gop ? fr + 5 : -1});   // motion of frames k, k+1
+      tasks.push_back({fr + 2, fr + 4});
+      tasks.push_back({fr + 1, fr + 3});
+    }
+  }
   std::atomic<int> next(0), corrupt(0);
-  const int n_recs = (int)recs.size();
+  const int n_tasks = (int)tasks.size();
   auto worker = [&]() {
-    RangeDecoder dec;
-    for (int i = next.fetch_add(1); i < n_recs; i = next.fetch_add(1)) {
-      const Rec &r = recs[i];
-      if (!dec.decode_all(r.code, r.nbytes, r.dst, r.n)) corrupt.store(1);
-      left[r.group].fetch_sub(1, std::memory_order_release);
+    RangeDecoder da, db;
+    for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) {
+      const Rec &ra = recs[tasks[i].a];
+      bool ok;
+      if (tasks[i].b < 0) ok = da.decode_all(ra.code, ra.nbytes, ra.dst, ra.n);
+      else {
+        const Rec &rb = recs[tasks[i].b];
+        ok = RangeDecoder::decode_pair(da, ra.code, ra.nbytes, ra.dst, ra.n, db, rb.code, rb.nbytes, rb.dst, rb.n);
+      }
+      if (!ok) corrupt.store(1);
+      left[ra.group].fetch_sub(tasks[i].b < 0 ? 1 : 2, std::memory_order_release);
     }
   };
   if (threads < 1) threads = 1;
-  if (threads > n_recs) threads = n_recs;
+  if (threads > n_tasks) threads = n_tasks;
   const auto t1 = std::chrono::steady_clock::now();
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; ++t) pool.emplace_back(worker);

@@ -358,57 +358,78 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
 // K4: unique-palette compaction.  One CTA per frame; ordered prefix sum over the
 // "(255,255)" motion entries; emits the interp words in raster order.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_compact_unique(SeqView v, int sa, unsigned long long *__restrict__ cand_counts, int f0, int fstride) {
-  __shared__ int warp_sums[32];
-  __shared__ int s_base;
-  const int f = f0 + blockIdx.x * fstride;
-  const uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
-  const uint64_t *blocks = v.final_blocks + (size_t)f * v.nb;
-  uint32_t *out = v.unique + (size_t)f * v.nb;
+// Two passes over chunks of 1024 raster-ordered blocks (any number of CTAs per frame): count the
+// unique blocks of every chunk, then every chunk emits its words behind the chunks before it.
+constexpr int kCompactChunk = 1024;
+
+__global__ void __launch_bounds__(kCompactChunk)
+k_compact_count(SeqView v, int sa, unsigned long long *__restrict__ cand_counts, int f0, int fstride) {
+  __shared__ int warp_cnt[kCompactChunk / 32];
+  __shared__ unsigned long long warp_cand[2][kCompactChunk / 32];
+  const int f = f0 + blockIdx.y * fstride;
+  const int b = blockIdx.x * kCompactChunk + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const bool intra_frame = ((f - v.first) % v.gop) == 0;
   unsigned long long n_inter = 0, n_intra = 0;  // full-window candidate positions
-  if (threadIdx.x == 0) s_base = 0;
-  __syncthreads();
-  for (int start = 0; start < v.nb; start += 1024) {
-    int b = start + threadIdx.x;
-    bool uniq = false;
-    if (b < v.nb) {
-      uint16_t m = reinterpret_cast<const uint16_t *>(motion)[b];
-      uniq = (m == 0xFFFFu);
-      int bx = b % v.bw, by = b / v.bw;
-      bool inter_hit = !intra_frame && (m & 0x8080u) == 0x8080u && !uniq;
-      if (!intra_frame)
-        n_inter += (unsigned long long)(min(bx + sa, v.bw) - max(bx - sa, 0)) * (min(by + sa, v.bh) - max(by - sa, 0));
-      if (!inter_hit)
-        n_intra += (unsigned long long)min(by, 2 * sa - 1) * (min(bx + sa - 1, v.bw - 1) - max(bx - sa, 0) + 1) + min(bx, sa);
-    }
-    unsigned bal = __ballot_sync(0xffffffffu, uniq);
-    int in_warp = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_sums[wid] = __popc(bal);
-    __syncthreads();
-    int base = s_base;
-    int before = 0, total = 0;
-    for (int k = 0; k < 32; ++k) {
-      int c = warp_sums[k];
-      if (k < wid) before += c;
-      total += c;
-    }
-    if (uniq) out[base + before + in_warp] = (uint32_t)(blocks[b] >> 32);
-    __syncthreads();
-    if (threadIdx.x == 0) s_base = base + total;
-    __syncthreads();
+  bool uniq = false;
+  if (b < v.nb) {
+    const uint16_t m = reinterpret_cast<const uint16_t *>(v.motion + (size_t)f * v.nb * 2)[b];
+    uniq = (m == 0xFFFFu);
+    const int bx = b % v.bw, by = b / v.bw;
+    const bool inter_hit = !intra_frame && (m & 0x8080u) == 0x8080u && !uniq;
+    if (!intra_frame)
+      n_inter = (unsigned long long)(min(bx + sa, v.bw) - max(bx - sa, 0)) * (min(by + sa, v.bh) - max(by - sa, 0));
+    if (!inter_hit)
+      n_intra = (unsigned long long)min(by, 2 * sa - 1) * (min(bx + sa - 1, v.bw - 1) - max(bx - sa, 0) + 1) + min(bx, sa);
   }
-  if (threadIdx.x == 0) v.n_unique[f] = (uint32_t)s_base;
+  const unsigned bal = __ballot_sync(0xffffffffu, uniq);
   for (int d = 16; d > 0; d >>= 1) {
     n_inter += __shfl_xor_sync(0xffffffffu, n_inter, d);
     n_intra += __shfl_xor_sync(0xffffffffu, n_intra, d);
   }
-  if (lane == 0) {
-    atomicAdd(cand_counts + 0, n_inter);
-    atomicAdd(cand_counts + 1, n_intra);
+  if (lane == 0) { warp_cnt[wid] = __popc(bal); warp_cand[0][wid] = n_inter; warp_cand[1][wid] = n_intra; }
+  __syncthreads();
+  if (wid == 0) {
+    int c = warp_cnt[lane];
+    unsigned long long ci = warp_cand[0][lane], ca = warp_cand[1][lane];
+    for (int d = 16; d > 0; d >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, d);
+      ci += __shfl_xor_sync(0xffffffffu, ci, d);
+      ca += __shfl_xor_sync(0xffffffffu, ca, d);
+    }
+    if (lane == 0) {
+      v.chunk_counts[(size_t)f * gridDim.x + blockIdx.x] = (uint32_t)c;
+      if (ci) atomicAdd(cand_counts + 0, ci);
+      if (ca) atomicAdd(cand_counts + 1, ca);
+    }
   }
+}
+
+__global__ void __launch_bounds__(kCompactChunk)
+k_compact_unique(SeqView v, int f0, int fstride) {
+  __shared__ int warp_cnt[kCompactChunk / 32];
+  __shared__ int chunk_base;
+  const int f = f0 + blockIdx.y * fstride;
+  const int b = blockIdx.x * kCompactChunk + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool uniq = b < v.nb && reinterpret_cast<const uint16_t *>(v.motion + (size_t)f * v.nb * 2)[b] == 0xFFFFu;
+  const unsigned bal = __ballot_sync(0xffffffffu, uniq);
+  if (lane == 0) warp_cnt[wid] = __popc(bal);
+  if (wid == 0) {   // unique blocks of the chunks before this one
+    int c = 0;
+    for (int i = lane; i < (int)blockIdx.x; i += 32) c += (int)v.chunk_counts[(size_t)f * gridDim.x + i];
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (lane == 0) chunk_base = c;
+  }
+  __syncthreads();
+  int before = chunk_base + __popc(bal & ((1u << lane) - 1u)), total = chunk_base;
+  for (int k = 0; k < kCompactChunk / 32; ++k) {
+    const int c = warp_cnt[k];
+    if (k < wid) before += c;
+    total += c;
+  }
+  if (uniq) v.unique[(size_t)f * v.nb + before] = (uint32_t)(v.final_blocks[(size_t)f * v.nb + b] >> 32);
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) v.n_unique[f] = (uint32_t)total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -520,7 +541,9 @@ void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, 
 
 void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, int f0, int fstride, int nf,
                            cudaStream_t s) {
-  k_compact_unique<<<nf, 1024, 0, s>>>(v, sa, cand_counts, f0, fstride);
+  dim3 grid((v.nb + kCompactChunk - 1) / kCompactChunk, nf);
+  k_compact_count<<<grid, kCompactChunk, 0, s>>>(v, sa, cand_counts, f0, fstride);
+  k_compact_unique<<<grid, kCompactChunk, 0, s>>>(v, f0, fstride);
 }
 
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s) {

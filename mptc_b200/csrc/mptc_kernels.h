@@ -16,6 +16,7 @@ struct SeqView {
   uint8_t *row_todo;       // [F][bh]   1 = the row has blocks the inter search left over
   uint32_t *unique;        // [F][nb]
   uint32_t *n_unique;      // [F]
+  uint32_t *chunk_counts;  // [F][ceil(nb/1024)]  unique blocks per chunk (K4)
   uint8_t *planes;         // [F][6][pbh][pbw]
   int *progress;           // [F][bh]   wavefront progress counters
   size_t frame_bytes;

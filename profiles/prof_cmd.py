@@ -18,3 +18,7 @@ for _ in range(2):
     ctx.seq_encode(0, N, SA, THR, GOP)
     ctx.sync()
 print({k: round(ctx.last_encode_ms(k), 3) for k in capi.STAGES}, ctx.last_candidate_count())
+for _ in range(2):   # decoder side: from the symbols the encode left on the device
+    ctx.seq_decode(0, N, SA, GOP, rgb=True)
+    ctx.sync()
+print({k: round(ctx.last_decode_ms(k), 3) for k in capi.DECODE_STAGES})
