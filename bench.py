@@ -428,6 +428,10 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         "overlapped_stage_ms_per_step": stage_ms, "candidates_per_step": {"inter": n_inter, "intra": n_intra},
         "ncu": ev,
     }
+    if ev and "smsp__issue_active.avg.pct_of_peak_sustained_active" in ev:
+        # issue slots the kernel actually EXECUTES per available slot (ncu); `frac` above counts the
+        # algorithm's nominal slots, most of which the de-duplicating kernel never issues
+        roofline["frac_executed"] = ev["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100.0
     if clocks.get("sm_mhz"):
         roofline["frac_at_sampled_clock"] = achieved / (SM_COUNT * SCHEDULERS * LANES * clocks["sm_mhz"] * 1e6 / 1e12)
 
