@@ -260,6 +260,7 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         raise SystemExit("bench.py: no CUDA device -- the encoder hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

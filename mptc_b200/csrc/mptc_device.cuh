@@ -222,7 +222,10 @@ __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos
         u -= c0;
         u = ((unsigned)u < (unsigned)cn) ? u : dummy;
       }
-      winner_update_fast(ws, errcol[u * 33], p);
+      const int e = errcol[u * 33];
+      // (a per-row vote that skips the first / lastneg reductions for rows without an err_diff <= 0
+      // candidate was measured: 17.6 vs 14.5 ms -- such rows are rare on the benchmark content)
+      winner_update_fast(ws, e, p);
     }
     return;
   }
