@@ -89,3 +89,59 @@ def test_endpoint_planes_api(ctx):
     for bw, bh in [(64, 64), (128, 64), (100, 70)]:
         blocks = rng.integers(0, 2**63, size=bw * bh, dtype=np.uint64)
         assert np.array_equal(ctx.endpoint_planes(blocks, bw, bh), port.endpoint_planes(blocks, bw, bh))
+
+
+def _diverse_frames(w, h, n, seed, kind):
+    """Content whose blocks keep ~distinct index words: the word tables of the tiled kernels
+    overflow and the chunked paths run."""
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+    base = make_sequence(w, h, n, seed=seed).astype(np.int16)
+    if kind == "noisy":        # the synthetic sequence + strong noise (camera-like)
+        base += rng.integers(-24, 25, size=base.shape, dtype=np.int16)
+    else:                      # "mixed": noise on the left half, clean content on the right
+        base[:, :, : w // 2] += rng.integers(-40, 41, size=(n, h, w // 2, 3), dtype=np.int16)
+    return np.clip(base, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("w,h,n,sa,thr,gop,kind", [
+    (256, 128, 3, 16, 0, 3, "noise"),      # every window far beyond the 256-word table, intra + inter leftovers
+    (256, 128, 2, 16, 50, 2, "noisy"),
+    (384, 96, 3, 8, 0, 3, "mixed"),        # groups on the fast path next to overflowing ones
+    (192, 192, 2, 16, 10, 1, "noisy"),     # intra only (two CTAs per row)
+    (132, 100, 3, 12, 0, 2, "noise"),      # ragged group at the row end, odd block counts
+])
+def test_word_diverse_content_bit_exact(ctx, w, h, n, sa, thr, gop, kind):
+    frames = _diverse_frames(w, h, n, 17, kind)
+    ref = oracle_sequence(frames, sa, thr, gop)
+    out = ctx.encode_sequence(frames, sa, thr, gop)
+    for i in range(n):
+        init, blocks, motion, unique = ref[i]
+        assert np.array_equal(out["motion"][i], motion), f"frame {i}"
+        assert np.array_equal(out["blocks"][i], blocks), f"frame {i}"
+        nu = int(out["n_unique"][i])
+        assert nu == unique.size and np.array_equal(out["unique"][i, :nu], unique)
+
+
+def test_word_diverse_content_with_row_wavefront_for_leftovers(ctx):
+    """The same with K3s switched off, so that the row wavefront (and its chunked path) takes the
+    inter frames' leftovers as well."""
+    import os
+    from mptc_b200 import capi
+    os.environ["MPTC_SPARSE_MAX_PCT"] = "0"
+    try:
+        c2 = capi.Context(0)
+    finally:
+        del os.environ["MPTC_SPARSE_MAX_PCT"]
+    try:
+        for kind, thr in (("noise", 0), ("mixed", 0), ("noisy", 50)):
+            w, h, n, sa, gop = 256, 128, 3, 16, 3
+            frames = _diverse_frames(w, h, n, 23, kind)
+            ref = oracle_sequence(frames, sa, thr, gop)
+            out = c2.encode_sequence(frames, sa, thr, gop)
+            for i in range(n):
+                assert np.array_equal(out["motion"][i], ref[i][2]), f"{kind} frame {i}"
+                assert np.array_equal(out["blocks"][i], ref[i][1]), f"{kind} frame {i}"
+    finally:
+        c2.close()
