@@ -338,17 +338,19 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     cores = os.cpu_count() or 1
     host_threads = max(1, cores // max(world, 1))      # the ranks of one box share its cores
     stream_bytes = 0
+    stream_buf = np.empty(frames.nbytes // 4 + (1 << 20), dtype=np.uint8)   # the caller's output buffer, reused
     for _ in range(2):
-        stream_bytes = len(capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)[0])
+        stream_bytes = len(capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads, out=stream_buf)[0])
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)
+        capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads, out=stream_buf)
     barrier()
     stream_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
 
     # ---- decoder side: the stream just written back to DXT1 blocks ----------------
     stream = capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)[0]
+    dec_pin = capi.PinnedArray((FRAMES, nb), np.uint64)
     ctx.seq_encode(0, FRAMES, SA, THR, GOP)           # leaves motion / unique / planes on the device
     ctx.sync()
     dec_ms = {k: 0.0 for k in ("total", "words", "planes", "rgb")}
@@ -359,11 +361,11 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
                 dec_ms[k] += ctx.last_decode_ms(k) / args.steps
     ctx.sync()
     dec_stats = None
-    capi.decode_stream(ctx, stream, threads=host_threads)
+    capi.decode_stream(ctx, stream, threads=host_threads, blocks_out=dec_pin.array)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dec_blocks, _, dec_stats = capi.decode_stream(ctx, stream, threads=host_threads)
+        dec_blocks, _, dec_stats = capi.decode_stream(ctx, stream, threads=host_threads, blocks_out=dec_pin.array)
     barrier()
     dec_stream_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     dec_ok = bool(np.array_equal(dec_blocks, out["blocks"]))

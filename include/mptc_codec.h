@@ -44,6 +44,7 @@ typedef struct mptc_stream_stats {
   double entropy_ms;  /* wall time of arithmetic coding + assembly on `threads` host threads; in
                          mptc_encode_stream this phase starts while the GPU is still running */
   double total_ms;    /* wall time of the whole call */
+  double assemble_ms; /* of which: laying the records out in the caller's buffer */
 } mptc_stream_stats;
 
 /* Whole-sequence encode to the reference's stream format: 34-byte

@@ -314,7 +314,8 @@ class DecodeStats(C.Structure):
 class StreamStats(C.Structure):
     _fields_ = [("max_unique_bytes", C.c_uint32), ("max_comp_palette", C.c_uint32), ("max_comp_motion", C.c_uint32),
                 ("max_comp_ep_y", C.c_uint32), ("max_comp_ep_c", C.c_uint32), ("n_groups", C.c_uint32),
-                ("gpu_ms", C.c_double), ("entropy_ms", C.c_double), ("total_ms", C.c_double)]
+                ("gpu_ms", C.c_double), ("entropy_ms", C.c_double), ("total_ms", C.c_double),
+                ("assemble_ms", C.c_double)]
 
 
 def _codec():
@@ -353,13 +354,15 @@ def stream_info(stream: bytes) -> StreamHeader:
     return hdr
 
 
-def decode_stream(ctx: "Context", stream, threads=1, rgb=False):
-    """Stream bytes -> (blocks [n, nb], rgb [n, h, w, 3] or None, DecodeStats)."""
+def decode_stream(ctx: "Context", stream, threads=1, rgb=False, blocks_out=None):
+    """Stream bytes -> (blocks [n, nb], rgb [n, h, w, 3] or None, DecodeStats).  blocks_out: a
+    caller-owned (ideally page-locked) uint64 [n, nb] array to decode into."""
     buf = np.frombuffer(stream, dtype=np.uint8) if not isinstance(stream, np.ndarray) else stream
     hdr = stream_info(buf)
     n, w, h = hdr.n_frames, hdr.width, hdr.height
     nb = (w // 4) * (h // 4)
-    blocks = np.empty((n, nb), dtype=np.uint64)
+    blocks = np.empty((n, nb), dtype=np.uint64) if blocks_out is None else blocks_out
+    assert blocks.shape == (n, nb) and blocks.dtype == np.uint64 and blocks.flags["C_CONTIGUOUS"]
     pix = np.empty((n, h, w, 3), dtype=np.uint8) if rgb else None
     st = DecodeStats()
     r = _codec().mptc_decode_stream(ctx._p, buf.ctypes.data, buf.size, threads, blocks.ctypes.data, _ptr(pix),
@@ -418,12 +421,15 @@ def assemble_stream(w, h, search_area, err_threshold, gop, motion, unique, n_uni
     return out[: nbytes.value].tobytes(), st
 
 
-def encode_stream(ctx: "Context", frames: np.ndarray, search_area, err_threshold, gop, threads=1):
-    """GPU hot path + host arithmetic coding -> (stream bytes, StreamStats)."""
+def encode_stream(ctx: "Context", frames: np.ndarray, search_area, err_threshold, gop, threads=1, out=None):
+    """GPU hot path + host arithmetic coding -> (stream bytes, StreamStats).  With a caller-owned
+    uint8 buffer in `out` (reused across calls) the stream is returned as a view into it."""
     assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
     n, h, w = frames.shape[:3]
-    cap = frames.nbytes // 2 + (1 << 20)
-    out = np.empty(cap, dtype=np.uint8)
+    own = out is None
+    if own:
+        out = np.empty(frames.nbytes // 2 + (1 << 20), dtype=np.uint8)
+    cap = out.size
     nbytes = C.c_size_t(0)
     st = StreamStats()
     p = Params(search_area, err_threshold, gop)
@@ -431,4 +437,4 @@ def encode_stream(ctx: "Context", frames: np.ndarray, search_area, err_threshold
                                     C.byref(nbytes), C.byref(st))
     if r != MPTC_OK:
         raise MptcError(f"mptc_encode_stream failed: {r}: {ctx._L.mptc_gpu_last_error(ctx._p).decode()}")
-    return out[: nbytes.value].tobytes(), st
+    return (out[: nbytes.value].tobytes() if own else out[: nbytes.value]), st

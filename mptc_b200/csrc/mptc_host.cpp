@@ -7,7 +7,10 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <thread>
 
 namespace mptc {
@@ -16,6 +19,43 @@ namespace {
 constexpr uint32_t kMinLength = 0x01000000u;   // renormalisation threshold (AC__MinLength)
 constexpr unsigned kLengthShift = 15;          // DM__LengthShift
 }  // namespace
+
+// ---- scratch for the coder's output ----------------------------------------------------------
+// A stream's code is at most encode_bound(n) bytes but typically ~0.3 n.  Coding into a fresh
+// std::vector of the bound means zero-filling and page-faulting 2n bytes per stream -- with 16
+// host threads that (the kernel's page-fault path) cost more than the coding.  The pool below keeps
+// raw buffers alive across calls: pages are touched once, workers take a buffer for the duration
+// of a call and copy only the bytes actually produced.
+namespace {
+std::mutex g_scratch_mu;
+std::vector<Scratch> g_scratch_free;
+}  // namespace
+
+Scratch scratch_acquire(size_t bytes) {
+  Scratch s;
+  {
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    size_t best = g_scratch_free.size();
+    for (size_t i = 0; i < g_scratch_free.size(); ++i)
+      if (best == g_scratch_free.size() || g_scratch_free[i].cap > g_scratch_free[best].cap) best = i;
+    if (best < g_scratch_free.size()) {
+      s = g_scratch_free[best];
+      g_scratch_free.erase(g_scratch_free.begin() + (long)best);
+    }
+  }
+  if (s.cap < bytes) {
+    free(s.p);
+    s.p = static_cast<uint8_t *>(malloc(bytes));
+    s.cap = s.p ? bytes : 0;
+  }
+  return s;
+}
+
+void scratch_release(Scratch s) {
+  if (!s.p) return;
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  g_scratch_free.push_back(s);
+}
 
 // Byte symbols must never be the model's last symbol (step() codes the general branch only).
 RangeEncoder::RangeEncoder(unsigned symbols)
@@ -56,11 +96,10 @@ struct RangeEncoder::State {
   uint32_t *count;
 };
 
-inline void RangeEncoder::begin(State &e, size_t n, std::vector<uint8_t> &out, size_t &start) {
+// buf: at least encode_bound(n) bytes.
+inline void RangeEncoder::begin(State &e, uint8_t *buf) {
   reset_model();
-  start = out.size();
-  out.resize(start + 2 * n + 16);   // an adaptive-model symbol never costs more than 15 bits
-  e.buf = e.p = out.data() + start;
+  e.buf = e.p = buf;
   e.base = 0;
   e.length = 0xFFFFFFFFu;
   e.until = until_;
@@ -102,7 +141,7 @@ inline void RangeEncoder::step(State &e, uint32_t s) {
 }
 
 // stop_encoder (arithmetic_codec.cpp:547-571)
-inline void RangeEncoder::finish(State &e, std::vector<uint8_t> &out, size_t start) {
+inline size_t RangeEncoder::finish(State &e) {
   until_ = e.until;
   const uint32_t before = e.base;
   if (e.length > 2 * kMinLength) {
@@ -117,25 +156,30 @@ inline void RangeEncoder::finish(State &e, std::vector<uint8_t> &out, size_t sta
     *e.p++ = (uint8_t)(e.base >> 24);
     e.base <<= 8;
   } while ((e.length <<= 8) < kMinLength);
-  out.resize(start + (size_t)(e.p - e.buf));
+  return (size_t)(e.p - e.buf);
+}
+
+size_t RangeEncoder::encode_raw(const uint8_t *sym, size_t n, uint8_t *buf) {
+  State e;
+  begin(e, buf);
+  for (size_t i = 0; i < n; ++i) step(e, sym[i]);
+  return finish(e);
 }
 
 void RangeEncoder::encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out) {
-  State e;
-  size_t start;
-  begin(e, n, out, start);
-  for (size_t i = 0; i < n; ++i) step(e, sym[i]);
-  finish(e, out, start);
+  Scratch sc = scratch_acquire(encode_bound(n));
+  const size_t len = encode_raw(sym, n, sc.p);
+  out.insert(out.end(), sc.p, sc.p + len);
+  scratch_release(sc);
 }
 
 // Two independent streams in one loop: the coder is a chain of dependent multiplies and shifts
 // (~10 cycles per symbol), so a second chain in flight nearly doubles a thread's throughput.
-void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, std::vector<uint8_t> &oa,
-                               RangeEncoder &mb, const uint8_t *sb, size_t nb, std::vector<uint8_t> &ob) {
+void RangeEncoder::encode_pair_raw(RangeEncoder &ma, const uint8_t *sa, size_t na, uint8_t *bufa, size_t *lena,
+                                   RangeEncoder &mb, const uint8_t *sb, size_t nb, uint8_t *bufb, size_t *lenb) {
   State a, b;
-  size_t start_a, start_b;
-  ma.begin(a, na, oa, start_a);
-  mb.begin(b, nb, ob, start_b);
+  ma.begin(a, bufa);
+  mb.begin(b, bufb);
   const size_t both = na < nb ? na : nb;
   for (size_t i = 0; i < both; ++i) {
     ma.step(a, sa[i]);
@@ -143,8 +187,18 @@ void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, s
   }
   for (size_t i = both; i < na; ++i) ma.step(a, sa[i]);
   for (size_t i = both; i < nb; ++i) mb.step(b, sb[i]);
-  ma.finish(a, oa, start_a);
-  mb.finish(b, ob, start_b);
+  *lena = ma.finish(a);
+  *lenb = mb.finish(b);
+}
+
+void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, std::vector<uint8_t> &oa,
+                               RangeEncoder &mb, const uint8_t *sb, size_t nb, std::vector<uint8_t> &ob) {
+  Scratch sc = scratch_acquire(encode_bound(na) + encode_bound(nb));
+  size_t la = 0, lb = 0;
+  encode_pair_raw(ma, sa, na, sc.p, &la, mb, sb, nb, sc.p + encode_bound(na), &lb);
+  oa.insert(oa.end(), sc.p, sc.p + la);
+  ob.insert(ob.end(), sc.p + encode_bound(na), sc.p + encode_bound(na) + lb);
+  scratch_release(sc);
 }
 
 // ---- decoder ---------------------------------------------------------------------------------
@@ -395,36 +449,59 @@ struct StreamPlan {
     }
   }
 
-  void write(std::vector<uint8_t> &bytes, mptc_stream_stats &st) {
+  // Lays the stream out directly in the caller's buffer (no intermediate copy of the whole stream):
+  // the record offsets follow from the code sizes, the copies run on `threads` host threads.
+  int write(uint8_t *out, size_t cap, size_t *out_bytes, mptc_stream_stats &st, int threads) {
     memset(&st, 0, sizeof st);
     st.n_groups = (uint32_t)n_groups;
-    bytes.reserve(64 + (size_t)n_used * nb);
-    put_u32(bytes, (uint32_t)h);                     // header (codec.cpp:1358-1367)
-    put_u32(bytes, (uint32_t)w);
-    bytes.push_back((uint8_t)p.gop);
-    bytes.push_back((uint8_t)p.search_area);
-    put_u32(bytes, (uint32_t)n_groups);
-    const size_t patch_at = bytes.size();            // == 14
-    for (int k = 0; k < 5; ++k) put_u32(bytes, 0);
+    std::vector<size_t> at(jobs.size());             // where each job's u32 size prefix goes
+    std::vector<size_t> group_at(n_groups), frame_at((size_t)n_used);
+    size_t total = 34;
+    for (int g = 0; g < n_groups; ++g) {
+      const size_t pj = (size_t)n_used * 5 + g;
+      group_at[g] = total;
+      at[pj] = total;
+      total += 4 + jobs[pj].out.size() + 4;          // palette record + u32 unique bytes
+      for (int f = g * p.gop; f < (g + 1) * p.gop; ++f) {
+        frame_at[f] = total;
+        total += 4;                                  // u32 n_unique (codec.cpp:1140-1142)
+        for (int q = 0; q < 5; ++q) {
+          at[(size_t)f * 5 + q] = total;
+          total += 4 + jobs[(size_t)f * 5 + q].out.size();
+        }
+      }
+    }
+    if (out_bytes) *out_bytes = total;
+    if (!out || total > cap) return MPTC_E_SPACE;
+    auto put = [&](size_t off, uint32_t x) { memcpy(out + off, &x, 4); };
+    put(0, (uint32_t)h);                             // header (codec.cpp:1358-1367)
+    put(4, (uint32_t)w);
+    out[8] = (uint8_t)p.gop;
+    out[9] = (uint8_t)p.search_area;
+    put(10, (uint32_t)n_groups);
     for (int g = 0; g < n_groups; ++g) {
       const std::vector<uint8_t> &cpal = jobs[(size_t)n_used * 5 + g].out;
-      put_u32(bytes, (uint32_t)cpal.size());
-      bytes.insert(bytes.end(), cpal.begin(), cpal.end());
-      put_u32(bytes, (uint32_t)palettes[g].size());
+      put(group_at[g] + 4 + cpal.size(), (uint32_t)palettes[g].size());
       if ((uint32_t)cpal.size() > st.max_comp_palette) st.max_comp_palette = (uint32_t)cpal.size();
       if ((uint32_t)palettes[g].size() > st.max_unique_bytes) st.max_unique_bytes = (uint32_t)palettes[g].size();
       for (int f = g * p.gop; f < (g + 1) * p.gop; ++f) {
-        StreamJob *fj = &jobs[(size_t)f * 5];
-        append_frame_payload(bytes, n_unique[f], fj);
+        const StreamJob *fj = &jobs[(size_t)f * 5];
+        put(frame_at[f], n_unique[f]);
         const uint32_t m = (uint32_t)fj[0].out.size();
         if (m > st.max_comp_motion) st.max_comp_motion = m;
-        for (int s : {1, 3}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_y) st.max_comp_ep_y = (uint32_t)fj[s].out.size();
-        for (int s : {2, 4}) if ((uint32_t)fj[s].out.size() > st.max_comp_ep_c) st.max_comp_ep_c = (uint32_t)fj[s].out.size();
+        for (int q : {1, 3}) if ((uint32_t)fj[q].out.size() > st.max_comp_ep_y) st.max_comp_ep_y = (uint32_t)fj[q].out.size();
+        for (int q : {2, 4}) if ((uint32_t)fj[q].out.size() > st.max_comp_ep_c) st.max_comp_ep_c = (uint32_t)fj[q].out.size();
       }
     }
     const uint32_t patch[5] = {st.max_unique_bytes, st.max_comp_palette, st.max_comp_motion, st.max_comp_ep_y,
                                st.max_comp_ep_c};   // codec.cpp:1514-1520
-    memcpy(bytes.data() + patch_at, patch, sizeof patch);
+    memcpy(out + 14, patch, sizeof patch);
+    parallel_for((int)jobs.size(), threads, [&](int j) {
+      const std::vector<uint8_t> &v = jobs[j].out;
+      put(at[j], (uint32_t)v.size());
+      if (!v.empty()) memcpy(out + at[j] + 4, v.data(), v.size());
+    });
+    return MPTC_OK;
   }
 };
 
@@ -477,14 +554,13 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
   const std::vector<StreamPlan::Task> tasks = plan.tasks_in_arrival_order();
   parallel_for((int)tasks.size(), threads, [&](int i) { plan.encode_task(tasks[i]); });
   mptc_stream_stats st;
-  std::vector<uint8_t> bytes;
-  plan.write(bytes, st);
+  const int wr = plan.write(out, cap, out_bytes, st, threads);
   st.entropy_ms = st.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (stats) {
     st.gpu_ms = stats->gpu_ms;
     *stats = st;
   }
-  return copy_out(bytes, out, cap, out_bytes);
+  return wr;
 }
 
 // GPU hot path and host arithmetic coding OVERLAPPED (BASELINE.json north_star): the encode is
@@ -535,15 +611,15 @@ int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, i
       if (r == MPTC_OK) r = wr;
       if (r == MPTC_OK) {
         mptc_stream_stats st;
-        std::vector<uint8_t> bytes;
-        plan.write(bytes, st);
+        const auto t15 = std::chrono::steady_clock::now();
+        r = plan.write(out, cap, out_bytes, st, threads);
         const auto t2 = std::chrono::steady_clock::now();
+        st.assemble_ms = std::chrono::duration<double, std::milli>(t2 - t15).count();
         float ms = 0.f;
         if (mptc_gpu_last_encode_ms(ctx, 0, &ms) == MPTC_OK) st.gpu_ms = ms;
-        st.entropy_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+        st.entropy_ms = std::chrono::duration<double, std::milli>(t15 - t1).count();
         st.total_ms = std::chrono::duration<double, std::milli>(t2 - t0).count();
         if (stats) *stats = st;
-        r = copy_out(bytes, out, cap, out_bytes);
       }
     }
   }

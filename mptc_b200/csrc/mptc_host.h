@@ -6,6 +6,17 @@
 
 namespace mptc {
 
+// Raw scratch buffers that outlive a call (mptc_host.cpp): the coder's worst-case output bound is
+// far above what it produces, and fresh zero-filled vectors of that size cost more than coding.
+struct Scratch {
+  uint8_t *p = nullptr;
+  size_t cap = 0;
+};
+Scratch scratch_acquire(size_t bytes);
+void scratch_release(Scratch s);
+// An adaptive-model symbol never costs more than 15 bits; +16 for the coder's look-ahead stores.
+inline size_t encode_bound(size_t n) { return 2 * n + 16; }
+
 // Adaptive multi-symbol model + 32-bit range coder, bit-compatible with the reference's
 // entropy::Adaptive_Data_Model / entropy::Arithmetic_Codec (entropy/arithmetic_codec.cpp).
 class RangeEncoder {
@@ -13,15 +24,19 @@ class RangeEncoder {
   explicit RangeEncoder(unsigned symbols = 257);
   // Appends the code bytes of `sym[0..n)` (fresh model, start .. stop) to `out`.
   void encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out);
+  // The same into a raw buffer of at least encode_bound(n) bytes; returns the code length.
+  size_t encode_raw(const uint8_t *sym, size_t n, uint8_t *buf);
+  static void encode_pair_raw(RangeEncoder &ma, const uint8_t *sa, size_t na, uint8_t *bufa, size_t *lena,
+                              RangeEncoder &mb, const uint8_t *sb, size_t nb, uint8_t *bufb, size_t *lenb);
   // Two independent streams coded in one interleaved loop (each with its own model / encoder).
   static void encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, std::vector<uint8_t> &oa,
                           RangeEncoder &mb, const uint8_t *sb, size_t nb, std::vector<uint8_t> &ob);
 
  private:
   struct State;
-  void begin(State &e, size_t n, std::vector<uint8_t> &out, size_t &start);
+  void begin(State &e, uint8_t *buf);
   void step(State &e, uint32_t s);
-  void finish(State &e, std::vector<uint8_t> &out, size_t start);
+  size_t finish(State &e);
   void reset_model();
   void update_model();
   unsigned n_;
