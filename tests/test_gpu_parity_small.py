@@ -145,3 +145,43 @@ def test_word_diverse_content_with_row_wavefront_for_leftovers(ctx):
                 assert np.array_equal(out["blocks"][i], ref[i][1]), f"{kind} frame {i}"
     finally:
         c2.close()
+
+
+@pytest.mark.parametrize("w,h,n,sa,thr,gop", [
+    (4, 4, 3, 1, 50, 2),          # one block per frame
+    (8, 4, 2, 63, 50, 2),         # the largest search area the uint8 motion bytes allow, tiny frame
+    (64, 32, 2, 63, 20, 2),       # search area far larger than the frame
+    (128, 64, 1, 40, 50, 1),      # single frame, window > 32 (multi-step scan paths)
+    (96, 64, 4, 5, -1, 2),        # negative threshold: only strictly better candidates are found
+    (96, 64, 3, 5, 1 << 30, 3),   # huge threshold: everything with an accepted candidate is found
+    (32, 128, 5, 7, 50, 255),     # gop longer than the sequence; tall narrow frame
+])
+def test_edge_geometries_and_thresholds(ctx, w, h, n, sa, thr, gop):
+    frames = make_sequence(w, h, n, seed=29)
+    ref = oracle_sequence(frames, sa, thr, gop)
+    out = ctx.encode_sequence(frames, sa, thr, gop)
+    for i in range(n):
+        init, blocks, motion, unique = ref[i]
+        assert np.array_equal(out["motion"][i], motion), f"frame {i}"
+        assert np.array_equal(out["blocks"][i], blocks), f"frame {i}"
+        nu = int(out["n_unique"][i])
+        assert nu == unique.size and np.array_equal(out["unique"][i, :nu], unique)
+        assert np.array_equal(out["planes"][i], port.endpoint_planes(blocks, w // 4, h // 4)), f"planes {i}"
+    # and back through the decoder
+    dec = ctx.decode_sequence(out["motion"], out["unique"], out["n_unique"], out["planes"], w, h, sa, gop)
+    assert np.array_equal(dec, out["blocks"])
+
+
+def test_bad_arguments_are_reported(ctx):
+    from mptc_b200 import capi
+    frames = make_sequence(64, 64, 2, seed=1)
+    with pytest.raises(capi.MptcError):
+        ctx.encode_sequence(frames, 64, 50, 2)            # search_area > 63
+    with pytest.raises(capi.MptcError):
+        ctx.encode_sequence(frames, 0, 50, 2)             # search_area < 1
+    with pytest.raises(capi.MptcError):
+        ctx.encode_sequence(frames, 4, 50, 0)             # gop < 1
+    with pytest.raises(capi.MptcError):
+        ctx.dxt1_fit(np.zeros((6, 8, 3), dtype=np.uint8))  # height not a multiple of 4
+    out = ctx.encode_sequence(frames, 4, 50, 2)           # the context still works
+    assert out["blocks"].shape == (2, 256)
