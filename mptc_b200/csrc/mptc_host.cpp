@@ -203,7 +203,8 @@ void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, s
 
 // ---- decoder ---------------------------------------------------------------------------------
 namespace {
-constexpr unsigned kTableShift = 8;                            // 128 buckets over the 15-bit range
+constexpr unsigned kTableShift = 8;                            // 128 buckets over the 15-bit range (1024 buckets
+                                                               // + branch-free steps measured 28 % slower: rebuilds)
 constexpr unsigned kTableSize = (1u << kLengthShift) >> kTableShift;
 }  // namespace
 
@@ -296,21 +297,43 @@ bool RangeDecoder::decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, 
   return d.ok && d.overrun <= 4;
 }
 
-// Two independent streams in one loop: each symbol costs a 32-bit division and a dependent table
-// walk, a second chain in flight hides most of that latency.
+// Several independent streams in one loop: each symbol costs a 32-bit division and a dependent
+// table walk; with two to four chains in flight the divider pipelines and most of that latency
+// hides.  Streams may have different lengths (the loop keeps going with the ones that are left).
+bool RangeDecoder::decode_multi(RangeDecoder *const *dec, const StreamIO *io, int k) {
+  State st[kMaxInterleave];
+  size_t longest = 0, shortest = (size_t)-1;
+  for (int q = 0; q < k; ++q) {
+    dec[q]->begin(st[q], io[q].code, io[q].nbytes);
+    longest = io[q].n > longest ? io[q].n : longest;
+    shortest = io[q].n < shortest ? io[q].n : shortest;
+  }
+  size_t i = 0;
+  if (k == 4)
+    for (; i < shortest; ++i) {
+      io[0].sym[i] = dec[0]->step(st[0]);
+      io[1].sym[i] = dec[1]->step(st[1]);
+      io[2].sym[i] = dec[2]->step(st[2]);
+      io[3].sym[i] = dec[3]->step(st[3]);
+    }
+  else if (k == 2)
+    for (; i < shortest; ++i) {
+      io[0].sym[i] = dec[0]->step(st[0]);
+      io[1].sym[i] = dec[1]->step(st[1]);
+    }
+  for (; i < longest; ++i)
+    for (int q = 0; q < k; ++q)
+      if (i < io[q].n) io[q].sym[i] = dec[q]->step(st[q]);
+  bool ok = true;
+  for (int q = 0; q < k; ++q) ok = ok && st[q].ok && st[q].overrun <= 4;
+  return ok;
+}
+
 bool RangeDecoder::decode_pair(RangeDecoder &ma, const uint8_t *ca, size_t ba, uint8_t *sa, size_t na,
                                RangeDecoder &mb, const uint8_t *cb, size_t bb, uint8_t *sb, size_t nb) {
-  State a, b;
-  ma.begin(a, ca, ba);
-  mb.begin(b, cb, bb);
-  const size_t both = na < nb ? na : nb;
-  for (size_t i = 0; i < both; ++i) {
-    sa[i] = ma.step(a);
-    sb[i] = mb.step(b);
-  }
-  for (size_t i = both; i < na; ++i) sa[i] = ma.step(a);
-  for (size_t i = both; i < nb; ++i) sb[i] = mb.step(b);
-  return a.ok && b.ok && a.overrun <= 4 && b.overrun <= 4;
+  RangeDecoder *d[2] = {&ma, &mb};
+  const StreamIO io[2] = {{ca, ba, sa, na}, {cb, bb, sb, nb}};
+  return decode_multi(d, io, 2);
 }
 
 namespace {
@@ -728,35 +751,38 @@ int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, i
   }
   std::vector<std::atomic<int>> left(H.n_groups);
   for (int g = 0; g < H.n_groups; ++g) left[g].store(1 + 5 * gop);
-  // tasks = one or two records decoded by one thread in an interleaved loop: per frame the two Y
-  // and the two Co|Cg planes (equal lengths), motion streams of two frames of a group
-  struct Task { int a, b; };
+  // tasks = records decoded by one thread in an interleaved loop: per frame the two Co|Cg and the
+  // two Y planes, the motion streams of two frames of a group, a palette alone (four at a time
+  // was measured and is no faster: the loop is bound by instruction throughput, not latency)
+  struct Task { int r[4]; int k; };
   std::vector<Task> tasks;
   tasks.reserve(recs.size());
   for (int g = 0; g < H.n_groups; ++g) {
     const int r0 = g * (1 + 5 * gop);
-    tasks.push_back({r0, -1});                                  // palette
+    tasks.push_back({{r0, -1, -1, -1}, 1});                     // palette
     for (int k = 0; k < gop; ++k) {
       const int fr = r0 + 1 + 5 * k;
-      if ((k & 1) == 0) tasks.push_back({fr, k + 1 < gop ? fr + 5 : -1});   // motion of frames k, k+1
-      tasks.push_back({fr + 2, fr + 4});
-      tasks.push_back({fr + 1, fr + 3});
+      if ((k & 1) == 0) {                                       // motion of frames k, k+1
+        if (k + 1 < gop) tasks.push_back({{fr, fr + 5, -1, -1}, 2});
+        else tasks.push_back({{fr, -1, -1, -1}, 1});
+      }
+      tasks.push_back({{fr + 2, fr + 4, -1, -1}, 2});           // Co|Cg 1, Co|Cg 2 (equal lengths)
+      tasks.push_back({{fr + 1, fr + 3, -1, -1}, 2});           // Y 1, Y 2
     }
   }
   std::atomic<int> next(0), corrupt(0);
   const int n_tasks = (int)tasks.size();
   auto worker = [&]() {
-    RangeDecoder da, db;
+    RangeDecoder pool4[4];
+    RangeDecoder *d[4] = {&pool4[0], &pool4[1], &pool4[2], &pool4[3]};
     for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) {
-      const Rec &ra = recs[tasks[i].a];
-      bool ok;
-      if (tasks[i].b < 0) ok = da.decode_all(ra.code, ra.nbytes, ra.dst, ra.n);
-      else {
-        const Rec &rb = recs[tasks[i].b];
-        ok = RangeDecoder::decode_pair(da, ra.code, ra.nbytes, ra.dst, ra.n, db, rb.code, rb.nbytes, rb.dst, rb.n);
-      }
+      const Task &t = tasks[i];
+      RangeDecoder::StreamIO io[4];
+      for (int q = 0; q < t.k; ++q) io[q] = {recs[t.r[q]].code, recs[t.r[q]].nbytes, recs[t.r[q]].dst, recs[t.r[q]].n};
+      const bool ok = t.k == 1 ? d[0]->decode_all(io[0].code, io[0].nbytes, io[0].sym, io[0].n)
+                               : RangeDecoder::decode_multi(d, io, t.k);
       if (!ok) corrupt.store(1);
-      left[ra.group].fetch_sub(tasks[i].b < 0 ? 1 : 2, std::memory_order_release);
+      left[recs[t.r[0]].group].fetch_sub(t.k, std::memory_order_release);
     }
   };
   if (threads < 1) threads = 1;

@@ -56,7 +56,11 @@ class RangeDecoder {
   // valid stream never needs more than the coder's 4-byte look-ahead).  Returns false if the code
   // ran out more than 4 bytes early or a symbol outside 0..255 appeared (corrupt stream).
   bool decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n);
-  // Two independent streams decoded in one interleaved loop (each with its own model / decoder).
+  // Up to kMaxInterleave independent streams decoded in one interleaved loop (each with its own
+  // model / decoder).
+  static constexpr int kMaxInterleave = 4;
+  struct StreamIO { const uint8_t *code; size_t nbytes; uint8_t *sym; size_t n; };
+  static bool decode_multi(RangeDecoder *const *dec, const StreamIO *io, int k);
   static bool decode_pair(RangeDecoder &ma, const uint8_t *ca, size_t ba, uint8_t *sa, size_t na,
                           RangeDecoder &mb, const uint8_t *cb, size_t bb, uint8_t *sb, size_t nb);
 
