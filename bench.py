@@ -232,7 +232,7 @@ def reference_arm(args, rank: int):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=claim_stdout(), flush=True)
 
 
 def ncu_evidence(dominant: str):
@@ -260,7 +260,6 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         raise SystemExit("bench.py: no CUDA device -- the encoder hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -472,12 +471,27 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
             "round_trip_equal": dec_ok,
         },
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=claim_stdout(), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else a library prints there (NCCL's version
+    banner, for one) is sent to stderr by pointing fd 1 at fd 2 and keeping the real stdout aside."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
