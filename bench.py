@@ -42,14 +42,25 @@ ALGO_SLOTS_PER_CANDIDATE = 360
 SM_COUNT, SCHEDULERS, LANES = 148, 4, 32
 WORKLOAD = ""
 # BASELINE.json configs: [1] is the default (the headline); [2] = 4K x120 with the host coder overlapped
-WORKLOADS = {"1080p60": (1920, 1080, 60), "4k120": (3840, 2160, 120)}
+WORKLOADS = {"1080p60": (1920, 1080, 60), "4k120": (3840, 2160, 120), "4k600": (3840, 2160, 600)}
+STRONG = {"4k600"}   # configs[4]: the frame count is that of the whole job, GOP-sharded over the GPUs
+SCALING = "weak"
 
 
-def set_workload(name: str, sa: int, thr: int):
-    global W, H, FRAMES, SA, THR, WORKLOAD
+def set_workload(name: str, sa: int, thr: int, world: int = 1):
+    global W, H, FRAMES, SA, THR, WORKLOAD, SCALING
     W, H, FRAMES = WORKLOADS[name]
     SA, THR = sa, thr
-    WORKLOAD = f"{W}x{H} synthetic x{FRAMES} frames/GPU, search_area={SA}, err_threshold={THR}, gop={GOP}"
+    if name in STRONG:
+        total, gops = FRAMES, FRAMES // GOP
+        assert gops % world == 0, f"{gops} GOPs do not split over {world} GPUs"
+        FRAMES = gops // world * GOP
+        SCALING = "strong"
+        WORKLOAD = (f"{W}x{H} synthetic x{total} frames in all = {FRAMES} frames/GPU, search_area={SA}, "
+                    f"err_threshold={THR}, gop={GOP}")
+    else:
+        SCALING = "weak"
+        WORKLOAD = f"{W}x{H} synthetic x{FRAMES} frames/GPU, search_area={SA}, err_threshold={THR}, gop={GOP}"
 METRIC = "mptc_encode_mpixel_per_s"
 UNIT = "Mpixel/s"
 
@@ -278,8 +289,12 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     nb = (W // 4) * (H // 4)
     # this rank's shard of the 60*world-frame sequence: frames [60*rank, 60*rank+60)
     pin_frames = capi.PinnedArray((FRAMES, H, W, 3), np.uint8)
-    for f in range(FRAMES):
+
+    def gen(f):
         pin_frames.array[f] = make_frame(W, H, FRAMES * rank + f)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, (os.cpu_count() or 1) // max(world, 1))) as pool:   # numpy releases the GIL
+        list(pool.map(gen, range(FRAMES)))
     frames = pin_frames.array
     pbw, pbh = (W // 4 + 63) // 64 * 64, (H // 4 + 63) // 64 * 64
     pins = {"blocks": capi.PinnedArray((FRAMES, nb), np.uint64), "motion": capi.PinnedArray((FRAMES, 2 * nb), np.uint8),
@@ -444,7 +459,7 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     line = {
         "metric": METRIC, "value": pixels_total / (step_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+        "scaling": SCALING, "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "sharding": f"gop-sharded x{world}, no collective",
                    "l2": f"inputs ({frames.nbytes // 1000000} MB RGB per step) exceed the 126 MB L2; no explicit flush"},
         "wall_ms_per_step": wall_ms,
@@ -499,13 +514,14 @@ def main():
     ap.add_argument("--impl", default="mptc_b200", choices=["mptc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p60", choices=sorted(WORKLOADS),
-                    help="1080p60 = BASELINE.json configs[1] (default, the headline); 4k120 = configs[2]")
+                    help="1080p60 = BASELINE.json configs[1] (default, the headline); 4k120 = configs[2]; "
+                         "4k600 = configs[4] (600 frames in all, GOP-sharded over the GPUs: strong scaling)")
     ap.add_argument("--search-area", type=int, default=SA)
     ap.add_argument("--err-threshold", type=int, default=THR)
     args = ap.parse_args()
-    set_workload(args.workload, args.search_area, args.err_threshold)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    set_workload(args.workload, args.search_area, args.err_threshold, world)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         reference_arm(args, rank)
