@@ -341,8 +341,9 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
       // restructured so that no table has to hold all words at once:
       //   1. wait until EVERYTHING the group's window can contain is final (no incremental near rows);
       //   2. reload the complete window, de-duplicate, all distinct words into ulist_all;
-      //   3. rows above + the own row left of the group: chunks of kMaxWords words through the
-      //      uniform evaluation (warp = word, lane = target) and a remapped window scan;
+      //   3. rows above: chunks of kMaxWords words through the uniform evaluation (warp = word,
+      //      lane = target) and a remapped window scan; then (3b) the <= sa blocks of the own row left
+      //      of the group, once the neighbour CTA has decided them;
       //   4. the group's own blocks in order by one warp, lane = target: block g resolves from its
       //      winner state, then its final word is evaluated for the 32 lanes at once and pushed to
       //      the <= sa targets on its right (no table: the err_diff stays in a register).
@@ -354,8 +355,6 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             const bool complete = r >= R || by - r < 0 || (!all_rows && !row_todo[by - r]);
             if (!complete)
               while (ld_acquire(progress + by - r) < need) __nanosleep(32);
-          } else if (lane == 0 && split > 1) {
-            while (ld_acquire(progress + by) < x0) __nanosleep(32);
           }
           __syncwarp();
           if (lane == 0) { s_count = 0; s_special = 0; }
@@ -371,7 +370,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             const int p = p0 + q * kThreads + tid;
             const int r = p / UW, uc = p - r * UW;
             const int j = by - r, i = x0 - sa + uc;
-            ok[q] = p < NP && i >= 0 && i < v.bw && j >= 0 && (r > 0 || i < x0);   // the group's own blocks arrive as pushes
+            ok[q] = p < NP && i >= 0 && i < v.bw && j >= 0 && r > 0;   // the own row comes later (steps 3b, 4)
             wv[q] = ok[q] ? ldcg_word(cur, (size_t)j * v.bw + i) : 0u;
           }
 #pragma unroll
@@ -404,12 +403,6 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             const int g = wid + q * kWarps;
             if (g >= n || !((todo_mask >> g) & 1u)) continue;
             scan_window<true>(wsq[q], sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, 1, min(R - 1, by) + 1, lane, c0, cn, kMaxWords);
-            for (int l = lane; l < sa; l += 32)      // own row left of the group: scan column sa + l
-              if (l >= g && x0 + g - 1 - l >= 0) {
-                int u = (int)sm.pos_uid[g + sa - 1 - l] - c0;
-                u = ((unsigned)u < (unsigned)cn) ? u : kMaxWords;
-                winner_update_fast(wsq[q], sm.err[u * 33 + g], (uint32_t)(sa + l));
-              }
           }
           __syncthreads();
         }
@@ -420,11 +413,28 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           winner_warp_reduce(wsq[q]);
           if (lane == 0) s_partial[g] = wsq[q];
         }
+        // 3b. the own row left of the group: only now does the group wait for its neighbour CTA (two
+        // CTAs per row on intra frames), so the chunk phase above overlapped the neighbour's decisions.
+        // Its <= sa words are evaluated one per warp, lane = target, into rows 0.. of the err table.
+        if (split > 1 && tid == 0)
+          while (ld_acquire(progress + by) < x0) __nanosleep(32);
+        __syncthreads();
+        const int n_left = min(sa, x0);
+        for (int j = wid; j < n_left; j += kWarps) {
+          const uint32_t word = ldcg_word(cur, (size_t)by * v.bw + x0 - 1 - j);
+          if (lane == 0) { sm.ulist[j] = word; word_info(word, sm.info[j]); }
+          __syncwarp();
+          sm.err[j * 33 + lane] = eval_uniform(t, word, sm.info[j], sm.lut5, sm.lut6);
+        }
         __syncthreads();
         if (wid == 0) {
           WinnerState ws;
           winner_init(ws);
-          if (todo) ws = s_partial[lane];
+          if (todo) {
+            ws = s_partial[lane];
+            for (int j = 0; j < n_left && lane + 1 + j <= sa; ++j)   // block x0-1-j is lane+1+j to the left
+              winner_update_fast(ws, sm.err[j * 33 + lane], (uint32_t)(sa + lane + j));
+          }
           uint32_t final_word = (in_row && !todo) ? ldcg_word(cur, (size_t)by * v.bw + gx) : 0u;
           int dec = -1, stored = 0;
           uint32_t w_prev = 0u;
@@ -440,6 +450,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
             if (fnd) {
               const int d = col - sa + 1;                       // row 0: the block d to the left
               if (row == 0 && lane - d >= 0) gi = lane - d;     // inside the group: that lane's final word
+              else if (row == 0) wt = sm.ulist[d - lane - 1];   // left of the group (step 3b)
               else wt = sm.ulist_all[sm.pos_uid[row * UW + lane + W - 1 - col]];
             }
             const int gi_g = __shfl_sync(0xffffffffu, gi, g);
