@@ -254,11 +254,14 @@ bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int s
   }
   const size_t bytes = tile_smem_bytes(sa, nullptr, nullptr);
   if (bytes + 1024 > (size_t)max_optin) return false;
-  static size_t configured = 0;
-  if (bytes > configured) {
+  static size_t configured[kMaxDevices] = {0};   // per device: one context per GPU may live in one process
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
+  if (bytes > conf) {
     if (cudaFuncSetAttribute(k_inter_search_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
       return false;
-    configured = bytes;
+    conf = bytes;
   }
   const int tiles = ((v.bw + kTileX - 1) / kTileX) * ((v.bh + kTileY - 1) / kTileY);
   dim3 grid(tiles, n_gops);

@@ -812,10 +812,13 @@ extern "C" void mptc_debug_phase_cycles(unsigned long long *out16, int reset) {
 
 bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                                   int grid_cap, cudaStream_t s) {
-  static int max_optin = -1, max_ctas = 0;
-  static size_t configured = 0;
+  static int max_optin = -1;
+  static int max_ctas_dev[kMaxDevices] = {0};
+  static size_t configured_dev[kMaxDevices] = {0};   // per device: one context per GPU may live in one process
   int dev = 0;
   cudaGetDevice(&dev);
+  size_t &configured = configured_dev[dev & (kMaxDevices - 1)];
+  int &max_ctas = max_ctas_dev[dev & (kMaxDevices - 1)];
   if (max_optin < 0) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t bytes = group_smem_bytes(sa, nullptr, nullptr);
   if (bytes + 4096 > (size_t)max_optin) return false;

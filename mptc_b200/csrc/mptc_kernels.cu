@@ -433,82 +433,77 @@ k_compact_unique(SeqView v, int f0, int fstride) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K5: endpoint planes.  One CTA per (64x64 tile, plane, frame).  Colour transform, six
-// in-place lifting levels (columns then rows, wavelet.cpp:110-130) and the +128 symbol
-// mapping all happen on the tile in shared memory; 4 B/block in, 6 B/block out.
+// K5: endpoint planes.  One CTA per (64x64 tile, frame) with all six planes of the tile in shared
+// memory (6 x 2 x 8 KB, ping-pong per lifting direction): the blocks are read once, the colour
+// transform, six lifting levels (columns then rows, wavelet.cpp:110-130) and the +128 symbol
+// mapping happen on chip; 8 B/block in, 6 B/block out.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int mirror_hi(int i, int n) { return i < n ? i : 2 * n - 2 - i; }
+constexpr int kPlaneTile = 64, kPlaneElems = kPlaneTile * kPlaneTile;
 
 __global__ void __launch_bounds__(1024)
 k_endpoint_planes(SeqView v, int pbw, int pbh, int f0, int fstride) {
-  __shared__ int16_t a[64][65];
-  __shared__ int16_t d[64][65];
-  const int tiles_x = pbw / 64;
-  const int tx = (blockIdx.x % tiles_x) * 64, ty = (blockIdx.x / tiles_x) * 64;
-  const int plane = blockIdx.y;            // ep*3 + ch
-  const int ep = plane / 3, ch = plane % 3;
-  const int f = f0 + blockIdx.z * fstride;
+  extern __shared__ int16_t plane_sm[];
+  int16_t *A = plane_sm, *B = plane_sm + 6 * kPlaneElems;   // [plane][y][x]
+  const int tiles_x = pbw / kPlaneTile;
+  const int tx = (blockIdx.x % tiles_x) * kPlaneTile, ty = (blockIdx.x / tiles_x) * kPlaneTile;
+  const int f = f0 + blockIdx.y * fstride;
   const uint64_t *blocks = v.final_blocks + (size_t)f * v.nb;
-  for (int e = threadIdx.x; e < 4096; e += 1024) {
-    int y = e >> 6, x = e & 63;
-    int sx = min(tx + x, v.bw - 1), sy = min(ty + y, v.bh - 1);  // edge replication (extension)
-    uint32_t c = (uint32_t)((blocks[(size_t)sy * v.bw + sx] >> (16 * ep)) & 0xFFFFu);
-    int r = (int)(c >> 11), g = (int)((c >> 5) & 63u), b = (int)(c & 31u);
-    int co = r - b, tt = r + b + (b >> 4), cg = g - tt, yy = tt + cg / 2;  // image_processing.cpp:10-27
-    a[y][x] = (int16_t)(ch == 0 ? yy : (ch == 1 ? co : cg));
+  for (int e = threadIdx.x; e < kPlaneElems; e += 1024) {
+    const int y = e >> 6, x = e & 63;
+    const int sx = min(tx + x, v.bw - 1), sy = min(ty + y, v.bh - 1);  // edge replication (extension)
+    const uint32_t eps = (uint32_t)blocks[(size_t)sy * v.bw + sx];
+#pragma unroll
+    for (int ep = 0; ep < 2; ++ep) {
+      const uint32_t c = (eps >> (16 * ep)) & 0xFFFFu;
+      const int r = (int)(c >> 11), g = (int)((c >> 5) & 63u), b = (int)(c & 31u);
+      const int co = r - b, tt = r + b + (b >> 4), cg = g - tt, yy = tt + cg / 2;  // image_processing.cpp:10-27
+      A[(3 * ep + 0) * kPlaneElems + e] = (int16_t)yy;
+      A[(3 * ep + 1) * kPlaneElems + e] = (int16_t)co;
+      A[(3 * ep + 2) * kPlaneElems + e] = (int16_t)cg;
+    }
   }
   __syncthreads();
-  for (int dim = 64; dim > 1; dim >>= 1) {
-    const int half = dim >> 1;
-    // columns: predict (odd rows) ...
-    for (int e = threadIdx.x; e < half * dim; e += 1024) {
-      int k = e / dim, c = e - k * dim, i = 2 * k + 1;
-      d[k][c] = (int16_t)(a[i][c] - (a[i - 1][c] + a[mirror_hi(i + 1, dim)][c]) / 2);
+  for (int dim = kPlaneTile; dim > 1; dim >>= 1) {
+    const int half = dim >> 1, items = 6 * half * dim;
+    const int sh = 31 - __clz(half);                       // half is a power of two
+    // columns (wavelet.cpp:110-119): predict the odd rows into the lower half of B ...
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int c = e & (dim - 1), k = (e >> (sh + 1)) & (half - 1), pl = e >> (2 * sh + 1);
+      const int16_t *a = A + pl * kPlaneElems + c;
+      const int i = 2 * k + 1, nx = i + 1 < dim ? i + 1 : dim - 2;   // mirror at the end
+      B[pl * kPlaneElems + (half + k) * kPlaneTile + c] = (int16_t)(a[i * kPlaneTile] - (a[(i - 1) * kPlaneTile] + a[nx * kPlaneTile]) / 2);
     }
     __syncthreads();
-    // ... update (even rows), gather low half on top
-    int16_t sv[2];
-    int cnt = 0;
-    for (int e = threadIdx.x; e < half * dim; e += 1024) {
-      int k = e / dim, c = e - k * dim;
-      int dp = k == 0 ? 0 : k - 1;            // mirror: d[-1] -> d[0]
-      sv[cnt++] = (int16_t)(a[2 * k][c] + (d[dp][c] + d[k][c] + 2) / 4);
+    // ... update the even rows into the upper half
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int c = e & (dim - 1), k = (e >> (sh + 1)) & (half - 1), pl = e >> (2 * sh + 1);
+      const int16_t *d = B + pl * kPlaneElems + half * kPlaneTile + c;
+      B[pl * kPlaneElems + k * kPlaneTile + c] =
+          (int16_t)(A[pl * kPlaneElems + 2 * k * kPlaneTile + c] + (d[max(k - 1, 0) * kPlaneTile] + d[k * kPlaneTile] + 2) / 4);
     }
     __syncthreads();
-    cnt = 0;
-    for (int e = threadIdx.x; e < half * dim; e += 1024) {
-      int k = e / dim, c = e - k * dim;
-      a[k][c] = sv[cnt++];
-      a[half + k][c] = d[k][c];
+    // rows (:121-130), from B back into A: predict the odd columns into the right half ...
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int k = e & (half - 1), r = (e >> sh) & (dim - 1), pl = e >> (2 * sh + 1);
+      const int16_t *b = B + pl * kPlaneElems + r * kPlaneTile;
+      const int i = 2 * k + 1, nx = i + 1 < dim ? i + 1 : dim - 2;
+      A[pl * kPlaneElems + r * kPlaneTile + half + k] = (int16_t)(b[i] - (b[i - 1] + b[nx]) / 2);
     }
     __syncthreads();
-    // rows: predict (odd columns)
-    for (int e = threadIdx.x; e < half * dim; e += 1024) {
-      int r = e / half, k = e - r * half, i = 2 * k + 1;
-      d[r][k] = (int16_t)(a[r][i] - (a[r][i - 1] + a[r][mirror_hi(i + 1, dim)]) / 2);
-    }
-    __syncthreads();
-    cnt = 0;
-    for (int e = threadIdx.x; e < half * dim; e += 1024) {
-      int r = e / half, k = e - r * half;
-      int dp = k == 0 ? 0 : k - 1;
-      sv[cnt++] = (int16_t)(a[r][2 * k] + (d[r][dp] + d[r][k] + 2) / 4);
-    }
-    __syncthreads();
-    cnt = 0;
-    for (int e = threadIdx.x; e < half * dim; e += 1024) {
-      int r = e / half, k = e - r * half;
-      a[r][k] = sv[cnt++];
-      a[r][half + k] = d[r][k];
+    // ... update the even columns into the left half
+    for (int e = threadIdx.x; e < items; e += 1024) {
+      const int k = e & (half - 1), r = (e >> sh) & (dim - 1), pl = e >> (2 * sh + 1);
+      int16_t *a = A + pl * kPlaneElems + r * kPlaneTile;
+      a[k] = (int16_t)(B[pl * kPlaneElems + r * kPlaneTile + 2 * k] + (a[half + max(k - 1, 0)] + a[half + k] + 2) / 4);
     }
     __syncthreads();
   }
-  uint8_t *out = v.planes + ((size_t)f * 6 + plane) * (size_t)pbw * pbh;
-  for (int e = threadIdx.x; e < 1024; e += 1024) {
-    int y = e >> 4, x4 = (e & 15) * 4;
+  for (int e = threadIdx.x; e < 6 * kPlaneElems / 4; e += 1024) {
+    const int pl = e >> 10, idx = (e & 1023) * 4, y = idx >> 6, x4 = idx & 63;
     uint32_t w = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w |= (uint32_t)((uint8_t)((int8_t)a[y][x4 + q] + 128)) << (8 * q);
+    for (int q = 0; q < 4; ++q) w |= (uint32_t)((uint8_t)((int8_t)A[pl * kPlaneElems + idx + q] + 128)) << (8 * q);
+    uint8_t *out = v.planes + ((size_t)f * 6 + pl) * (size_t)pbw * pbh;
     *reinterpret_cast<uint32_t *>(out + (size_t)(ty + y) * pbw + tx + x4) = w;
   }
 }
@@ -547,8 +542,16 @@ void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_co
 }
 
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s) {
-  dim3 grid((pbw / 64) * (pbh / 64), 6, nf);
-  k_endpoint_planes<<<grid, 1024, 0, s>>>(v, pbw, pbh, f0, fstride);
+  static bool configured[kMaxDevices] = {false};   // per device: one context per GPU may live in one process
+  const int bytes = 12 * kPlaneElems * (int)sizeof(int16_t);
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (!configured[cur_dev & (kMaxDevices - 1)]) {
+    cudaFuncSetAttribute(k_endpoint_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    configured[cur_dev & (kMaxDevices - 1)] = true;
+  }
+  dim3 grid((pbw / kPlaneTile) * (pbh / kPlaneTile), nf);
+  k_endpoint_planes<<<grid, 1024, bytes, s>>>(v, pbw, pbh, f0, fstride);
 }
 
 int intra_wavefront_max_ctas(int device) {

@@ -6,6 +6,8 @@
 
 namespace mptc {
 
+constexpr int kMaxDevices = 64;   // per-device launch configuration caches (power of two)
+
 // Device-resident sequence: all arrays are [frame][...] over the reserved capacity.
 struct SeqView {
   const uint8_t *rgb;      // [F][h][w][3]

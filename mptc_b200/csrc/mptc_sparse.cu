@@ -312,10 +312,13 @@ void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int
                          int max_items, cudaStream_t s) {
   const int np = 4 * sa * sa;
   const size_t bytes = np <= kMaxPos ? sparse_smem_bytes(np) : 0;
-  static size_t configured = 48 * 1024 - 13 * 1024;   // what fits next to the static arrays without opt-in
-  if (bytes > configured) {
+  static size_t configured[kMaxDevices] = {0};   // per device; 0 = nothing beyond what fits without opt-in
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
+  if (bytes > 48 * 1024 - 13 * 1024 && bytes > conf) {   // 35 KB fit next to the static arrays without opt-in
     if (cudaFuncSetAttribute(k_intra_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return;
-    configured = bytes;
+    conf = bytes;
   }
   dim3 grid(ctas_per_frame, n_gops);
   k_intra_sparse<<<grid, kThreads, bytes, s>>>(v, k_in_gop, sa, thr, max_items, tickets);

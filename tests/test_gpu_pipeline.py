@@ -111,3 +111,25 @@ def test_leftover_paths_bit_exact(max_pct, sa, thr, monkeypatch):
         assert left > 0, "the case must exercise the leftover path"
     finally:
         c.close()
+
+
+def test_two_devices_in_one_process():
+    """One context per GPU inside one process: per-device launch
+    configuration, same results on every device.  Needs two GPUs; skipped otherwise."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    w, h, n, sa, thr, gop = 256, 128, 4, 16, 50, 2
+    frames = make_sequence(w, h, n, seed=13)
+    ref = oracle_sequence(frames, sa, thr, gop)
+    ctxs = [capi.Context(d) for d in (1, 0)]
+    try:
+        for c in ctxs:
+            out = c.encode_sequence(frames, sa, thr, gop)
+            for i in range(n):
+                assert np.array_equal(out["blocks"][i], ref[i][0]), f"device {c.device} frame {i}"
+            dec = c.decode_sequence(out["motion"], out["unique"], out["n_unique"], out["planes"], w, h, sa, gop)
+            assert np.array_equal(dec, out["blocks"])
+    finally:
+        for c in ctxs:
+            c.close()
