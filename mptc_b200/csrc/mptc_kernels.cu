@@ -2,9 +2,12 @@
 //
 //   K1 k_dxt1_fit          stb_compress_dxt_block(HIGHQUAL) per 4x4 block   (Include/stb_dxt.h:467-538)
 //   K2 k_inter_search      DXTImage::InterBlockSearch + winner apply        (codec/dxt_image.cpp:715-774, :885-908)
+//                          direct form (one CTA per target); the tiled form is in mptc_inter.cu
 //   K3 k_intra_wavefront   DXTImage::IntraSearch + winner apply, raster     (codec/dxt_image.cpp:652-713, :912-955)
-//                          dependency resolved by a row-staggered wavefront
-//   K4 k_compact_unique    _unique_palette push_backs as a prefix sum       (codec/dxt_image.cpp:953-954)
+//                          dependency resolved by a row-staggered wavefront; direct form, the tiled
+//                          form is in mptc_intra.cu, the leftover kernel of inter frames in mptc_sparse.cu
+//   K4 k_compact_count /   _unique_palette push_backs as an ordered prefix  (codec/dxt_image.cpp:953-954)
+//      k_compact_unique    sum over chunks of 1024 blocks
 //   K5 k_endpoint_planes   RGB565 -> YCoCg667 -> 64x64 5/3 wavelet -> u8    (codec/codec.cpp:804-839, wavelet.cpp:30-131)
 //
 // No tensor cores: nothing here is a dense contraction (integer / ordered-FP32 work).
@@ -355,11 +358,11 @@ k_intra_wavefront(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int *__r
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: unique-palette compaction.  One CTA per frame; ordered prefix sum over the
-// "(255,255)" motion entries; emits the interp words in raster order.
+// K4: unique-palette compaction: ordered prefix sum over the "(255,255)" motion entries, emits
+// the interp words in raster order.  Two passes over chunks of 1024 raster-ordered blocks (any
+// number of CTAs per frame): count the unique blocks of every chunk, then every chunk emits its
+// words behind the chunks before it.
 // ------------------------------------------------------------------------------------------
-// Two passes over chunks of 1024 raster-ordered blocks (any number of CTAs per frame): count the
-// unique blocks of every chunk, then every chunk emits its words behind the chunks before it.
 constexpr int kCompactChunk = 1024;
 
 __global__ void __launch_bounds__(kCompactChunk)
