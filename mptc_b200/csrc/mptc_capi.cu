@@ -294,7 +294,13 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
     StageEvent &e = stage_begin(L, 3, s);
     if (k > 0) {
       int ctas = c->sparse_ctas;
-      if (ctas <= 0) { ctas = 592 / L.n_gops; ctas = ctas < 16 ? 16 : (ctas > 148 ? 148 : ctas); }
+      if (ctas <= 0) {
+        // small windows leave more blocks over and make the items cheap: twice the CTAs per frame pay
+        // there (sa 2: +18 %), while at the default window they cost 1 % (profiles/r1_v7_sparse_ctas.txt)
+        const int cap = sa <= 4 ? 296 : 148;
+        ctas = 4 * cap / L.n_gops;
+        ctas = ctas < 16 ? 16 : (ctas > cap ? cap : ctas);
+      }
       const int max_items = (int)((long long)c->nb * c->sparse_max_pct / 100);
       launch_intra_sparse(v, k, L.n_gops, sa, thr, L.d_tickets + gop + k * L.n_gops, ctas, max_items, s);
     }
