@@ -111,6 +111,9 @@ def _diverse_frames(w, h, n, seed, kind):
     (384, 96, 3, 8, 0, 3, "mixed"),        # groups on the fast path next to overflowing ones
     (192, 192, 2, 16, 10, 1, "noisy"),     # intra only (two CTAs per row)
     (132, 100, 3, 12, 0, 2, "noise"),      # ragged group at the row end, odd block counts
+    (192, 128, 2, 24, 0, 2, "noise"),      # window wider than 32: the general scan path, chunked
+    (256, 64, 3, 3, 0, 3, "noise"),        # tiny window, nearly every block left over
+    (160, 160, 2, 40, 5, 2, "mixed"),      # search area larger than the tiled kernels' tables on noise
 ])
 def test_word_diverse_content_bit_exact(ctx, w, h, n, sa, thr, gop, kind):
     frames = _diverse_frames(w, h, n, 17, kind)
