@@ -60,30 +60,13 @@ __device__ __forceinline__ uint16_t hash_insert(uint32_t *keys, int ht, int hshi
   return (uint16_t)h;
 }
 
-}  // namespace
-
-__global__ void __launch_bounds__(kThreads)
-k_intra_sparse(SeqView v, int k_in_gop, int sa, int thr, int max_items, int *__restrict__ tickets) {
-  __shared__ uint16_t s_rows[kMaxRows];
-  __shared__ int s_row_off[kMaxRows + 1];
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_wsum[kWarps];
-  __shared__ int s_n, s_item, s_count, s_special, s_pending, s_late;
-  __shared__ TargetCtx s_t;
-  __shared__ WinnerState s_red[kWarps];
-
-  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
-  if (f >= v.first + v.count) return;
+// Builds the frame's raster-ordered directory of leftover blocks in shared memory (every CTA the
+// same one): s_rows[q] = q-th block row with leftovers, s_row_off[q] = leftovers before that row.
+// Returns the number of items, or -1 if the frame is left to the row wavefront.
+__device__ __forceinline__ int sparse_directory(const SeqView &v, const uint8_t *flags, const uint8_t *row_todo, int max_items,
+                                                uint16_t *s_rows, int *s_row_off, int *s_wsum, int *s_n_ptr, int &n_rows_out) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint8_t *frame = v.rgb + v.frame_bytes * f;
-  uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
-  const uint32_t *cur_words = reinterpret_cast<const uint32_t *>(cur);
-  const uint64_t *init = v.init_blocks + (size_t)f * v.nb;
-  uint8_t *flags = v.flags + (size_t)f * v.nb;
-  uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
-  const uint8_t *row_todo = v.row_todo + (size_t)f * v.bh;
-  int *ticket = tickets + blockIdx.y;
-
+  int &s_n = *s_n_ptr;
   // ---- rows with leftovers, in order ------------------------------------------------------------
   int n_rows = 0;
   for (int r0 = 0; r0 < v.bh; r0 += kThreads) {
@@ -140,6 +123,69 @@ k_intra_sparse(SeqView v, int k_in_gop, int sa, int thr, int max_items, int *__r
     __syncthreads();
     overflow = s_n > max_items;
   }
+  n_rows_out = n_rows;
+  return overflow ? -1 : s_n;
+}
+
+// item -> (block row, block column): every warp resolves it redundantly (no barrier needed).
+__device__ __forceinline__ void sparse_locate(const SeqView &v, const uint8_t *flags, const uint16_t *s_rows, const int *s_row_off,
+                                              int n_rows, int item, int lane, int &by_out, int &bx_out) {
+  int lo = 0, hi = n_rows - 1;
+  while (lo < hi) {   // largest q with s_row_off[q] <= item
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_row_off[mid] <= item) lo = mid; else hi = mid - 1;
+  }
+  const int by = s_rows[lo];
+  int nth = item - s_row_off[lo], bx = 0;
+  const uint8_t *fr = flags + (size_t)by * v.bw;
+  for (int x0 = 0; x0 < v.bw; x0 += 32 * 8) {       // 8 independent loads in flight per lane
+    uint8_t fl[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int x = x0 + 32 * q + lane;
+      fl[q] = x < v.bw ? ld_flag(fr + x) : (uint8_t)1;
+    }
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const unsigned m = __ballot_sync(0xffffffffu, fl[q] != 1);
+      const int c = __popc(m);
+      if (!done && nth < c) { bx = x0 + 32 * q + (int)__fns(m, 0, nth + 1); done = true; }
+      if (!done) nth -= c;
+    }
+    if (done) break;
+  }
+  by_out = by;
+  bx_out = bx;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads)
+k_intra_sparse(SeqView v, int k_in_gop, int sa, int thr, int max_items, int *__restrict__ tickets) {
+  __shared__ uint16_t s_rows[kMaxRows];
+  __shared__ int s_row_off[kMaxRows + 1];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_wsum[kWarps];
+  __shared__ int s_n, s_item, s_count, s_special, s_pending, s_late;
+  __shared__ TargetCtx s_t;
+  __shared__ WinnerState s_red[kWarps];
+
+  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
+  if (f >= v.first + v.count) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint8_t *frame = v.rgb + v.frame_bytes * f;
+  uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
+  const uint32_t *cur_words = reinterpret_cast<const uint32_t *>(cur);
+  const uint64_t *init = v.init_blocks + (size_t)f * v.nb;
+  uint8_t *flags = v.flags + (size_t)f * v.nb;
+  uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
+  const uint8_t *row_todo = v.row_todo + (size_t)f * v.bh;
+  int *ticket = tickets + blockIdx.y;
+
+  int n_rows = 0;
+  const int dir_items = sparse_directory(v, flags, row_todo, max_items, s_rows, s_row_off, s_wsum, &s_n, n_rows);
+  const bool overflow = dir_items < 0;
   const int n_items = overflow ? 0 : s_n;
   if (blockIdx.x == 0 && tid == 0) v.n_unique[f] = overflow ? kSparseNotHandled : (uint32_t)n_items;
   if (overflow || n_items == 0) return;   // the row wavefront takes the frame / nothing to do
@@ -163,34 +209,8 @@ k_intra_sparse(SeqView v, int k_in_gop, int sa, int thr, int max_items, int *__r
     __syncthreads();
     const int item = s_item;
     if (item >= n_items) return;
-    // item -> (row, column): every warp resolves it redundantly (no barrier needed)
-    int lo = 0, hi = n_rows - 1;
-    while (lo < hi) {   // largest q with s_row_off[q] <= item
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_row_off[mid] <= item) lo = mid; else hi = mid - 1;
-    }
-    const int by = s_rows[lo];
-    int nth = item - s_row_off[lo], bx = 0;
-    {
-      const uint8_t *fr = flags + (size_t)by * v.bw;
-      for (int x0 = 0; x0 < v.bw; x0 += 32 * 8) {       // 8 independent loads in flight per lane
-        uint8_t fl[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int x = x0 + 32 * q + lane;
-          fl[q] = x < v.bw ? ld_flag(fr + x) : (uint8_t)1;
-        }
-        bool done = false;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const unsigned m = __ballot_sync(0xffffffffu, fl[q] != 1);
-          const int c = __popc(m);
-          if (!done && nth < c) { bx = x0 + 32 * q + (int)__fns(m, 0, nth + 1); done = true; }
-          if (!done) nth -= c;
-        }
-        if (done) break;
-      }
-    }
+    int by, bx;
+    sparse_locate(v, flags, s_rows, s_row_off, n_rows, item, lane, by, bx);
     const int b = by * v.bw + bx;
     if (tid == 0) build_target(s_t, frame, v.w, bx, by, init[b]);
     WinnerState s;
@@ -308,6 +328,89 @@ k_intra_sparse(SeqView v, int k_in_gop, int sa, int thr, int max_items, int *__r
   }
 }
 
+// Tiny windows (search_area <= 2 as launched; the kernel handles up to 64 positions): one WARP per item.  Small windows leave
+// 10-45 % of an inter frame's blocks over and each item is cheap, so what counts is the number of
+// items in flight: eight per CTA instead of one.  Same directory, same ticket order, same
+// per-block flags as k_intra_sparse; no de-duplication (every lane evaluates its one or two
+// positions directly).
+__global__ void __launch_bounds__(kThreads)
+k_intra_sparse_warp(SeqView v, int k_in_gop, int sa, int thr, int max_items, int *__restrict__ tickets) {
+  __shared__ uint16_t s_rows[kMaxRows];
+  __shared__ int s_row_off[kMaxRows + 1];
+  __shared__ int s_wsum[kWarps];
+  __shared__ int s_n;
+  __shared__ TargetCtx s_t[kWarps];
+
+  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
+  if (f >= v.first + v.count) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint8_t *frame = v.rgb + v.frame_bytes * f;
+  uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
+  const uint32_t *cur_words = reinterpret_cast<const uint32_t *>(cur);
+  uint32_t *cur_words_rw = reinterpret_cast<uint32_t *>(cur);
+  const uint64_t *init = v.init_blocks + (size_t)f * v.nb;
+  uint8_t *flags = v.flags + (size_t)f * v.nb;
+  uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
+  const uint8_t *row_todo = v.row_todo + (size_t)f * v.bh;
+  int *ticket = tickets + blockIdx.y;
+
+  int n_rows = 0;
+  const int dir_items = sparse_directory(v, flags, row_todo, max_items, s_rows, s_row_off, s_wsum, &s_n, n_rows);
+  const bool overflow = dir_items < 0;
+  const int n_items = overflow ? 0 : s_n;
+  if (blockIdx.x == 0 && tid == 0) v.n_unique[f] = overflow ? kSparseNotHandled : (uint32_t)n_items;
+  if (overflow || n_items == 0) return;
+
+  const int W = 2 * sa, NP = W * W;   // NP <= 64
+  TargetCtx &t = s_t[wid];
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(ticket, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) return;
+    int by, bx;
+    sparse_locate(v, flags, s_rows, s_row_off, n_rows, item, lane, by, bx);
+    const int b = by * v.bw + bx;
+    __syncwarp();                      // the previous item's reads of t are done
+    if (lane == 0) build_target(t, frame, v.w, bx, by, init[b]);
+    __syncwarp();
+    WinnerState s;
+    winner_init(s);
+    for (int p = lane; p < NP; p += 32) {
+      const int row = p / W, col = p - row * W;          // scan order: j downwards, i downwards
+      const int j = by - row, i = bx + sa - 1 - col;
+      if (i < 0 || j < 0 || i >= v.bw || (row == 0 && i >= bx)) continue;
+      const size_t idx = (size_t)j * v.bw + i;
+      uint8_t fl = ld_flag(flags + idx);
+      while (fl == 0) {                                  // an earlier leftover, still undecided
+        __nanosleep(32);
+        fl = ld_flag(flags + idx);
+      }
+      if (fl == 2) __threadfence();                      // decided by another warp of this launch
+      winner_update(s, eval_candidate(t, __ldcg(cur_words + 2 * idx + 1)), row, col, W);
+    }
+    winner_warp_reduce(s);
+    if (lane == 0) {
+      int row, col;
+      const int min_err = winner_resolve(s, W, row, col);
+      if (min_err <= thr) {
+        const size_t src = (size_t)(by - row) * v.bw + (bx + sa - 1 - col);
+        const uint32_t word = __ldcg(cur_words + 2 * src + 1);
+        cur_words_rw[2 * (size_t)b + 1] = word;          // the index word first: all a dependant waits for
+        __threadfence();
+        *reinterpret_cast<volatile uint8_t *>(flags + b) = 2;
+        cur_words_rw[2 * (size_t)b] = (uint32_t)winning_block(t, word);
+        motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);   // x = (i - bx) + sa
+        motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);   // y = (j - by) + 2sa - 1
+      } else {
+        *reinterpret_cast<volatile uint8_t *>(flags + b) = 2;   // keeps its initial block
+        motion[2 * b + 0] = 255;
+        motion[2 * b + 1] = 255;
+      }
+    }
+  }
+}
+
 void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
                          int max_items, cudaStream_t s) {
   const int np = 4 * sa * sa;
@@ -321,6 +424,11 @@ void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int
     conf = bytes;
   }
   dim3 grid(ctas_per_frame, n_gops);
+  if (np <= 16) {   // search_area <= 2 (measured: sa 2 +16 % at thr 50, +11 % at thr 0; sa 4 -31 % at thr 0, where
+                    // de-duplicating the 64 positions per item pays)
+    k_intra_sparse_warp<<<grid, kThreads, 0, s>>>(v, k_in_gop, sa, thr, max_items, tickets);
+    return;
+  }
   k_intra_sparse<<<grid, kThreads, bytes, s>>>(v, k_in_gop, sa, thr, max_items, tickets);
 }
 
