@@ -34,6 +34,7 @@ struct TileSmem {
   uint32_t *ulist;     // [NP]   dense list of distinct words
   WordInfo *info;      // [kChunk]
   int *err;            // [kChunk + 1][33]; row kChunk = "rejected" for every target
+  uint32_t *epk;       // [kChunk][33]; the refitted endpoints of (word, target), packed 565 | 565 << 16
   uint8_t *lut5, *lut6;  // ToFiveBits / ToSixBits tables
 };
 
@@ -52,6 +53,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int sa, int *np_out, int *ht_o
   size_t b = 0;
   b += (size_t)kChunk * sizeof(WordInfo);          // info (16-byte aligned first)
   b += (size_t)(kChunk + 1) * 33 * sizeof(int);    // err
+  b += (size_t)kChunk * 33 * sizeof(uint32_t);     // epk
   b += 512;                                        // lut5, lut6
   b += (size_t)NP * 4;                             // win
   b += (size_t)(HT + 1) * 4;                       // keys
@@ -78,6 +80,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     unsigned char *p = smem_raw;
     sm.info = reinterpret_cast<WordInfo *>(p); p += (size_t)kChunk * sizeof(WordInfo);
     sm.err = reinterpret_cast<int *>(p);       p += (size_t)(kChunk + 1) * 33 * sizeof(int);
+    sm.epk = reinterpret_cast<uint32_t *>(p);  p += (size_t)kChunk * 33 * sizeof(uint32_t);
     sm.lut5 = p; sm.lut6 = p + 256;            p += 512;
     sm.win = reinterpret_cast<uint32_t *>(p);  p += (size_t)NP * 4;
     sm.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)(HT + 1) * 4;
@@ -195,7 +198,9 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     // evaluate: warp = one distinct word, lane = target
     for (int u = wid; u < cn; u += kWarps) {
       const uint32_t word = sm.ulist[c0 + u];
-      sm.err[u * 33 + lane] = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6);
+      uint32_t packed;
+      sm.err[u * 33 + lane] = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6, &packed);
+      sm.epk[u * 33 + lane] = packed;
     }
     __syncthreads();
 
@@ -232,8 +237,15 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     const int row = s_res_pos[lane] >> 8, col = s_res_pos[lane] & 0xFF;
     uint8_t flag = 0;
     if (min_err <= thr) {
-      const uint32_t word = sm.win[((lane >> 3) + row) * UW + (lane & (kTileX - 1)) + col];
-      v.final_blocks[(size_t)f * v.nb + tb] = lane_winning_block(t, word);
+      const int at = ((lane >> 3) + row) * UW + (lane & (kTileX - 1)) + col;
+      const uint32_t word = sm.win[at];
+      // the winner's endpoints were computed when its word was evaluated: with a single chunk of
+      // words the table still holds them and the block needs no second refit
+      uint64_t blk;
+      if (word == t.own_word) blk = t.own_block;
+      else if (U <= kChunk) blk = (uint64_t)sm.epk[(int)sm.pos_uid[at] * 33 + lane] | ((uint64_t)word << 32);
+      else blk = lane_winning_block(t, word);
+      v.final_blocks[(size_t)f * v.nb + tb] = blk;
       v.motion[((size_t)f * v.nb + tb) * 2 + 0] = (uint8_t)(col | 0x80);   // x = (i - bx) + sa
       v.motion[((size_t)f * v.nb + tb) * 2 + 1] = (uint8_t)(row | 0x80);   // y = (j - by) + sa
       flag = 1;

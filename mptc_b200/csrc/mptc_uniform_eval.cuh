@@ -114,8 +114,10 @@ constexpr int kRejectedSmall = 65535;  // "rejected" marker that fits the packed
 
 // err_diff of (this lane's target, warp-uniform `word`), or kRejectedSmall.
 // lut5/lut6: 256-entry tables of ToFiveBits / ToSixBits (dxt_image.cpp:72-121) in shared memory.
+// packed_out (optional): the refitted endpoints as they would be emitted, Pack565(ep1) | Pack565(ep2) << 16,
+// so that the winner's 8-byte block needs no second refit.
 __device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, const WordInfo &wi,
-                                            const uint8_t *lut5, const uint8_t *lut6) {
+                                            const uint8_t *lut5, const uint8_t *lut6, uint32_t *packed_out = nullptr) {
   // wi lives in shared memory: every read below is a warp-uniform (broadcast) load
   // (ax_j, bx_j) accumulated as pairs: two individually rounded products, one packed add.
   // (Scalar FMUL + FADD2 is not contracted by ptxas; FMUL2 + FADD2 would be.)
@@ -156,6 +158,7 @@ __device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, 
   uint32_t sum = plane_error(t.pl + 0, palr, wi.sel, 0u);
   sum = plane_error(t.pl + 4, palg, wi.sel, sum);
   sum = plane_error(t.pl + 8, palb, wi.sel, sum);
+  if (packed_out) *packed_out = pk1 | (pk2 << 16);
   int e = (int)(sum / 48u) - t.orig_err;
   e = (pk1 > pk2) ? e : kRejectedSmall;
   return (word == t.own_word) ? 0 : e;
