@@ -302,7 +302,8 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
         ctas = ctas < 16 ? 16 : (ctas > cap ? cap : ctas);
       }
       const int max_items = (int)((long long)c->nb * c->sparse_max_pct / 100);
-      launch_intra_sparse(v, k, L.n_gops, sa, thr, L.d_tickets + gop + k * L.n_gops, ctas, max_items, s);
+      if (!launch_intra_sparse(v, k, L.n_gops, sa, thr, L.d_tickets + gop + k * L.n_gops, ctas, max_items, s))
+        return fail(c, MPTC_E_CUDA, "the sparse intra search kernel could not be configured for search_area %d", sa);
     }
     launch_intra_wavefront(v, k, L.n_gops, sa, thr, L.d_tickets + k, c->max_wave_ctas, wave_rows * L.n_gops, s);
     stage_end(c, e, s, k > 0 ? 2 : 1);

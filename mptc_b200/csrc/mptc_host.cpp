@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <thread>
 
 namespace mptc {
@@ -168,6 +169,7 @@ size_t RangeEncoder::encode_raw(const uint8_t *sym, size_t n, uint8_t *buf) {
 
 void RangeEncoder::encode_all(const uint8_t *sym, size_t n, std::vector<uint8_t> &out) {
   Scratch sc = scratch_acquire(encode_bound(n));
+  if (!sc.p) throw std::bad_alloc();   // reported as MPTC_E_NOMEM at the C boundary
   const size_t len = encode_raw(sym, n, sc.p);
   out.insert(out.end(), sc.p, sc.p + len);
   scratch_release(sc);
@@ -194,6 +196,7 @@ void RangeEncoder::encode_pair_raw(RangeEncoder &ma, const uint8_t *sa, size_t n
 void RangeEncoder::encode_pair(RangeEncoder &ma, const uint8_t *sa, size_t na, std::vector<uint8_t> &oa,
                                RangeEncoder &mb, const uint8_t *sb, size_t nb, std::vector<uint8_t> &ob) {
   Scratch sc = scratch_acquire(encode_bound(na) + encode_bound(nb));
+  if (!sc.p) throw std::bad_alloc();
   size_t la = 0, lb = 0;
   encode_pair_raw(ma, sa, na, sc.p, &la, mb, sb, nb, sc.p + encode_bound(na), &lb);
   oa.insert(oa.end(), sc.p, sc.p + la);
@@ -354,13 +357,31 @@ void parallel_for(int n_tasks, int threads, F &&fn) {
     return;
   }
   std::atomic<int> next(0);
+  std::atomic<bool> threw(false);   // an exception must not leave a std::thread (std::terminate)
   std::vector<std::thread> pool;
   pool.reserve(threads);
   for (int t = 0; t < threads; ++t)
     pool.emplace_back([&]() {
-      for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) fn(i);
+      try {
+        for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) fn(i);
+      } catch (...) {
+        threw.store(true);
+        next.store(n_tasks);
+      }
     });
   for (auto &th : pool) th.join();
+  if (threw.load()) throw std::bad_alloc();
+}
+
+// Body of an extern "C" entry point: no exception crosses the C ABI (allocation failures of the
+// std::vector bookkeeping become MPTC_E_NOMEM).
+template <typename F>
+int guarded(F &&body) {
+  try {
+    return body();
+  } catch (...) {
+    return MPTC_E_NOMEM;
+  }
 }
 
 struct StreamJob {
@@ -536,16 +557,19 @@ using namespace mptc;
 extern "C" {
 
 int mptc_arith_encode(const uint8_t *sym, size_t n, uint8_t *out, size_t cap, size_t *out_bytes) {
+  return guarded([&]() -> int {
   if (!sym && n) return MPTC_E_ARG;
   std::vector<uint8_t> bytes;
   RangeEncoder enc;
   enc.encode_all(sym, n, bytes);
   return copy_out(bytes, out, cap, out_bytes);
+  });
 }
 
 int mptc_frame_payload(const uint8_t *motion, size_t nb, const uint8_t *planes, size_t plane_syms,
                        uint32_t n_unique, int threads, uint8_t *out, size_t cap, size_t *out_bytes,
                        uint32_t *sizes) {
+  return guarded([&]() -> int {
   if (!motion || !planes) return MPTC_E_ARG;
   StreamJob jobs[5];
   frame_jobs(motion, nb, planes, plane_syms, jobs);
@@ -563,12 +587,14 @@ int mptc_frame_payload(const uint8_t *motion, size_t nb, const uint8_t *planes, 
   if (sizes)
     for (int s = 0; s < 5; ++s) sizes[s] = (uint32_t)jobs[s].out.size();
   return copy_out(bytes, out, cap, out_bytes);
+  });
 }
 
 int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, const uint8_t *motion,
                          const uint32_t *unique, const uint32_t *n_unique, const uint8_t *planes,
                          int threads, uint8_t *out, size_t cap, size_t *out_bytes,
                          mptc_stream_stats *stats) {
+  return guarded([&]() -> int {
   if (!p || !motion || !unique || !n_unique || !planes || n_frames < 1) return MPTC_E_ARG;
   if (p->gop < 1 || p->gop > 255 || p->search_area < 1 || p->search_area > 63) return MPTC_E_ARG;
   const auto t0 = std::chrono::steady_clock::now();
@@ -584,6 +610,7 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
     *stats = st;
   }
   return wr;
+  });
 }
 
 // GPU hot path and host arithmetic coding OVERLAPPED (BASELINE.json north_star): the encode is
@@ -593,6 +620,7 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
 int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, int w, int h,
                        const mptc_gpu_params *p, int threads, uint8_t *out, size_t cap,
                        size_t *out_bytes, mptc_stream_stats *stats) {
+  return guarded([&]() -> int {
   if (!ctx || !frames || !p || n_frames < 1) return MPTC_E_ARG;
   if (w < 4 || h < 4 || (w & 3) || (h & 3)) return MPTC_E_ARG;
   if (p->gop < 1 || p->gop > 255 || p->search_area < 1 || p->search_area > 63) return MPTC_E_ARG;
@@ -647,14 +675,17 @@ int mptc_encode_stream(mptc_gpu_ctx *ctx, const uint8_t *frames, int n_frames, i
     }
   }
   return r;
+  });
 }
 
 // ---- decoder side ------------------------------------------------------------------------------
 
 int mptc_arith_decode(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n) {
+  return guarded([&]() -> int {
   if ((!code && nbytes) || (!sym && n)) return MPTC_E_ARG;
   RangeDecoder dec;
   return dec.decode_all(code, nbytes, sym, n) ? MPTC_OK : MPTC_E_DATA;
+  });
 }
 
 int mptc_stream_info(const uint8_t *stream, size_t bytes, mptc_stream_header *hdr) {
@@ -667,12 +698,18 @@ int mptc_stream_info(const uint8_t *stream, size_t bytes, mptc_stream_header *hd
   hdr->height = (int)v[0]; hdr->width = (int)v[1];
   hdr->gop = stream[8]; hdr->search_area = stream[9];
   hdr->n_groups = (int)g;
-  hdr->n_frames = (int)g * hdr->gop;
+  hdr->n_frames = 0;
   hdr->max_unique_bytes = mx[0]; hdr->max_comp_palette = mx[1]; hdr->max_comp_motion = mx[2];
   hdr->max_comp_ep_y = mx[3]; hdr->max_comp_ep_c = mx[4];
   if (hdr->width < 4 || hdr->height < 4 || (hdr->width & 3) || (hdr->height & 3) || hdr->width > 65536 ||
       hdr->height > 65536 || hdr->gop < 1 || hdr->search_area < 1 || hdr->search_area > 63 || g < 1 || g > (1u << 24))
     return MPTC_E_DATA;
+  // every group holds at least two u32 (palette size, unique bytes) and every frame six (n_unique +
+  // five record sizes): a header that promises more than the stream can hold is corrupt, and it is
+  // rejected before anything is sized by it
+  const uint64_t n_frames = (uint64_t)g * (uint64_t)hdr->gop;
+  if (n_frames > (1u << 24) || (uint64_t)bytes < 34 + (uint64_t)g * 8 + n_frames * 24) return MPTC_E_DATA;
+  hdr->n_frames = (int)n_frames;
   return MPTC_OK;
 }
 
@@ -684,6 +721,7 @@ int mptc_stream_info(const uint8_t *stream, size_t bytes, mptc_stream_header *hd
 // in the same launches -- while the pool is already decoding the next groups.
 int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, int threads, uint64_t *blocks_out,
                        uint8_t *rgb_out, mptc_decode_stats *stats) {
+  return guarded([&]() -> int {
   if (!ctx || !stream) return MPTC_E_ARG;
   const auto t0 = std::chrono::steady_clock::now();
   mptc_stream_header H;
@@ -773,16 +811,21 @@ int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, i
   std::atomic<int> next(0), corrupt(0);
   const int n_tasks = (int)tasks.size();
   auto worker = [&]() {
-    RangeDecoder pool4[4];
-    RangeDecoder *d[4] = {&pool4[0], &pool4[1], &pool4[2], &pool4[3]};
-    for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) {
-      const Task &t = tasks[i];
-      RangeDecoder::StreamIO io[4];
-      for (int q = 0; q < t.k; ++q) io[q] = {recs[t.r[q]].code, recs[t.r[q]].nbytes, recs[t.r[q]].dst, recs[t.r[q]].n};
-      const bool ok = t.k == 1 ? d[0]->decode_all(io[0].code, io[0].nbytes, io[0].sym, io[0].n)
-                               : RangeDecoder::decode_multi(d, io, t.k);
-      if (!ok) corrupt.store(1);
-      left[recs[t.r[0]].group].fetch_sub(t.k, std::memory_order_release);
+    try {
+      RangeDecoder pool4[4];
+      RangeDecoder *d[4] = {&pool4[0], &pool4[1], &pool4[2], &pool4[3]};
+      for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) {
+        const Task &t = tasks[i];
+        RangeDecoder::StreamIO io[4];
+        for (int q = 0; q < t.k; ++q) io[q] = {recs[t.r[q]].code, recs[t.r[q]].nbytes, recs[t.r[q]].dst, recs[t.r[q]].n};
+        const bool ok = t.k == 1 ? d[0]->decode_all(io[0].code, io[0].nbytes, io[0].sym, io[0].n)
+                                 : RangeDecoder::decode_multi(d, io, t.k);
+        if (!ok) corrupt.store(1);
+        left[recs[t.r[0]].group].fetch_sub(t.k, std::memory_order_release);
+      }
+    } catch (...) {               // an exception must not leave a std::thread; release the feeder loop
+      corrupt.store(2);
+      for (int g = 0; g < H.n_groups; ++g) left[g].store(0, std::memory_order_release);
     }
   };
   if (threads < 1) threads = 1;
@@ -802,7 +845,7 @@ int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, i
   }
   for (auto &th : pool) th.join();
   const auto t2 = std::chrono::steady_clock::now();
-  if (r == MPTC_OK && corrupt.load()) r = MPTC_E_DATA;
+  if (r == MPTC_OK && corrupt.load()) r = corrupt.load() == 2 ? MPTC_E_NOMEM : MPTC_E_DATA;
   if (r == MPTC_OK) r = mptc_gpu_seq_decode_download(ctx, 0, n_frames, blocks_out, rgb_out);
   const auto t3 = std::chrono::steady_clock::now();
   if (stats) {
@@ -812,6 +855,7 @@ int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, i
     stats->symbols = (uint64_t)n * (2 * nb + 6 * ps) + pal_total;
   }
   return r;
+  });
 }
 
 }  // extern "C"

@@ -259,21 +259,20 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
 // caller then uses the direct kernel.
 bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
   static int max_optin = -1;
-  if (max_optin < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  }
-  const size_t bytes = tile_smem_bytes(sa, nullptr, nullptr);
-  if (bytes + 1024 > (size_t)max_optin) return false;
   static size_t configured[kMaxDevices] = {0};   // per device: one context per GPU may live in one process
+  const size_t bytes = tile_smem_bytes(sa, nullptr, nullptr);
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
-  size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
-  if (bytes > conf) {
-    if (cudaFuncSetAttribute(k_inter_search_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
-      return false;
-    conf = bytes;
+  {
+    std::lock_guard<std::mutex> lock(launch_cfg_mutex());
+    if (max_optin < 0) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cur_dev);
+    if (bytes + 1024 > (size_t)max_optin) return false;
+    size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
+    if (bytes > conf) {
+      if (cudaFuncSetAttribute(k_inter_search_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return false;
+      conf = bytes;
+    }
   }
   const int tiles = ((v.bw + kTileX - 1) / kTileX) * ((v.bh + kTileY - 1) / kTileY);
   dim3 grid(tiles, n_gops);

@@ -177,7 +177,9 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
     __syncthreads();
     const int item = s_item;
     if (item >= n_items) return;
-    const int gop_i = item % n_gops, by = (item / n_gops) / split, part = (item / n_gops) % split;
+    // the `split` CTAs of a row hold ADJACENT tickets: a part only ever waits for rows above (lower
+    // tickets, handed out earlier) and for its partner, whose ticket is the next one to be taken
+    const int part = item % split, gop_i = (item / split) % n_gops, by = item / (split * n_gops);
     const int f = v.first + gop_i * v.gop + k_in_gop;
     if (f >= v.first + v.count) continue;
     if (k_in_gop > 0 && v.n_unique[f] != kSparseNotHandled) continue;
@@ -815,30 +817,35 @@ bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, in
   static int max_optin = -1;
   static int max_ctas_dev[kMaxDevices] = {0};
   static size_t configured_dev[kMaxDevices] = {0};   // per device: one context per GPU may live in one process
+  static int split_intra = -1;
   int dev = 0;
   cudaGetDevice(&dev);
-  size_t &configured = configured_dev[dev & (kMaxDevices - 1)];
-  int &max_ctas = max_ctas_dev[dev & (kMaxDevices - 1)];
-  if (max_optin < 0) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t bytes = group_smem_bytes(sa, nullptr, nullptr);
-  if (bytes + 4096 > (size_t)max_optin) return false;
-  if (bytes > configured) {
-    if (cudaFuncSetAttribute(k_intra_wavefront_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
-      return false;
-    configured = bytes;
-    int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intra_wavefront_tiled, kThreads, bytes);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    max_ctas = (per_sm < 1 ? 1 : per_sm) * sms;
+  int max_ctas = 0;
+  {
+    std::lock_guard<std::mutex> lock(launch_cfg_mutex());
+    size_t &configured = configured_dev[dev & (kMaxDevices - 1)];
+    if (max_optin < 0) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (bytes + 4096 > (size_t)max_optin) return false;
+    if (bytes > configured) {
+      if (cudaFuncSetAttribute(k_intra_wavefront_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return false;
+      configured = bytes;
+      int per_sm = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intra_wavefront_tiled, kThreads, bytes);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      max_ctas_dev[dev & (kMaxDevices - 1)] = (per_sm < 1 ? 1 : per_sm) * sms;
+    }
+    max_ctas = max_ctas_dev[dev & (kMaxDevices - 1)];
+    if (split_intra < 0) {
+      const char *e = getenv("MPTC_ROW_SPLIT");
+      split_intra = (e && *e) ? atoi(e) : 2;
+      if (split_intra < 1) split_intra = 1;
+    }
   }
-  static int split_intra = -1;
-  if (split_intra < 0) {
-    const char *e = getenv("MPTC_ROW_SPLIT");
-    split_intra = (e && *e) ? atoi(e) : 2;
-    if (split_intra < 1) split_intra = 1;
-  }
-  // Intra frames: `split` CTAs per row (see the kernel).  A CTA of a row waits for its neighbour,
-  // whose ticket is the next one, so at least `split` CTAs must be resident.
+  // Intra frames: `split` CTAs per row (see the kernel).  A CTA of a row waits for its neighbours,
+  // whose tickets are adjacent to its own (item = (row * n_gops + gop) * split + part), so `split`
+  // resident CTAs are enough whatever n_gops is.
   int split = k_in_gop == 0 ? split_intra : 1;
   if (grid_cap > 0 && grid_cap < split) split = 1;
   const int items = n_gops * v.bh * split;

@@ -544,14 +544,22 @@ void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_co
   k_compact_unique<<<grid, kCompactChunk, 0, s>>>(v, f0, fstride);
 }
 
+std::mutex &launch_cfg_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s) {
   static bool configured[kMaxDevices] = {false};   // per device: one context per GPU may live in one process
   const int bytes = 12 * kPlaneElems * (int)sizeof(int16_t);
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
-  if (!configured[cur_dev & (kMaxDevices - 1)]) {
-    cudaFuncSetAttribute(k_endpoint_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    configured[cur_dev & (kMaxDevices - 1)] = true;
+  {
+    std::lock_guard<std::mutex> lock(launch_cfg_mutex());
+    if (!configured[cur_dev & (kMaxDevices - 1)]) {
+      cudaFuncSetAttribute(k_endpoint_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      configured[cur_dev & (kMaxDevices - 1)] = true;
+    }
   }
   dim3 grid((pbw / kPlaneTile) * (pbh / kPlaneTile), nf);
   k_endpoint_planes<<<grid, 1024, bytes, s>>>(v, pbw, pbh, f0, fstride);

@@ -3,10 +3,15 @@
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <mutex>
 
 namespace mptc {
 
 constexpr int kMaxDevices = 64;   // per-device launch configuration caches (power of two)
+// The launchers cache per-device kernel attributes (opt-in shared memory, occupancy) in function-local
+// statics; several host threads (one context each, include/mptc_gpu.h) may launch at once, so every
+// read-modify-write of those caches happens under this mutex.
+std::mutex &launch_cfg_mutex();
 
 // Device-resident sequence: all arrays are [frame][...] over the reserved capacity.
 struct SeqView {
@@ -30,7 +35,8 @@ struct SeqView {
 // Inter frames: K3s (mptc_sparse.cu) handles frames with at most max_items leftover blocks and
 // tells the row wavefront through n_unique[f] (0xFFFFFFFF = not handled, take the frame).
 constexpr uint32_t kSparseNotHandled = 0xFFFFFFFFu;
-void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
+// Returns false if the kernel could not be configured (nothing was launched).
+bool launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
                          int max_items, cudaStream_t s);
 
 cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);

@@ -411,25 +411,31 @@ k_intra_sparse_warp(SeqView v, int k_in_gop, int sa, int thr, int max_items, int
   }
 }
 
-void launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
+bool launch_intra_sparse(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *tickets, int ctas_per_frame,
                          int max_items, cudaStream_t s) {
   const int np = 4 * sa * sa;
   const size_t bytes = np <= kMaxPos ? sparse_smem_bytes(np) : 0;
   static size_t configured[kMaxDevices] = {0};   // per device; 0 = nothing beyond what fits without opt-in
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
-  size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
-  if (bytes > 48 * 1024 - 13 * 1024 && bytes > conf) {   // 35 KB fit next to the static arrays without opt-in
-    if (cudaFuncSetAttribute(k_intra_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return;
-    conf = bytes;
+  {
+    std::lock_guard<std::mutex> lock(launch_cfg_mutex());
+    size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
+    if (bytes > 48 * 1024 - 13 * 1024 && bytes > conf) {   // 35 KB fit next to the static arrays without opt-in
+      // on failure nothing is launched and the caller reports the error: the frames' n_unique would
+      // otherwise keep a stale "handled" value and their leftover blocks would never be searched
+      if (cudaFuncSetAttribute(k_intra_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+      conf = bytes;
+    }
   }
   dim3 grid(ctas_per_frame, n_gops);
   if (np <= 16) {   // search_area <= 2 (measured: sa 2 +16 % at thr 50, +11 % at thr 0; sa 4 -31 % at thr 0, where
                     // de-duplicating the 64 positions per item pays)
     k_intra_sparse_warp<<<grid, kThreads, 0, s>>>(v, k_in_gop, sa, thr, max_items, tickets);
-    return;
+    return true;
   }
   k_intra_sparse<<<grid, kThreads, bytes, s>>>(v, k_in_gop, sa, thr, max_items, tickets);
+  return true;
 }
 
 }  // namespace mptc

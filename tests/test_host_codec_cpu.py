@@ -109,3 +109,18 @@ def test_stream_info_reads_the_reference_header():
     assert (hdr.max_unique_bytes, hdr.max_comp_palette, hdr.max_comp_motion, hdr.max_comp_ep_y, hdr.max_comp_ep_c) == tuple(want)
     with pytest.raises(capi.MptcError):
         capi.stream_info(g["stream"].tobytes()[:20])
+
+
+def test_stream_info_rejects_headers_that_promise_more_than_the_stream_holds():
+    """A crafted 34-byte header (2^24 groups x gop 255) must be reported as corrupt before anything
+    is sized by it (mptc_decode_stream allocates per group / per frame)."""
+    import struct
+    hdr = struct.pack("<IIBBI", 256, 256, 255, 4, 1 << 24) + b"\0" * 20
+    assert len(hdr) == 34
+    with pytest.raises(capi.MptcError):
+        capi.stream_info(hdr)
+    g = load("stream_256x256_sa4_gop2")
+    s = bytearray(g["stream"].tobytes())
+    s[10:14] = struct.pack("<I", 1 << 20)           # far more groups than the stream has bytes for
+    with pytest.raises(capi.MptcError):
+        capi.stream_info(bytes(s))
