@@ -63,6 +63,14 @@ def set_workload(name: str, sa: int, thr: int, world: int = 1):
         WORKLOAD = f"{W}x{H} synthetic x{FRAMES} frames/GPU, search_area={SA}, err_threshold={THR}, gop={GOP}"
 METRIC = "mptc_encode_mpixel_per_s"
 UNIT = "Mpixel/s"
+SCAN_SLOTS_PER_POSITION = 8             # winner_update_fast: IMAD+MIN, NEG+LOP3+MIN, SHF+LOP3+MAX
+
+
+def base_config(world: int) -> dict:
+    """The `config` object of BOTH arms (the driver compares them key by key)."""
+    rgb_mb = FRAMES * W * H * 3 // 1000000
+    return {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "sharding": f"gop-sharded x{world}, no collective",
+            "l2": f"inputs ({rgb_mb} MB RGB per step) exceed the 126 MB L2; no explicit flush"}
 
 
 def measured_peaks():
@@ -237,7 +245,8 @@ def reference_arm(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU encoder; each step is a bounded sample of the workload"},
+        "config": base_config(max(args.gpus, 1)),
+        "reference_sample": "reference CPU encoder; each step is a bounded sample of the workload named in config",
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{cores} threads x one 2-frame GOP of a 512x512 crop, fit+search, sa={SA} thr={THR}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -246,30 +255,79 @@ def reference_arm(args, rank: int):
     print(json.dumps(line), file=claim_stdout(), flush=True)
 
 
-def ncu_evidence(dominant: str):
+def ncu_evidence(stage: str):
     """Counters of the dominant kernel from the committed ncu capture (profiles/ncu_counters.json,
-    written by profiles/ncu_summary.py --json); None if the file is missing."""
+    written by profiles/ncu_summary.py --json).  The capture is stamped with the hash of the kernel's
+    sources; a capture of other sources says nothing about the kernel that was just timed and is
+    reported as stale instead of being copied into the line."""
+    from mptc_b200.build import kernel_source_sha
     p = os.path.join(ROOT, "profiles", "ncu_counters.json")
     try:
         with open(p) as f:
-            return json.load(f).get(dominant)
+            ev = json.load(f).get(stage)
     except Exception:
-        return None
+        return None, "profiles/ncu_counters.json missing"
+    if not ev:
+        return None, f"no capture of the {stage} kernel"
+    have, want = ev.get("source_sha16"), kernel_source_sha(stage)
+    if have != want:
+        return None, f"capture is of other kernel sources (sha {have}, now {want}); re-run profiles/run_profile.sh"
+    keep = ("kernel", "frames_per_launch", "source", "source_sha16", "gpu__time_duration.sum", "dram_bytes_per_frame",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+    return {k: ev[k] for k in keep if k in ev}, None
+
+
+def parity_record(out, first_frame: int, what: str, w: int, h: int, sa: int, thr: int):
+    """Checks the outputs of the step that was just timed against the committed full-GOP fixture of the
+    unmodified reference for this configuration (tests/golden/gen_golden_full.py).  Hashing only --
+    no oracle code runs here."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from golden_util import compare_with_full_fixture, full_fixture_name, load
+    name = full_fixture_name(w, h, sa, thr, GOP)
+    if name is None:
+        return {"fixture": None, "frames": 0, "equal": None, "note": "no reference fixture for this configuration"}
+    g = load(name)
+    n, bad = compare_with_full_fixture(g, out["blocks"], out["motion"], out["unique"], out["n_unique"], first_frame=first_frame)
+    rec = {"fixture": f"tests/golden/{name}.npz", "frames": n, "equal": (not bad) if n else None,
+           "compared": "per-frame SHA-256 of final blocks, motion bytes and unique palette of " + what +
+                       " vs the unmodified reference (oracle/_ref) on the same frames",
+           "not_covered": "endpoint planes at 1080p/4K: the reference's wavelet is undefined unless the plane sizes are "
+                          "multiples of 64 blocks (image_processing.h:293-294); planes are pinned on 256-multiple fixtures"}
+    if bad:
+        rec["mismatches"] = bad[:8]
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def gen_frames(pin, w, h, first_frame, kind="clean", seed=1234):
+    """Fills a pinned (n, h, w, 3) array with the synthetic sequence (numpy releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from mptc_b200.synth import make_frame
+
+    def gen(f):
+        fr = make_frame(w, h, first_frame + f, seed)
+        if kind == "noisy":   # camera-like noise of +-24 on top of the sequence: ~distinct index words
+            rng = np.random.default_rng(1000 + first_frame + f)
+            fr = np.clip(fr.astype(np.int16) + rng.integers(-24, 25, size=fr.shape, dtype=np.int16), 0, 255).astype(np.uint8)
+        pin[f] = fr
+    with ThreadPoolExecutor(max(1, len(os.sched_getaffinity(0)))) as pool:
+        list(pool.map(gen, range(pin.shape[0])))
+
+
 def gpu_arm(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
 
     from mptc_b200 import capi
-    from mptc_b200.synth import make_frame
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the encoder hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = capi.bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {"numa_node": None}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -285,82 +343,92 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    cores = len(os.sched_getaffinity(0))
+    host_threads = max(1, min(cores, (os.cpu_count() or 1) // max(world, 1)))   # the ranks of one box share its cores
     ctx = capi.Context(local_rank)
-    nb = (W // 4) * (H // 4)
-    # this rank's shard of the 60*world-frame sequence: frames [60*rank, 60*rank+60)
-    pin_frames = capi.PinnedArray((FRAMES, H, W, 3), np.uint8)
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    issue_peak = SM_COUNT * SCHEDULERS * LANES * sm_max_mhz * 1e6 / 1e12
 
-    def gen(f):
-        pin_frames.array[f] = make_frame(W, H, FRAMES * rank + f)
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max(1, (os.cpu_count() or 1) // max(world, 1))) as pool:   # numpy releases the GIL
-        list(pool.map(gen, range(FRAMES)))
-    frames = pin_frames.array
-    pbw, pbh = (W // 4 + 63) // 64 * 64, (H // 4 + 63) // 64 * 64
-    pins = {"blocks": capi.PinnedArray((FRAMES, nb), np.uint64), "motion": capi.PinnedArray((FRAMES, 2 * nb), np.uint8),
-            "unique": capi.PinnedArray((FRAMES, nb), np.uint32), "n_unique": capi.PinnedArray((FRAMES,), np.uint32),
-            "planes": capi.PinnedArray((FRAMES, 6, pbh, pbw), np.uint8)}
-    out = {k: v.array for k, v in pins.items()}
-    h2d_bytes = frames.nbytes
-    d2h_bytes = sum(a.nbytes for a in out.values())
+    def measure(w, h, n_frames, first_frame, sa, thr, kind="clean", steps=args.steps, warmup=args.warmup,
+                want_stream=True, want_parity=False, sampler=None):
+        """One workload through the three timed paths.  Returns a dict of raw results (this rank)."""
+        nb = (w // 4) * (h // 4)
+        pbw, pbh = (w // 4 + 63) // 64 * 64, (h // 4 + 63) // 64 * 64
+        pin_frames = capi.PinnedArray((n_frames, h, w, 3), np.uint8)
+        gen_frames(pin_frames.array, w, h, first_frame, kind)
+        frames = pin_frames.array
+        pins = {"blocks": capi.PinnedArray((n_frames, nb), np.uint64), "motion": capi.PinnedArray((n_frames, 2 * nb), np.uint8),
+                "unique": capi.PinnedArray((n_frames, nb), np.uint32), "n_unique": capi.PinnedArray((n_frames,), np.uint32),
+                "planes": capi.PinnedArray((n_frames, 6, pbh, pbw), np.uint8)}
+        out = {k: v.array for k, v in pins.items()}
+        ctx.seq_reserve(w, h, n_frames)
+        ctx.seq_upload(frames)
+        ctx.sync()
+        r = {"frames": frames, "out": out, "pins": (pin_frames, pins), "nb": nb, "pixels": n_frames * w * h}
+        # ---- device-resident: inputs in HBM when the timed region starts -----------------------
+        for _ in range(warmup):
+            ctx.seq_encode(0, n_frames, sa, thr, GOP)
+        ctx.sync()
+        barrier()
+        if sampler:
+            sampler.start()   # nvidia-smi clocks / throttle reasons DURING the timed regions (resident + end to end)
+        launches0 = ctx.launches
+        dev_ms, stage_ms = [], {k: 0.0 for k in ("fit", "inter", "intra", "compact", "planes")}
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.seq_encode(0, n_frames, sa, thr, GOP)
+            dev_ms.append(ctx.last_encode_ms("total"))   # synchronises on the step's end event
+            for k in stage_ms:
+                stage_ms[k] += ctx.last_encode_ms(k) / steps
+        barrier()
+        r["wall_ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+        r["launches"] = ctx.launches - launches0
+        r["step_ms"] = max_over_ranks(float(np.mean(dev_ms)))
+        r["stage_ms"] = stage_ms
+        r["work"] = ctx.last_work_count()
+        # ---- end to end: host (pinned) frames in, host results out -------------------------------
+        e2e = lambda: ctx.encode_sequence(frames, sa, thr, GOP, out=out)   # noqa: E731  (returns after the D2H copies)
+        for _ in range(min(warmup, 3)):
+            e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e()
+        barrier()
+        r["e2e_ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+        if sampler:
+            r["clocks"] = sampler.stop()
+        r["h2d_bytes"] = int(frames.nbytes)
+        # blocks, motion, planes are copied whole; of `unique` only the n_unique words of each frame travel
+        r["d2h_bytes"] = int(out["blocks"].nbytes + out["motion"].nbytes + out["planes"].nbytes + out["n_unique"].nbytes +
+                             4 * int(out["n_unique"].sum()))
+        r["n_unique_sum"] = int(out["n_unique"].sum())
+        if want_parity:
+            r["parity"] = parity_record(out, first_frame, "the timed end-to-end step", w, h, sa, thr)
+        # ---- end to end incl. the host arithmetic coder (stream bytes out), overlapped with the GPU ----
+        if want_stream:
+            stream_buf = np.empty(frames.nbytes // 4 + (1 << 20), dtype=np.uint8)   # the caller's output buffer, reused
+            for _ in range(2):
+                r["stream_bytes"] = len(capi.encode_stream(ctx, frames, sa, thr, GOP, host_threads, out=stream_buf)[0])
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                capi.encode_stream(ctx, frames, sa, thr, GOP, host_threads, out=stream_buf)
+            barrier()
+            r["stream_ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / steps)
+        return r
 
-    ctx.seq_reserve(W, H, FRAMES)
-    ctx.seq_upload(frames)
-    ctx.sync()
+    def release(r):
+        pf, pins = r.pop("pins")
+        r.pop("frames", None); r.pop("out", None)
+        pf.free()
+        for v in pins.values():
+            v.free()
 
-    def resident_step():
-        ctx.seq_encode(0, FRAMES, SA, THR, GOP)
-
-    def e2e_step():
-        ctx.encode_sequence(frames, SA, THR, GOP, out=out)
-
-    # ---- device-resident value ------------------------------------------------------------
-    for _ in range(args.warmup):
-        resident_step()
-    ctx.sync()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    launches0 = ctx.launches
-    dev_ms, stage_ms = [], {k: 0.0 for k in ("fit", "inter", "intra", "compact", "planes")}
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        resident_step()
-        dev_ms.append(ctx.last_encode_ms("total"))   # synchronises on the step's end event
-        for k in stage_ms:
-            stage_ms[k] += ctx.last_encode_ms(k)
-    barrier()
-    wall_s = time.perf_counter() - t0
-    launches = ctx.launches - launches0
-    n_inter, n_intra = ctx.last_candidate_count()
-    step_ms = max_over_ranks(float(np.mean(dev_ms)))
-    wall_ms = max_over_ranks(wall_s * 1e3 / args.steps)
-
-    # ---- end to end (host buffers) ----------------------------------------------------------
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()                                    # returns after the D2H copies completed
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
-    clocks = sampler.stop()
-    checksum = int(out["n_unique"].sum())
-
-    # ---- end to end incl. the host arithmetic coder (stream bytes out), overlapped with the GPU ----
-    cores = os.cpu_count() or 1
-    host_threads = max(1, cores // max(world, 1))      # the ranks of one box share its cores
-    stream_bytes = 0
-    stream_buf = np.empty(frames.nbytes // 4 + (1 << 20), dtype=np.uint8)   # the caller's output buffer, reused
-    for _ in range(2):
-        stream_bytes = len(capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads, out=stream_buf)[0])
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads, out=stream_buf)
-    barrier()
-    stream_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    # ============================ the headline workload ==========================================
+    m = measure(W, H, FRAMES, FRAMES * rank, SA, THR, want_parity=(rank == 0), sampler=ClockSampler(local_rank))
+    clocks = m["clocks"]
+    frames, out, nb = m["frames"], m["out"], m["nb"]
 
     # ---- decoder side (SURVEY.md 8f-2): the stream just written back to DXT1 blocks ----------------
     stream = capi.encode_stream(ctx, frames, SA, THR, GOP, host_threads)[0]
@@ -389,87 +457,125 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     # ---- kernel attribution pass: one GOP lane, so that kernels do not overlap and the CUDA events
     # around each launch measure that kernel alone (in the timed region above, kernels of different
     # lanes share the GPU and their event intervals include each other's time) ---------------------
+    ctx.seq_upload(frames)
     ctx.set_schedule(1, 0, 0)
     for _ in range(2):
-        resident_step()
+        ctx.seq_encode(0, FRAMES, SA, THR, GOP)
     ctx.sync()
-    serial_ms, serial_total = {k: 0.0 for k in stage_ms}, 0.0
+    serial_ms, serial_total = {k: 0.0 for k in m["stage_ms"]}, 0.0
     for _ in range(args.steps):
-        resident_step()
+        ctx.seq_encode(0, FRAMES, SA, THR, GOP)
         serial_total += ctx.last_encode_ms("total") / args.steps
         for k in serial_ms:
             serial_ms[k] += ctx.last_encode_ms(k) / args.steps
     ctx.set_schedule(0, 0, 0)
+    dec_pin.free()
+    release(m)
+
+    # ============================ other content / other geometry ====================================
+    legs = {}
+    if not args.no_extra_legs and args.workload == "1080p60":
+        def leg(w, h, n_frames, first, sa, thr, kind, stream, parity=False):
+            x = measure(w, h, n_frames, first, sa, thr, kind, steps=max(2, args.steps // 2), warmup=3, want_stream=stream,
+                        want_parity=parity and rank == 0)
+            pix = x["pixels"] * world
+            o = {"workload": f"{w}x{h} synthetic{' + noise(+-24)' if kind == 'noisy' else ''} x{n_frames} frames/GPU, "
+                             f"search_area={sa}, err_threshold={thr}, gop={GOP}",
+                 "value": pix / (x["step_ms"] * 1e-3) / 1e6, "ms_per_step": x["step_ms"],
+                 "e2e": pix / (x["e2e_ms"] * 1e-3) / 1e6, "unit": UNIT, "n_unique": x["n_unique_sum"],
+                 "distinct_words_per_inter_tile": x["work"]["inter_evals"] / max(1, 32 * x["work"]["inter_tiles"])}
+            if stream:
+                o["e2e_stream"] = pix / (x["stream_ms"] * 1e-3) / 1e6
+            if "parity" in x:
+                o["parity"] = x["parity"]
+            release(x)
+            return o
+        # word-diverse content: the de-duplicating kernels live on word re-use
+        legs["robustness"] = {
+            "noisy_thr50": leg(W, H, GOP, 0, SA, THR, "noisy", False),
+            "clean_thr0": leg(W, H, GOP, 0, SA, 0, "clean", False),
+            "note": "one GOP of 15 frames each; same kernels, content / threshold that keep the frames' own ~distinct index words",
+        }
+        # BASELINE configs[2] geometry: 4K, host entropy coding overlapped (4 GOPs per GPU)
+        legs["4k"] = leg(3840, 2160, 4 * GOP, 4 * GOP * rank, SA, THR, "clean", True, parity=True)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pixels_total = FRAMES * W * H * world
-    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
-    for k in stage_ms:
-        stage_ms[k] /= args.steps
+    pixels_total = m["pixels"] * world
+    step_ms, e2e_ms, stream_ms, stage_ms = m["step_ms"], m["e2e_ms"], m["stream_ms"], m["stage_ms"]
     dominant = max(("inter", "intra"), key=lambda k: serial_ms[k])
-    n_cand = n_inter if dominant == "inter" else n_intra
+    work = m["work"]
+    n_gops = FRAMES // GOP
     k_launches = (GOP - 1) if dominant == "inter" else GOP   # one launch covers frame k of every GOP
     k_ms = serial_ms[dominant]
-    achieved = n_cand * ALGO_SLOTS_PER_CANDIDATE / (k_ms * 1e-3) / 1e12
-    clk = sm_max_mhz
-    peak = SM_COUNT * SCHEDULERS * LANES * clk * 1e6 / 1e12
-    n_gops = FRAMES // GOP
+    evals, scanned = work[f"{dominant}_evals"], work[f"{dominant}_scanned"]
+    nominal = work[f"nominal_{dominant}"]
+    slots = evals * ALGO_SLOTS_PER_CANDIDATE + scanned * SCAN_SLOTS_PER_POSITION
+    achieved = slots / (k_ms * 1e-3) / 1e12
     # algorithmic HBM bytes of the search kernels: 72 B/block in + 20 B per
     # distinct candidate + ~14 B/block out
     frames_k = n_gops * ((GOP - 1) if dominant == "inter" else GOP)
     algo_bytes = frames_k * nb * (72 + 20 + 14)
-    # DRAM bytes per launch from the committed ncu --set full capture (per frame x frames per launch)
-    ev = ncu_evidence(dominant)
-    if ev:   # keep the bench line readable: the counters DESIGN.md cites, not the whole capture
-        keep = ("kernel", "frames_per_launch", "source", "gpu__time_duration.sum", "dram_bytes_per_frame",
-                "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-                "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-                "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
-        ev = {k: ev[k] for k in keep if k in ev}
+    ev, stale = ncu_evidence(dominant)
     traffic = ev["dram_bytes_per_frame"] * n_gops if ev and "dram_bytes_per_frame" in ev else None
     roofline = {
         "kernel": "k_inter_search_tiled" if dominant == "inter" else "k_intra_wavefront_tiled",
         "measured": "CUDA events around each launch in a one-lane pass of the same workload (kernels serialised)",
         "share_of_step": k_ms / serial_total, "serial_step_ms": serial_total, "serial_stage_ms": serial_ms,
-        "bound": "issue", "achieved": achieved, "peak": peak, "unit": "Tslot/s", "frac": achieved / peak,
-        "peak_source": f"148 SMs x 4 schedulers x 32 lanes x {clk:.0f} MHz (clocks.max.sm, {peak_src}); issue-slot roofline per SURVEY.md 8(d)",
-        "units_per_launch": n_cand / max(k_launches, 1), "launches_per_step": k_launches,
+        "bound": "issue", "achieved": achieved, "peak": issue_peak, "unit": "Tslot/s", "frac": achieved / issue_peak,
+        "peak_source": f"148 SMs x 4 schedulers x 32 lanes x {sm_max_mhz:.0f} MHz (clocks.max.sm, {peak_src}); issue-slot roofline per SURVEY.md 8(d)",
+        "work": "EXECUTED work, counted by the kernel (one atomicAdd per tile): (index word, target block) evaluations x "
+                f"{ALGO_SLOTS_PER_CANDIDATE} slots (SURVEY.md 8d) + window positions scanned x {SCAN_SLOTS_PER_POSITION} slots",
+        "evaluations_per_step": evals, "positions_scanned_per_step": scanned,
+        "units_per_launch": evals / max(k_launches, 1), "launches_per_step": k_launches,
         "avg_launch_ms": k_ms / max(k_launches, 1), "algo_slots_per_unit": ALGO_SLOTS_PER_CANDIDATE,
+        "scan_slots_per_position": SCAN_SLOTS_PER_POSITION,
+        "distinct_words_per_tile": work["inter_evals"] / max(1, 32 * work["inter_tiles"]),
+        # what the same time would score if every window position were evaluated, as the reference does
+        # and as SURVEY.md 8(d) counts: the de-duplication's gain, not a roofline fraction
+        "nominal_candidates_per_step": nominal,
+        "dedup_speedup": nominal * ALGO_SLOTS_PER_CANDIDATE / max(slots, 1),
         "traffic": traffic,
         "hbm": {"achieved": algo_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src},
-        "overlapped_stage_ms_per_step": stage_ms, "candidates_per_step": {"inter": n_inter, "intra": n_intra},
+        "overlapped_stage_ms_per_step": stage_ms,
+        "candidates_per_step": {"inter": work["nominal_inter"], "intra": work["nominal_intra"]},
         "ncu": ev,
     }
+    if stale:
+        roofline["ncu_stale"] = stale
     if ev and "smsp__issue_active.avg.pct_of_peak_sustained_active" in ev:
-        # issue slots the kernel actually EXECUTES per available slot (ncu); `frac` above counts the
-        # algorithm's nominal slots, most of which the de-duplicating kernel never issues
-        roofline["frac_executed"] = ev["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100.0
+        roofline["issue_active_ncu"] = ev["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100.0
     if clocks.get("sm_mhz"):
         roofline["frac_at_sampled_clock"] = achieved / (SM_COUNT * SCHEDULERS * LANES * clocks["sm_mhz"] * 1e6 / 1e12)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_baseline(1)
+        cpu, cpu_times = cpu_baseline(3)
+        cpu["steps"] = len(cpu_times)
+        cpu["step_s"] = [round(t, 3) for t in cpu_times]
 
+    cfg = base_config(world)
     line = {
         "metric": METRIC, "value": pixels_total / (step_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": SCALING, "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES, "sharding": f"gop-sharded x{world}, no collective",
-                   "l2": f"inputs ({frames.nbytes // 1000000} MB RGB per step) exceed the 126 MB L2; no explicit flush"},
-        "wall_ms_per_step": wall_ms,
+        "config": cfg,
+        "wall_ms_per_step": m["wall_ms"],
         "e2e": {"value": pixels_total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+                "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
+                "h2d_gb_per_s_per_rank": m["h2d_bytes"] / (e2e_ms * 1e-3) / 1e9,
+                "d2h_gb_per_s_per_rank": m["d2h_bytes"] / (e2e_ms * 1e-3) / 1e9, "numa": numa},
         "e2e_stream": {"value": pixels_total / (stream_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": stream_ms,
-                       "host_threads": host_threads, "stream_bytes": stream_bytes,
+                       "host_threads": host_threads, "stream_bytes": m["stream_bytes"],
                        "note": "e2e + the host arithmetic coder and stream assembly (mptc_encode_stream), coder overlapped with the GPU"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "checksum_n_unique": checksum,
+        "parity": m.get("parity"),
+        "gpu_launches": int(m["launches"]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "checksum_n_unique": m["n_unique_sum"],
+        "legs": legs,
         "decode": {
             "note": "decoder side (SURVEY.md 8f-2), same frames: device = symbols resident in HBM -> DXT1 blocks + RGB "
                     "pictures (CUDA events); stream = mptc_decode_stream from the stream bytes to host DXT1 blocks, host "
@@ -513,6 +619,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mptc_b200", choices=["mptc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the robustness and 4K legs of the default line")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the ranks to their GPU's NUMA node (N > 1)")
     ap.add_argument("--workload", default="1080p60", choices=sorted(WORKLOADS),
                     help="1080p60 = BASELINE.json configs[1] (default, the headline); 4k120 = configs[2]; "
                          "4k600 = configs[4] (600 frames in all, GOP-sharded over the GPUs: strong scaling)")

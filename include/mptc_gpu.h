@@ -168,6 +168,14 @@ void mptc_gpu_host_free(void *p);
  * the frame (the algorithmic unit count, independent of any early exit). */
 int mptc_gpu_last_candidate_count(mptc_gpu_ctx *ctx, uint64_t *inter, uint64_t *intra);
 
+/* Work the search kernels actually EXECUTED in the last encode call (they evaluate each distinct
+ * index word of a tile / group once instead of every window position, dxt_image.cpp:731-770):
+ * counters[0..1] = the nominal candidate positions above (inter, intra), [2] = (index word, target
+ * block) evaluations of the inter search, [3] = window positions its winner scan visited,
+ * [4], [5] = the same for the intra wavefront, [6] = inter tiles, [7] = intra groups.  n = how many
+ * to copy (<= 8).  This is what bench.py's roofline counts. */
+int mptc_gpu_last_work_count(mptc_gpu_ctx *ctx, uint64_t *counters, int n);
+
 #ifdef __cplusplus
 }
 #endif

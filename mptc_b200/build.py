@@ -24,6 +24,24 @@ NVCC_FLAGS = [
 ]
 
 
+# Sources that determine each search kernel's machine code: profiles/ncu_counters.json is stamped with
+# their hash (profiles/ncu_summary.py --json) and bench.py drops the ncu block when it no longer matches.
+KERNEL_SOURCES = {
+    "inter": ["mptc_inter.cu", "mptc_uniform_eval.cuh", "mptc_device.cuh", "mptc_kernels.h"],
+    "intra": ["mptc_intra.cu", "mptc_uniform_eval.cuh", "mptc_device.cuh", "mptc_kernels.h"],
+}
+
+
+def kernel_source_sha(stage: str) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES[stage]:
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):

@@ -23,7 +23,7 @@ EXPORTS = [
     "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count", "mptc_gpu_set_schedule",
     "mptc_gpu_encode_sequence_async", "mptc_gpu_wait_frame", "mptc_gpu_wait",
     "mptc_gpu_decode_sequence", "mptc_gpu_seq_decode_upload", "mptc_gpu_seq_decode",
-    "mptc_gpu_seq_decode_download", "mptc_gpu_last_decode_ms",
+    "mptc_gpu_seq_decode_download", "mptc_gpu_last_decode_ms", "mptc_gpu_last_work_count",
 ]
 DECODE_STAGES = {"total": 0, "words": 1, "planes": 2, "rgb": 3}
 
@@ -77,6 +77,7 @@ def load():
     L.mptc_gpu_host_free.argtypes = [vp]
     L.mptc_gpu_last_candidate_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.mptc_gpu_set_schedule.argtypes = [vp, ci, ci, ci]
+    L.mptc_gpu_last_work_count.argtypes = [vp, C.POINTER(C.c_uint64), ci]
     L.mptc_gpu_decode_sequence.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, ci, ci, ci, ci, ci, vp, vp]
     L.mptc_gpu_seq_decode_upload.argtypes = [vp, ci, ci, vp, vp, vp, C.c_size_t, vp]
     L.mptc_gpu_seq_decode.argtypes = [vp, ci, ci, ci, ci, ci]
@@ -88,6 +89,37 @@ def load():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def bind_to_gpu_numa_node(device: int) -> dict:
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the
+    page-locked frame / result buffers it allocates next and its arithmetic-coder threads are local
+    to the GPU's PCIe root: with eight ranks on a two-socket box, half of the H2D/D2H traffic otherwise
+    crosses the socket interconnect.  Returns what was done (for the bench line); never fails."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+    except Exception as e:   # containers without sysfs, single-node boxes, ...
+        info["error"] = str(e)[:80]
+    return info
 
 
 class PinnedArray:
@@ -230,6 +262,14 @@ class Context:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._check(self._L.mptc_gpu_last_candidate_count(self._p, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def last_work_count(self) -> dict:
+        """Work the search kernels executed in the last encode call (mptc_gpu_last_work_count)."""
+        a = (C.c_uint64 * 8)()
+        self._check(self._L.mptc_gpu_last_work_count(self._p, a, 8))
+        keys = ("nominal_inter", "nominal_intra", "inter_evals", "inter_scanned", "intra_evals", "intra_scanned",
+                "inter_tiles", "intra_groups")
+        return {k: int(x) for k, x in zip(keys, a)}
 
     def wait_frame(self, frame: int):
         """Blocks until the results of `frame` of the last (async) encode are in the host buffers."""

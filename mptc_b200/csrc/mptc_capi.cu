@@ -166,7 +166,7 @@ SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
   SeqView v;
   v.rgb = c->d_rgb; v.init_blocks = c->d_init; v.final_blocks = c->d_final; v.motion = c->d_motion;
   v.flags = c->d_flags; v.row_todo = c->d_row_todo; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.chunk_counts = c->d_chunks; v.planes = c->d_planes;
-  v.progress = c->d_progress; v.frame_bytes = c->frame_bytes;
+  v.progress = c->d_progress; v.work = c->d_cand; v.frame_bytes = c->frame_bytes;
   v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb;
   v.first = first; v.count = count; v.gop = gop;
   return v;
@@ -229,8 +229,21 @@ struct HostIO {
   uint8_t *motion = nullptr;
   uint32_t *unique = nullptr, *n_unique = nullptr;
   uint8_t *planes = nullptr;
+  // device-visible aliases of unique / n_unique when the caller's buffers are page-locked: K4 then
+  // writes the n_unique words of a frame straight to the host instead of a D2H copy of nb words
+  uint32_t *unique_mapped = nullptr, *n_unique_mapped = nullptr;
   bool any_out() const { return blocks || motion || unique || n_unique || planes; }
 };
+
+// The device-visible address of a page-locked host buffer (cudaHostAlloc / cudaHostRegister), or null
+// for pageable memory.
+template <typename T>
+T *mapped_alias(T *host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return a.type == cudaMemoryTypeHost ? static_cast<T *>(a.devicePointer) : nullptr;
+}
 
 // Copies `rows` chunks of `width` bytes that lie `pitch` bytes apart in both src and dst (frame k of
 // consecutive GOPs).  One 2D copy when the pitch allows it, otherwise one copy per chunk.
@@ -312,7 +325,8 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
   CU(c, cudaStreamWaitEvent(t, L.ev_k[k], 0));
   {
     StageEvent &e = stage_begin(L, 4, t);
-    launch_compact_unique(v, sa, c->d_cand, fk, gop, nf, t);
+    launch_compact_unique(v, sa, c->d_cand, fk, gop, nf, t, io ? io->unique_mapped : nullptr,
+                          io ? io->n_unique_mapped : nullptr, call_first);
     stage_end(c, e, t, 2);
   }
   if (planes) {
@@ -328,8 +342,8 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
     CU(c, cudaStreamWaitEvent(d, L.ev_side[k], 0));
     if (io->blocks) CU(c, copy_strided(io->blocks + o * nb, c->d_final + f * nb, nb * 8, g * nb * 8, nf, D2H, d));
     if (io->motion) CU(c, copy_strided(io->motion + o * nb * 2, c->d_motion + f * nb * 2, nb * 2, g * nb * 2, nf, D2H, d));
-    if (io->unique) CU(c, copy_strided(io->unique + o * nb, c->d_unique + f * nb, nb * 4, g * nb * 4, nf, D2H, d));
-    if (io->n_unique) CU(c, copy_strided(io->n_unique + o, c->d_nunique + f, 4, g * 4, nf, D2H, d));
+    if (io->unique && !io->unique_mapped) CU(c, copy_strided(io->unique + o * nb, c->d_unique + f * nb, nb * 4, g * nb * 4, nf, D2H, d));
+    if (io->n_unique && !io->n_unique_mapped) CU(c, copy_strided(io->n_unique + o, c->d_nunique + f, 4, g * 4, nf, D2H, d));
     if (io->planes) CU(c, copy_strided(io->planes + o * c->plane_bytes, c->d_planes + f * c->plane_bytes, c->plane_bytes,
                                        g * c->plane_bytes, nf, D2H, d));
     CU(c, cudaEventRecord(L.ev_down[k], d));
@@ -355,7 +369,7 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
   const int rows_intra = c->wave_rows_intra > 0 ? c->wave_rows_intra : (nl > 1 ? 32 : 0);
   const int rows_inter = c->wave_rows_inter;
   cudaStream_t s0 = c->s_compute;
-  CU(c, cudaMemsetAsync(c->d_cand, 0, 2 * sizeof(unsigned long long), s0));
+  CU(c, cudaMemsetAsync(c->d_cand, 0, kWorkCounters * sizeof(unsigned long long), s0));
   CU(c, cudaEventRecord(c->ev_begin, s0));
   if (io && io->frames) CU(c, cudaStreamWaitEvent(c->s_h2d, c->ev_begin, 0));
   for (int i = 0; i < nl; ++i) {
@@ -423,7 +437,7 @@ int mptc_gpu_create(int device, mptc_gpu_ctx **out) {
             cudaEventCreate(&c->ev_begin) == cudaSuccess && cudaEventCreate(&c->ev_end) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_encoded, cudaEventDisableTiming) == cudaSuccess &&
-            cudaMalloc(&c->d_cand, 2 * sizeof(unsigned long long)) == cudaSuccess;
+            cudaMalloc(&c->d_cand, kWorkCounters * sizeof(unsigned long long)) == cudaSuccess;
   if (ok) {
     uint8_t t5[512], t6[512];
     build_match_table(t5, 5);
@@ -586,6 +600,17 @@ int mptc_gpu_last_candidate_count(mptc_gpu_ctx *c, uint64_t *inter, uint64_t *in
   return MPTC_OK;
 }
 
+int mptc_gpu_last_work_count(mptc_gpu_ctx *c, uint64_t *counters, int n) {
+  if (!c || !counters || n < 1) return MPTC_E_ARG;
+  if (!c->encoded) return fail(c, MPTC_E_STATE, "no encode has run");
+  CU(c, cudaSetDevice(c->device));
+  unsigned long long h[kWorkCounters];
+  CU(c, cudaStreamSynchronize(c->s_compute));
+  CU(c, cudaMemcpy(h, c->d_cand, sizeof h, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) counters[i] = i < kWorkCounters ? h[i] : 0;
+  return MPTC_OK;
+}
+
 int mptc_gpu_dxt1_fit(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, uint64_t *blocks_out) {
   if (!c || !rgb || !blocks_out) return MPTC_E_ARG;
   if (int r = mptc_gpu_seq_reserve(c, w, h, 2)) return r;
@@ -655,6 +680,11 @@ int mptc_gpu_encode_sequence_async(mptc_gpu_ctx *c, const uint8_t *frames, int n
   if (int r = mptc_gpu_seq_reserve(c, w, h, n_frames)) return r;
   HostIO io;
   io.frames = frames; io.blocks = blocks; io.motion = motion; io.unique = unique; io.n_unique = n_unique; io.planes = planes;
+  if (env_int("MPTC_UNIQUE_COPY", 0) == 0) {   // 1 = always D2H-copy the nb-word slots (A/B measurements)
+    io.unique_mapped = mapped_alias(unique);
+    io.n_unique_mapped = mapped_alias(n_unique);
+    if (!io.unique_mapped || !io.n_unique_mapped) io.unique_mapped = io.n_unique_mapped = nullptr;
+  }
   return run_encode(c, 0, n_frames, p->gop, p->search_area, p->err_threshold, true, 0, planes != nullptr, &io);
 }
 

@@ -220,6 +220,15 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     __syncthreads();
   }
 
+  // executed work (bench.py's roofline): every distinct word once per valid target, every window
+  // position of every valid target once per chunk pass
+  if (tid == 0) {
+    const unsigned long long nt = (unsigned long long)(min(kTileX, v.bw - tx0) * min(kTileY, v.bh - ty0));
+    atomicAdd(v.work + kWorkInterEvals, nt * (unsigned long long)U);
+    atomicAdd(v.work + kWorkInterScanned, nt * (unsigned long long)(W * W) * (unsigned long long)((U + kChunk - 1) / kChunk));
+    atomicAdd(v.work + kWorkInterTiles, 1ull);
+  }
+
   // ---- phase 6: resolve and apply ------------------------------------------------------------
 #pragma unroll
   for (int q = 0; q < kTileX * kTileY / kWarps; ++q) {

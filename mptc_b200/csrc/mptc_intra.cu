@@ -321,6 +321,7 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           }
           winner_block_reduce<kWarps>(s, s_red);
           if (tid == 0) {
+            atomicAdd(v.work + kWorkIntraEvals, (unsigned long long)(W * W));   // every window position evaluated
             int row, col;
             const int min_err = winner_resolve(s, W, row, col);
             if (min_err <= thr) {
@@ -383,6 +384,13 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
         }
         __syncthreads();
         const int UA = s_count;
+        if (tid == 0) {   // executed work: all distinct words + the pushed final words, once per block of the group
+          const unsigned long long nn = (unsigned long long)(x_end - x0);
+          atomicAdd(v.work + kWorkIntraEvals, ((unsigned long long)UA + (unsigned long long)min(sa, x0) + nn) * nn);
+          atomicAdd(v.work + kWorkIntraScanned, (unsigned long long)__popc(todo_mask) * (unsigned long long)(min(R - 1, by) * W) *
+                                                   (unsigned long long)((UA + kMaxWords - 1) / kMaxWords));
+          atomicAdd(v.work + kWorkIntraGroups, 1ull);
+        }
         for (int p = tid; p < NP; p += kThreads) {
           const uint16_t slot = sm.pos_uid[p];
           if (slot != kNone) sm.pos_uid[p] = sm.slot_uid[slot];   // kNone = 0xFFFF is outside every chunk
@@ -761,6 +769,11 @@ k_intra_wavefront_tiled(SeqView v, int k_in_gop, int n_gops, int sa, int thr, in
           }
         }
         PHASE_MARK(7);   // in-row decisions
+        if (lane == 0) {   // executed work: every word of the table once per block of the group; rows above + own row scanned
+          atomicAdd(v.work + kWorkIntraEvals, (unsigned long long)U * (unsigned long long)n);
+          atomicAdd(v.work + kWorkIntraScanned, (unsigned long long)__popc(todo_mask) * (unsigned long long)(min(R - 1, by) * W + sa));
+          atomicAdd(v.work + kWorkIntraGroups, 1ull);
+        }
         // ---- endpoints + motion for the decided blocks (nobody waits on these inside the kernel) ------
         if (todo && lane < g_end) {
           const size_t b = (size_t)by * v.bw + gx;

@@ -408,8 +408,13 @@ k_compact_count(SeqView v, int sa, unsigned long long *__restrict__ cand_counts,
   }
 }
 
+// host_unique / host_n_unique (optional): the caller's page-locked result buffers, mapped into the
+// device's address space.  The unique words then go straight to the host from here -- n_unique words
+// per frame over PCIe instead of a copy of the whole nb-word slot (a 1080p frame has ~100 unique
+// blocks of 129 600).  host_first = the sequence frame that host frame 0 corresponds to.
 __global__ void __launch_bounds__(kCompactChunk)
-k_compact_unique(SeqView v, int f0, int fstride) {
+k_compact_unique(SeqView v, int f0, int fstride, uint32_t *__restrict__ host_unique, uint32_t *__restrict__ host_n_unique,
+                 int host_first) {
   __shared__ int warp_cnt[kCompactChunk / 32];
   __shared__ int chunk_base;
   const int f = f0 + blockIdx.y * fstride;
@@ -431,8 +436,15 @@ k_compact_unique(SeqView v, int f0, int fstride) {
     if (k < wid) before += c;
     total += c;
   }
-  if (uniq) v.unique[(size_t)f * v.nb + before] = (uint32_t)(v.final_blocks[(size_t)f * v.nb + b] >> 32);
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) v.n_unique[f] = (uint32_t)total;
+  if (uniq) {
+    const uint32_t word = (uint32_t)(v.final_blocks[(size_t)f * v.nb + b] >> 32);
+    v.unique[(size_t)f * v.nb + before] = word;
+    if (host_unique) host_unique[(size_t)(f - host_first) * v.nb + before] = word;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    v.n_unique[f] = (uint32_t)total;
+    if (host_n_unique) host_n_unique[f - host_first] = (uint32_t)total;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -538,10 +550,10 @@ void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, 
 }
 
 void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, int f0, int fstride, int nf,
-                           cudaStream_t s) {
+                           cudaStream_t s, uint32_t *host_unique, uint32_t *host_n_unique, int host_first) {
   dim3 grid((v.nb + kCompactChunk - 1) / kCompactChunk, nf);
   k_compact_count<<<grid, kCompactChunk, 0, s>>>(v, sa, cand_counts, f0, fstride);
-  k_compact_unique<<<grid, kCompactChunk, 0, s>>>(v, f0, fstride);
+  k_compact_unique<<<grid, kCompactChunk, 0, s>>>(v, f0, fstride, host_unique, host_n_unique, host_first);
 }
 
 std::mutex &launch_cfg_mutex() {

@@ -26,11 +26,19 @@ struct SeqView {
   uint32_t *chunk_counts;  // [F][ceil(nb/1024)]  unique blocks per chunk (K4)
   uint8_t *planes;         // [F][6][pbh][pbw]
   int *progress;           // [F][bh]   wavefront progress counters
+  unsigned long long *work; // executed-work counters of the search kernels (kWork*), one atomicAdd per tile / group
   size_t frame_bytes;
   int w, h, bw, bh, nb;
   int first, count;        // frame range of this encode call
   int gop;
 };
+
+// Executed work of the search kernels since the start of the last encode call (bench.py's roofline):
+// (index word, target block) evaluations actually run and window positions actually scanned -- the
+// de-duplicating kernels evaluate each distinct word of a tile once, so these are far below the
+// nominal candidate positions of SURVEY.md 8(d).
+enum { kWorkNominalInter = 0, kWorkNominalIntra = 1, kWorkInterEvals = 2, kWorkInterScanned = 3,
+       kWorkIntraEvals = 4, kWorkIntraScanned = 5, kWorkInterTiles = 6, kWorkIntraGroups = 7, kWorkCounters = 8 };
 
 // Inter frames: K3s (mptc_sparse.cu) handles frames with at most max_items leftover blocks and
 // tells the row wavefront through n_unique[f] (0xFFFFFFFF = not handled, take the frame).
@@ -50,8 +58,11 @@ bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int s
 // frame busy, and idle CTAs would block the SMs for kernels of other lanes.
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                             int max_ctas, int grid_cap, cudaStream_t s);
+// host_unique / host_n_unique: device-visible addresses of page-locked host result buffers (or null):
+// the unique words are then also written straight to the host (frame f -> host frame f - host_first).
 void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_counts, int f0, int fstride, int nf,
-                           cudaStream_t s);
+                           cudaStream_t s, uint32_t *host_unique = nullptr, uint32_t *host_n_unique = nullptr,
+                           int host_first = 0);
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s);
 int intra_wavefront_max_ctas(int device);
 

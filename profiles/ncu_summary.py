@@ -3,8 +3,12 @@
 usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/rNN_kernel.txt]"""
 import csv
 import io
+import os
 import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mptc_b200.build import kernel_source_sha  # noqa: E402  (stamps the capture with the kernel sources' hash)
 
 KEYS = [
     "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "launch__grid_size", "launch__block_size",
@@ -63,7 +67,8 @@ def to_json(rep, frames_per_launch, source):
         t = float(d["gpu__time_duration.sum"][1].replace(",", ""))
         if stage in best and best[stage][0] >= t:
             continue
-        o = {"kernel": r[name_col].split("(")[0], "frames_per_launch": frames_per_launch, "source": source}
+        o = {"kernel": r[name_col].split("(")[0], "frames_per_launch": frames_per_launch, "source": source,
+             "source_sha16": kernel_source_sha(stage)}
         for k in JSON_KEYS:
             if k in d:
                 u, v = d[k]

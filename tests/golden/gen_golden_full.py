@@ -61,7 +61,7 @@ def run_gop(job):
         fin, mo, un = fr.blocks(), fr.motion(), fr.unique()
         out.append({"hashes": [sha(init), sha(fin), sha(mo), sha(un)], "n_unique": un.size,
                     "rows_final": row_crcs(fin, bh), "rows_motion": row_crcs(mo, bh),
-                    "n_inter": int(np.count_nonzero((mo[0::2] & 0x80) & (mo[0::2] != 255)))})
+                    "n_inter": int(np.count_nonzero(((mo[0::2] & 0x80) != 0) & (mo[0::2] != 255)))})
         prev = fr
         print(f"  frame {f0 + k} of {w}x{h}: {time.time() - t0:.1f} s, {un.size} unique", flush=True)
     return f0, out
@@ -73,9 +73,14 @@ def run_case(name):
     with mp.get_context("spawn").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
         res = dict(pool.map(run_gop, jobs))
     frames = [fr for f0 in sorted(res) for fr in res[f0]]
+    from mptc_b200.synth import make_frame
+    h_in = hashlib.sha256()                      # the input the fixture belongs to
+    for f in range(n):
+        h_in.update(make_frame(w, h, f, seed).tobytes())
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
         params=np.array([w, h, n, seed, sa, thr, gop], dtype=np.int64),
+        frames_sha=np.array(h_in.hexdigest()),
         hashes=np.array([f["hashes"] for f in frames]),
         n_unique=np.array([f["n_unique"] for f in frames], dtype=np.uint32),
         n_inter=np.array([f["n_inter"] for f in frames], dtype=np.uint32),
