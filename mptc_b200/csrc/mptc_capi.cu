@@ -37,6 +37,8 @@ struct mptc_gpu_ctx {
   uint8_t *d_motion = nullptr, *d_flags = nullptr, *d_planes = nullptr, *d_row_todo = nullptr;
   uint32_t *d_unique = nullptr, *d_nunique = nullptr, *d_chunks = nullptr;
   int *d_progress = nullptr;
+  unsigned long long *d_wordflag = nullptr;
+  uint32_t epoch = 0;            // one per encode call: validity tag of the wavefront's hand-over entries
   unsigned long long *d_cand = nullptr;
   int max_wave_ctas = 0;
   bool encoded = false;
@@ -119,7 +121,8 @@ void build_match_table(uint8_t *table, int bits) {
 void free_seq(mptc_gpu_ctx *c) {
   cudaFree(c->d_rgb); cudaFree(c->d_init); cudaFree(c->d_final); cudaFree(c->d_motion);
   cudaFree(c->d_flags); cudaFree(c->d_planes); cudaFree(c->d_unique); cudaFree(c->d_nunique);
-  cudaFree(c->d_progress); cudaFree(c->d_row_todo); cudaFree(c->d_chunks);
+  cudaFree(c->d_progress); cudaFree(c->d_row_todo); cudaFree(c->d_chunks); cudaFree(c->d_wordflag);
+  c->d_wordflag = nullptr;
   c->d_chunks = nullptr;
   c->d_rgb = nullptr; c->d_init = c->d_final = nullptr; c->d_motion = c->d_flags = c->d_planes = nullptr;
   c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr; c->d_row_todo = nullptr;
@@ -166,7 +169,7 @@ SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
   SeqView v;
   v.rgb = c->d_rgb; v.init_blocks = c->d_init; v.final_blocks = c->d_final; v.motion = c->d_motion;
   v.flags = c->d_flags; v.row_todo = c->d_row_todo; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.chunk_counts = c->d_chunks; v.planes = c->d_planes;
-  v.progress = c->d_progress; v.work = c->d_cand; v.frame_bytes = c->frame_bytes;
+  v.progress = c->d_progress; v.wordflag = c->d_wordflag; v.epoch = c->epoch; v.work = c->d_cand; v.frame_bytes = c->frame_bytes;
   v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb;
   v.first = first; v.count = count; v.gop = gop;
   return v;
@@ -191,6 +194,11 @@ StageEvent &stage_begin(Lane &L, int stage, cudaStream_t st) {
 void stage_end(mptc_gpu_ctx *c, StageEvent &e, cudaStream_t st, int n_launches = 1) {
   cudaEventRecord(e.b, st);
   c->launches += n_launches;
+  static const bool debug_sync = getenv("MPTC_DEBUG_SYNC") != nullptr;   // debugging: which stage faults?
+  if (debug_sync) {
+    const cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) fprintf(stderr, "mptc: stage %d failed: %s\n", e.stage, cudaGetErrorString(err));
+  }
 }
 
 int check_params(mptc_gpu_ctx *c, int sa, int gop) {
@@ -369,6 +377,10 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
   const int rows_intra = c->wave_rows_intra > 0 ? c->wave_rows_intra : (nl > 1 ? 32 : 0);
   const int rows_inter = c->wave_rows_inter;
   cudaStream_t s0 = c->s_compute;
+  if (++c->epoch == 0) {   // wrapped: entries of 2^32 calls ago would look current
+    CU(c, cudaMemsetAsync(c->d_wordflag, 0, (size_t)c->cap_frames * c->nb * sizeof(unsigned long long), s0));
+    c->epoch = 1;
+  }
   CU(c, cudaMemsetAsync(c->d_cand, 0, kWorkCounters * sizeof(unsigned long long), s0));
   CU(c, cudaEventRecord(c->ev_begin, s0));
   if (io && io->frames) CU(c, cudaStreamWaitEvent(c->s_h2d, c->ev_begin, 0));
@@ -517,6 +529,9 @@ int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
   CU(c, cudaMalloc(&c->d_chunks, F * ((nb + 1023) / 1024) * 4));
   CU(c, cudaMalloc(&c->d_planes, F * c->plane_bytes));
   CU(c, cudaMalloc(&c->d_progress, F * c->bh * sizeof(int)));
+  CU(c, cudaMalloc(&c->d_wordflag, F * nb * sizeof(unsigned long long)));
+  CU(c, cudaMemset(c->d_wordflag, 0, F * nb * sizeof(unsigned long long)));   // epoch 0 is never used
+  c->epoch = 0;
   c->cap_frames = n_frames;
   c->h_uoff.resize(F);
   for (size_t f = 0; f < F; ++f) c->h_uoff[f] = (uint32_t)(f * nb);   // the encoder's layout

@@ -1,0 +1,1117 @@
+// mptc_intra_rows.cu -- K3, second generation: intra search (DXTImage::IntraSearch + the winner apply
+// of Reencode, codec/dxt_image.cpp:652-713, :912-955) as a row-staggered wavefront whose rows hand
+// their decisions over WORD BY WORD.
+//
+// Dependency: block (x, y) reads the FINAL index words of (x-sa..x-1, y) and of
+// (x-sa..x+sa-1, y-1..y-2sa+1).  One CTA walks one block row left to right (two CTAs per row on intra
+// frames, alternating groups), a group of 32 targets at a time (lane = target), exactly as the first
+// generation (mptc_intra.cu) did: de-duplicate the union window's words, evaluate every distinct word
+// once per target, scan the rows above with all warps.  What changed is how a row learns what the
+// rows next to it decided -- the 13.5 us a row used to trail the row above by were a fence, a progress
+// counter in global memory, a polled acquire load and a merge loop on the decider warp
+// (VERDICT r1 weak #3):
+//   * every decided index word is handed over through `wordflag[f][block] = {word, epoch}`, ONE 8-byte
+//     relaxed store that carries its own validity tag (the encode call's epoch): no fence, no counter,
+//     no publisher warp, and the consumer's single load returns readiness and data together;
+//   * the rows directly above (kNear of them) and the part of the own row that the partner CTA
+//     decides are followed by MERGER warps, one per row: each polls its row's entries, looks the new
+//     words up in the group's word table (adds and evaluates the rare word that is not there yet),
+//     folds their err_diff values into a per-target partial WinnerState and publishes that partial in
+//     shared memory as soon as a target's part of that row is complete;
+//   * the DECIDER warp (lane = target) therefore only does, per block: merge the finished partials of
+//     lane g, resolve, fetch the winner's word id, broadcast it, push its err_diff to the <= sa targets
+//     on the right, store the 8-byte entry.  WinnerState is an associative reduction (mptc_device.cuh),
+//     so the order in which partials arrive cannot change a result.
+// Rows are handed out in increasing order through a ticket, the CTAs of one row hold adjacent
+// tickets: a CTA only ever waits for CTAs whose tickets were taken before its own or for its
+// partner -- no deadlock for any grid size.
+#include "mptc_kernels.h"
+#include "mptc_uniform_eval.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace mptc {
+
+namespace {
+
+constexpr int kG = 32;                        // targets per group
+#ifndef MPTC_K3R_THREADS
+#define MPTC_K3R_THREADS 512
+#endif
+constexpr int kThreads = MPTC_K3R_THREADS, kWarps = kThreads / 32;
+constexpr int kCtasPerSm = kThreads <= 256 ? 2 : 1;
+// distinct words per group on the fast path (with two CTAs per SM the tables of both must fit the SM's
+// 228 KB of shared memory)
+constexpr int kMaxWords = kCtasPerSm == 2 ? 240 : 256;
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr uint16_t kNone = 0xFFFFu;           // window position without a word (outside the frame / not there yet)
+constexpr uint16_t kNotReady = 0xFFFEu;       // hash slot claimed, the word's table row still being computed
+constexpr uint16_t kOverflowUid = 0xFFFDu;    // hash slot claimed after the table was full
+#ifndef MPTC_K3R_NEAR
+#define MPTC_K3R_NEAR 2
+#endif
+constexpr int kNear = MPTC_K3R_NEAR;          // rows directly above that are followed word by word
+constexpr int kSparseTodo = 2;                // groups with this few targets take the direct path
+constexpr int kChunkedTodo = 6;               // word-diverse groups with at least this many targets take the chunked path
+constexpr int kNeedOwn = 0x7fff0000;          // "lane keeps its own initial word" in the decider's broadcast
+constexpr int kEvalWarp = kNear + 2;          // adds the decider's rare new words to the table; refits the endpoints
+
+struct GroupSmem {
+  WordInfo *info;      // [kMaxWords]
+  int *err;            // [kMaxWords + 1][33]; last row = rejected for every target
+  uint8_t *lut5, *lut6;
+  uint32_t *keys;      // [HT + 1]
+  uint32_t *ulist;     // [kMaxWords + kG]
+  uint16_t *pos_uid;   // [R][UW]: row 0 = the group's own row, row r = r rows above
+  uint16_t *slot_uid;  // [HT + 2]
+  uint32_t *ulist_all; // [NP + kG]: every distinct word of the window (word-diverse groups, chunked path)
+};
+
+__host__ __device__ inline int pow2_at_least(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+__host__ __device__ inline size_t rows_smem_bytes(int sa, int *np_out, int *ht_out) {
+  const int R = 2 * sa, UW = kG + 2 * sa - 1;
+  const int NP = R * UW;
+  const int HT = pow2_at_least(NP + kG + (NP + kG) / 4);
+  if (np_out) *np_out = NP;
+  if (ht_out) *ht_out = HT;
+  size_t b = 0;
+  b += (size_t)kMaxWords * sizeof(WordInfo);
+  b += (size_t)(kMaxWords + 1) * 33 * sizeof(int);
+  b += 512;
+  b += (size_t)(HT + 1) * 4;
+  b += (size_t)(kMaxWords + kG) * 4;
+  b += (size_t)NP * 2;
+  b += (size_t)(HT + 2) * 2;
+  b += (size_t)(NP + kG) * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+// ---- the hand-over medium: one 8-byte entry per block, {index word, epoch of the encode call} ----------
+__device__ __forceinline__ unsigned long long ld_entry(const unsigned long long *p) {
+  unsigned long long x;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
+  return x;
+}
+__device__ __forceinline__ void st_entry(unsigned long long *p, uint32_t word, uint32_t epoch) {
+  const unsigned long long x = ((unsigned long long)epoch << 32) | (unsigned long long)word;
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory");
+}
+
+// Where the final index words of one frame are read from while the kernel runs.
+struct RowIO {
+  const uint64_t *cur;        // final_blocks of the frame (rows that are not searched by this launch)
+  unsigned long long *wf;     // wordflag of the frame
+  const uint8_t *row_todo;    // inter frames: rows in which the inter search left blocks over
+  uint32_t epoch;
+  int bw;
+  bool all_rows;              // intra frame: every row is searched
+  // rows this launch writes hand their words over through `wf`; all others are final since the inter search
+  __device__ __forceinline__ bool tagged(int j) const { return all_rows || row_todo[j] != 0; }
+  __device__ __forceinline__ bool ready(int j, int i) const {
+    return !tagged(j) || (uint32_t)(ld_entry(wf + (size_t)j * bw + i) >> 32) == epoch;
+  }
+  // final word of block (i, j); waits for it if it has not been handed over yet
+  __device__ __forceinline__ uint32_t word(int j, int i) const {
+    const size_t idx = (size_t)j * bw + i;
+    if (!tagged(j)) return __ldcg(reinterpret_cast<const uint32_t *>(cur) + 2 * idx + 1);
+    for (;;) {
+      const unsigned long long e = ld_entry(wf + idx);
+      if ((uint32_t)(e >> 32) == epoch) return (uint32_t)e;
+      __nanosleep(20);
+    }
+  }
+};
+
+// Inserts `word` into the open-addressing set (bulk phase: nobody reads the table rows before the next
+// barrier); the thread that claims a slot also hands out the word's dense id (ids >= cap only count).
+__device__ __forceinline__ uint16_t wordset_insert(uint32_t *keys, uint32_t hmask, int hshift, int HT, int *special,
+                                                   int *count, uint16_t *slot_uid, uint32_t *ulist, uint32_t word,
+                                                   int cap = kMaxWords) {
+  if (word == kEmpty) {
+    if (atomicExch(special, 1) == 0) {
+      const int uid = atomicAdd(count, 1);
+      slot_uid[HT] = (uint16_t)uid;
+      if (uid < cap) ulist[uid] = kEmpty;
+    }
+    return (uint16_t)HT;
+  }
+  uint32_t h = (word * 0x9E3779B1u) >> hshift;
+  for (;;) {
+    const uint32_t old = atomicCAS(&keys[h], kEmpty, word);
+    if (old == kEmpty) {
+      const int uid = atomicAdd(count, 1);
+      slot_uid[h] = (uint16_t)uid;
+      if (uid < cap) ulist[uid] = word;
+      break;
+    }
+    if (old == word) break;
+    h = (h + 1u) & hmask;
+  }
+  return (uint16_t)h;
+}
+
+#ifdef MPTC_PHASE_TIMING
+__device__ unsigned long long g_rows_cycles[24];
+#define PHASE_MARK(i) do { if (tid == 0) { long long now_ = clock64(); atomicAdd(&g_rows_cycles[i], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+#define PHASE_ADD(i, x) atomicAdd(&g_rows_cycles[i], (unsigned long long)(x))
+// wavefront trace of the launch's first frame: per (row, group) the times (globaltimer, ns) at which the
+// group started waiting for the far rows, started loading, started its own row, made its first and its
+// last decision
+__device__ unsigned long long g_rows_trace[512 * 16 * 6];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long x;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(x));
+  return x;
+}
+__device__ unsigned long long g_rows_steps[8 * 512];   // decision time of every block of rows 100..107 of the first frame
+#define TRACE(k) do { if (tid == 0 && gop_i == 0 && by < 512 && (x0 >> 5) < 16) g_rows_trace[(by * 16 + (x0 >> 5)) * 6 + (k)] = gtime(); } while (0)
+#else
+#define TRACE(k) do { } while (0)
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_ADD(i, x) do { } while (0)
+#endif
+
+__device__ __forceinline__ int vld(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void vst(int *p, int x) { *reinterpret_cast<volatile int *>(p) = x; }
+__device__ __forceinline__ uint16_t vld16(const uint16_t *p) { return *reinterpret_cast<const volatile uint16_t *>(p); }
+__device__ __forceinline__ uint32_t vld32(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, int *__restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_item, s_count, s_special, s_overflow, s_gdone;
+  __shared__ int s_avail[kNear + 1];       // [r]: columns < s_avail[r] of row by-r went into the word table at load time
+  __shared__ int s_near_done[kNear + 1];   // [r]: targets < s_near_done[r] have their partial of row by-r in s_near
+  __shared__ WinnerState s_near[kNear + 1][kG];
+  __shared__ WinnerState s_partial[kG];
+  __shared__ int s_fin_uid[kG], s_fin_dec[kG];   // the decider's results, for the warp that refits the endpoints
+  __shared__ int s_req_state, s_req_uid, s_ddone;   // decider -> evaluator warp: "add this word to the table"
+  __shared__ uint32_t s_req_word;
+  __shared__ TargetCtx s_t;                // direct path only
+  __shared__ WinnerState s_red[kWarps];
+
+  const int W = 2 * sa, R = 2 * sa, UW = kG + 2 * sa - 1;
+  int NP, HT;
+  rows_smem_bytes(sa, &NP, &HT);
+  GroupSmem sm;
+  {
+    unsigned char *p = smem_raw;
+    sm.info = reinterpret_cast<WordInfo *>(p);  p += (size_t)kMaxWords * sizeof(WordInfo);
+    sm.err = reinterpret_cast<int *>(p);        p += (size_t)(kMaxWords + 1) * 33 * sizeof(int);
+    sm.lut5 = p; sm.lut6 = p + 256;             p += 512;
+    sm.keys = reinterpret_cast<uint32_t *>(p);  p += (size_t)(HT + 1) * 4;
+    sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)(kMaxWords + kG) * 4;
+    sm.pos_uid = reinterpret_cast<uint16_t *>(p); p += (size_t)NP * 2;
+    sm.slot_uid = reinterpret_cast<uint16_t *>(p); p += (size_t)(HT + 2) * 2;
+    sm.ulist_all = reinterpret_cast<uint32_t *>(p);
+  }
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t hmask = (uint32_t)HT - 1u;
+  const int hshift = 33 - __ffs(HT);
+  const int n_items = n_gops * v.bh * split;   // one item = one row, or 1/split of its groups
+  const uint32_t epoch = v.epoch;
+
+  if (tid < 256) {
+    sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);
+    sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
+  }
+  if (tid < 33) sm.err[kMaxWords * 33 + tid] = kRejectedSmall;
+
+  if (k_in_gop > 0) {   // inter frames: anything left that K3s did not take?
+    bool any = false;
+    for (int g = 0; g < n_gops; ++g) {
+      const int f = v.first + g * v.gop + k_in_gop;
+      any = any || (f < v.first + v.count && v.n_unique[f] == kSparseNotHandled);
+    }
+    if (!any) return;
+  }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) return;
+    // the `split` CTAs of a row hold ADJACENT tickets (see the header comment)
+    const int part = item % split, gop_i = (item / split) % n_gops, by = item / (split * n_gops);
+    const int f = v.first + gop_i * v.gop + k_in_gop;
+    if (f >= v.first + v.count) continue;
+    if (k_in_gop > 0 && v.n_unique[f] != kSparseNotHandled) continue;
+    const uint8_t *frame = v.rgb + v.frame_bytes * f;
+    uint64_t *cur = v.final_blocks + (size_t)f * v.nb;
+    const uint64_t *init = v.init_blocks + (size_t)f * v.nb;
+    const uint8_t *flags = v.flags + (size_t)f * v.nb;
+    uint8_t *motion = v.motion + (size_t)f * v.nb * 2;
+    unsigned long long *wf = v.wordflag + (size_t)f * v.nb;
+    // Inter frames: only rows in which the inter search left blocks over have work; every other row is
+    // final already and is read from final_blocks by its dependants.
+    const bool all_rows = (k_in_gop == 0);
+    const uint8_t *row_todo = v.row_todo + (size_t)f * v.bh;
+    if (!all_rows && !row_todo[by]) continue;
+    RowIO io;
+    io.cur = cur; io.wf = wf; io.row_todo = row_todo; io.epoch = epoch; io.bw = v.bw; io.all_rows = all_rows;
+    unsigned long long *wf_row = wf + (size_t)by * v.bw;
+
+#ifdef MPTC_PHASE_TIMING
+    long long t_mark_ = clock64();
+#endif
+    for (int x0 = part * kG; x0 < v.bw; x0 += split * kG) {
+      const int x_end = min(x0 + kG, v.bw);
+      const int n = x_end - x0;
+      PHASE_MARK(0);
+      // ---- which blocks of the group still need the intra search ----------------------------
+      const int gx = x0 + lane;
+      const bool in_row = gx < v.bw;
+      const bool todo = in_row && flags[(size_t)by * v.bw + gx] == 0;
+      const unsigned todo_mask = __ballot_sync(0xffffffffu, todo);   // identical in every warp
+      if (todo_mask == 0u) {   // (inter frames) nothing to search: hand the final words of the inter search over
+        if (wid == 0 && in_row) st_entry(wf_row + gx, (uint32_t)(cur[(size_t)by * v.bw + gx] >> 32), epoch);
+        continue;
+      }
+      const bool sparse = __popc(todo_mask) <= kSparseTodo;
+      const int need = min(x_end - 1 + sa, v.bw);   // rows above: columns < need are in the group's windows
+      const int lo = max(x0 - sa, 0);
+
+      // ---- phase A.  warp 0 waits for the FAR rows (kNear + 1 and more above): their last needed entry is
+      // there.  The other warps clear the word table meanwhile.  The kNear rows directly above and the
+      // own row's left part are NOT waited for: they are looked at as late as possible (phase B2, after
+      // the far rows have been loaded, evaluated and scanned -- 10 us during which those rows advance by a
+      // whole window), and what is still missing then is followed by the merger warps of phase D. ---------
+      __syncthreads();   // the previous group's tables are no longer in use
+      TRACE(0);
+      if (wid == 0) {
+        for (int base = sparse ? 1 : kNear + 1; base < R; base += 32) {
+          const int r = base + lane;
+          bool ok = r >= R || by - r < 0 || !io.tagged(by - r);
+          const unsigned long long *pe = wf + (size_t)(ok ? 0 : by - r) * v.bw + need - 1;
+          while (!__all_sync(0xffffffffu, ok)) {
+            if (!ok) ok = (uint32_t)(ld_entry(pe) >> 32) == epoch;
+            if (!ok) __nanosleep(32);
+          }
+        }
+        if (sparse && split > 1 && x0 > 0 && lane == 0)
+          while (!io.ready(by, x0 - 1)) __nanosleep(32);
+        if (lane == 0) { s_count = 0; s_special = 0; s_overflow = 0; s_gdone = 0; s_req_state = 0; s_ddone = 0; }
+        if (lane <= kNear) s_near_done[lane] = 0;
+      } else if (!sparse) {
+        for (int s = tid - 32; s <= HT; s += kThreads - 32) sm.keys[s] = kEmpty;
+        for (int s = tid - 32; s <= HT + 1; s += kThreads - 32) sm.slot_uid[s] = kNotReady;
+      }
+      __syncthreads();
+      PHASE_MARK(1);   // far rows + clear
+      TRACE(1);
+
+      // ---- direct path: one target at a time, every window position evaluated.  Taken for sparse groups
+      // (typical for the leftovers of an inter frame), for a handful of targets in a word-diverse window,
+      // and to finish a group whose word table overflowed. ------------------------------------------
+      auto direct_targets = [&](int g_begin, bool wait_all) {
+        if (wait_all) {   // every row of the window, and the own row left of the group
+          if (wid == 0) {
+            for (int base = 1; base < R; base += 32) {
+              const int r = base + lane;
+              bool ok = r >= R || by - r < 0 || !io.tagged(by - r);
+              const unsigned long long *pe = wf + (size_t)(ok ? 0 : by - r) * v.bw + need - 1;
+              while (!__all_sync(0xffffffffu, ok)) {
+                if (!ok) ok = (uint32_t)(ld_entry(pe) >> 32) == epoch;
+                if (!ok) __nanosleep(32);
+              }
+            }
+            if (split > 1 && x0 > 0 && lane == 0)
+              while (!io.ready(by, x0 - 1)) __nanosleep(32);
+          }
+          __syncthreads();
+        }
+        for (int g = g_begin; g < n; ++g) {
+          const int bx = x0 + g, b = by * v.bw + bx;
+          if (!((todo_mask >> g) & 1u)) {   // final since the inter search: hand its word over in order
+            if (tid == 0) st_entry(wf + b, (uint32_t)(cur[b] >> 32), epoch);
+            continue;
+          }
+          if (tid == 0) build_target(s_t, frame, v.w, bx, by, init[b]);
+          __syncthreads();
+          WinnerState s;
+          winner_init(s);
+          for (int p = tid; p < W * W; p += kThreads) {
+            const int row = p / W, col = p - row * W;
+            const int j = by - row, i = bx + sa - 1 - col;
+            if (i < 0 || j < 0 || i >= v.bw || (row == 0 && i >= bx)) continue;
+            winner_update(s, eval_candidate(s_t, io.word(j, i)), row, col, W);
+          }
+          winner_block_reduce<kWarps>(s, s_red);
+          if (tid == 0) {
+            atomicAdd(v.work + kWorkIntraEvals, (unsigned long long)(W * W));   // every window position evaluated
+            int row, col;
+            const int min_err = winner_resolve(s, W, row, col);
+            uint32_t final_word = s_t.own_word;
+            if (min_err <= thr) {
+              final_word = io.word(by - row, bx + sa - 1 - col);
+              cur[b] = winning_block(s_t, final_word);
+              motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);
+              motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);
+            } else {
+              motion[2 * b + 0] = 255;
+              motion[2 * b + 1] = 255;
+            }
+            st_entry(wf + b, final_word, epoch);
+          }
+          __syncthreads();
+        }
+      };
+      if (sparse) {
+        direct_targets(0, false);
+        continue;
+      }
+
+      // ---- phase B: load the FAR rows of the union window (loads first, then the hash inserts) -----------
+      LaneTarget t;
+      for (int p0 = 0; p0 < NP; p0 += 4 * kThreads) {
+        uint32_t wv[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int p = p0 + q * kThreads + tid;
+          const int r = p / UW, uc = p - r * UW;
+          const int j = by - r, i = x0 - sa + uc;
+          bool valid = p < NP && i >= 0 && i < v.bw && j >= 0;
+          bool own_final = false;   // a block of the group that the inter search already decided
+          if (r == 0) {
+            own_final = valid && i >= x0 && i < x_end && flags[(size_t)by * v.bw + i] != 0;
+            valid = own_final;       // the own row's left part comes with the near rows (phase B2)
+          } else if (r <= kNear) {
+            valid = false;
+          }
+          ok[q] = valid;
+          wv[q] = !valid ? 0u : (own_final ? (uint32_t)(cur[(size_t)j * v.bw + i] >> 32) : io.word(j, i));
+        }
+        if (p0 == 0) {   // the target's pixel loads go out behind the first batch of window loads
+          if (in_row) {
+            load_lane_target(t, frame, v.w, gx, by, init[(size_t)by * v.bw + gx]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
+            t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int p = p0 + q * kThreads + tid;
+          if (p < NP) sm.pos_uid[p] = ok[q] ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, &s_count, sm.slot_uid, sm.ulist, wv[q]) : kNone;
+        }
+      }
+      __syncthreads();
+      const int U0 = s_count;
+      PHASE_MARK(2);   // window load + hash
+
+      // ---- word-diverse group (more distinct words than the table holds: noise, err_threshold 0,
+      // anything that keeps the frame's own ~distinct index words).  Same plan as the fast path,
+      // restructured so that no table has to hold all words at once:
+      //   1. wait until EVERYTHING the group's window can contain is final (no incremental near rows);
+      //   2. reload the complete window, de-duplicate, all distinct words into ulist_all;
+      //   3. rows above: chunks of kMaxWords words through the uniform evaluation (warp = word,
+      //      lane = target) and a remapped window scan; then (3b) the <= sa blocks of the own row left
+      //      of the group, once the neighbour CTA has decided them;
+      //   4. the group's own blocks in order by one warp, lane = target: block g resolves from its
+      //      winner state, then its final word is evaluated for the 32 lanes at once and pushed to
+      //      the <= sa targets on its right (no table: the err_diff stays in a register). ----------------
+      auto overflow_group = [&]() {
+        if (wid == 0) {
+          if (lane >= 1 && lane <= kNear) {
+            const int r = lane;
+            if (r < R && by - r >= 0)
+              while (!io.ready(by - r, need - 1)) __nanosleep(32);
+          }
+          __syncwarp();
+          if (lane == 0) { s_count = 0; s_special = 0; }
+        } else {
+          for (int s = tid - 32; s <= HT; s += kThreads - 32) sm.keys[s] = kEmpty;
+        }
+        __syncthreads();
+        for (int p0 = 0; p0 < NP; p0 += 4 * kThreads) {
+          uint32_t wv[4];
+          bool ok[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q * kThreads + tid;
+            const int r = p / UW, uc = p - r * UW;
+            const int j = by - r, i = x0 - sa + uc;
+            ok[q] = p < NP && i >= 0 && i < v.bw && j >= 0 && r > 0;   // the own row comes later (steps 3b, 4)
+            wv[q] = ok[q] ? io.word(j, i) : 0u;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int p = p0 + q * kThreads + tid;
+            if (p < NP) sm.pos_uid[p] = ok[q] ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, &s_count, sm.slot_uid, sm.ulist_all, wv[q], NP + kG) : kNone;
+          }
+        }
+        __syncthreads();
+        const int UA = s_count;
+        if (tid == 0) {   // executed work: all distinct words + the pushed final words, once per block of the group
+          const unsigned long long nn = (unsigned long long)n;
+          atomicAdd(v.work + kWorkIntraEvals, ((unsigned long long)UA + (unsigned long long)min(sa, x0) + nn) * nn);
+          atomicAdd(v.work + kWorkIntraScanned, (unsigned long long)__popc(todo_mask) * (unsigned long long)(min(R - 1, by) * W) *
+                                                   (unsigned long long)((UA + kMaxWords - 1) / kMaxWords));
+          atomicAdd(v.work + kWorkIntraGroups, 1ull);
+        }
+        for (int p = tid; p < NP; p += kThreads) {
+          const uint16_t slot = sm.pos_uid[p];
+          if (slot != kNone) sm.pos_uid[p] = sm.slot_uid[slot];   // kNone = 0xFFFF is outside every chunk
+        }
+        __syncthreads();
+        constexpr int kPerWarp = kG / kWarps > 0 ? kG / kWarps : 1;
+        WinnerState wsq[kPerWarp];
+#pragma unroll
+        for (int q = 0; q < kPerWarp; ++q) winner_init(wsq[q]);
+        for (int c0 = 0; c0 < UA; c0 += kMaxWords) {
+          const int cn = min(kMaxWords, UA - c0);
+          for (int u = tid; u < cn; u += kThreads) word_info(sm.ulist_all[c0 + u], sm.info[u]);
+          __syncthreads();
+          for (int u = wid; u < cn; u += kWarps)
+            sm.err[u * 33 + lane] = eval_uniform(t, sm.ulist_all[c0 + u], sm.info[u], sm.lut5, sm.lut6);
+          __syncthreads();
+#pragma unroll
+          for (int q = 0; q < kPerWarp; ++q) {
+            const int g = wid + q * kWarps;
+            if (g >= n || !((todo_mask >> g) & 1u)) continue;
+            scan_window<true>(wsq[q], sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, 1, min(R - 1, by) + 1, lane, c0, cn, kMaxWords);
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int q = 0; q < kPerWarp; ++q) {
+          const int g = wid + q * kWarps;
+          if (g >= n || !((todo_mask >> g) & 1u)) continue;
+          winner_warp_reduce(wsq[q]);
+          if (lane == 0) s_partial[g] = wsq[q];
+        }
+        // 3b. the own row left of the group: only now does the group wait for its neighbour CTA (two
+        // CTAs per row on intra frames), so the chunk phase above overlapped the neighbour's decisions.
+        // Its <= sa words are evaluated one per warp, lane = target, into rows 0.. of the err table.
+        if (split > 1 && x0 > 0 && tid == 0)
+          while (!io.ready(by, x0 - 1)) __nanosleep(32);
+        __syncthreads();
+        const int n_left = min(sa, x0);
+        for (int j = wid; j < n_left; j += kWarps) {
+          const uint32_t word = io.word(by, x0 - 1 - j);
+          if (lane == 0) { sm.ulist[j] = word; word_info(word, sm.info[j]); }
+          __syncwarp();
+          sm.err[j * 33 + lane] = eval_uniform(t, word, sm.info[j], sm.lut5, sm.lut6);
+        }
+        __syncthreads();
+        if (wid == 0) {
+          WinnerState ws;
+          winner_init(ws);
+          if (todo) {
+            ws = s_partial[lane];
+            for (int j = 0; j < n_left && lane + 1 + j <= sa; ++j)   // block x0-1-j is lane+1+j to the left
+              winner_update_fast(ws, sm.err[j * 33 + lane], (uint32_t)(sa + lane + j));
+          }
+          uint32_t final_word = (in_row && !todo) ? (uint32_t)(cur[(size_t)by * v.bw + gx] >> 32) : 0u;
+          int dec = -1;
+          uint32_t w_prev = 0u;
+          int e_prev = kRejectedSmall;
+          bool have_prev = false;
+          for (int g = 0; g < n; ++g) {
+            // lane g has seen all its candidates: resolve (every lane does, lane g's result counts)
+            int row, col;
+            const int min_err = winner_resolve_fast(ws, row, col);
+            const bool fnd = todo && min_err <= thr;
+            int gi = -1;
+            uint32_t wt = 0u;
+            if (fnd) {
+              const int d = col - sa + 1;                       // row 0: the block d to the left
+              if (row == 0 && lane - d >= 0) gi = lane - d;     // inside the group: that lane's final word
+              else if (row == 0) wt = sm.ulist[d - lane - 1];   // left of the group (step 3b)
+              else wt = sm.ulist_all[sm.pos_uid[row * UW + lane + W - 1 - col]];
+            }
+            const int gi_g = __shfl_sync(0xffffffffu, gi, g);
+            const uint32_t w_in = __shfl_sync(0xffffffffu, final_word, gi_g >= 0 ? gi_g : 0);
+            const uint32_t w_tab = __shfl_sync(0xffffffffu, wt, g);
+            const uint32_t w_own = __shfl_sync(0xffffffffu, (in_row && !todo) ? final_word : t.own_word, g);
+            const bool fnd_g = __shfl_sync(0xffffffffu, (int)fnd, g) != 0;
+            const uint32_t w = fnd_g ? (gi_g >= 0 ? w_in : w_tab) : w_own;   // final word of block g
+            if (lane == g) {
+              final_word = w;
+              dec = fnd ? ((row << 8) | col) : -1;
+              st_entry(wf_row + gx, w, epoch);                   // handed over at once
+            }
+            // push it to the <= sa undecided targets on its right
+            const unsigned right = (todo_mask >> g) >> 1;
+            if (right & ((sa >= 32) ? 0xffffffffu : ((1u << sa) - 1u))) {
+              int e;
+              if (have_prev && w == w_prev) e = e_prev;        // runs of the same word are common
+              else {
+                if (lane == 0) word_info(w, sm.info[0]);
+                __syncwarp();
+                e = eval_uniform(t, w, sm.info[0], sm.lut5, sm.lut6);
+                __syncwarp();
+                w_prev = w; e_prev = e; have_prev = true;
+              }
+              const int d = lane - g;
+              const bool acc = d >= 1 && d <= sa && todo && e != kRejectedSmall;
+              winner_update_fast(ws, acc ? e : kRejectedSmall, acc ? (uint32_t)(sa + d - 1) : 0u);
+            }
+          }
+          if (todo) {   // endpoints + motion: nobody waits on these inside the kernel
+            const size_t b = (size_t)by * v.bw + gx;
+            if (dec >= 0) {
+              const int row = dec >> 8, col = dec & 0xFF;
+              cur[b] = lane_winning_block(t, final_word);
+              motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);   // x = (i - bx) + sa
+              motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);   // y = (j - by) + 2sa - 1
+            } else {
+              motion[2 * b + 0] = 255;
+              motion[2 * b + 1] = 255;
+            }
+          }
+        }
+      };
+      if (U0 + kG > kMaxWords) {
+        // the chunked path costs ~U evaluations x 32 lanes whatever the number of targets; a handful
+        // of targets is cheaper one at a time (measured: leftovers of inter frames at err_threshold 0)
+        if (__popc(todo_mask) >= kChunkedTodo) overflow_group();
+        else direct_targets(0, true);
+        continue;
+      }
+
+      // ---- phase C: ids per position, per-word constants, evaluation, rows above ------------------------
+      for (int p = tid; p < NP; p += kThreads) {
+        const uint16_t slot = sm.pos_uid[p];
+        sm.pos_uid[p] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
+      }
+      for (int u = tid; u < U0; u += kThreads) word_info(sm.ulist[u], sm.info[u]);
+      __syncthreads();
+      // warp = one distinct word, lane = target
+      for (int u = wid; u < U0; u += kWarps)
+        sm.err[u * 33 + lane] = eval_uniform(t, sm.ulist[u], sm.info[u], sm.lut5, sm.lut6);
+      __syncthreads();
+      PHASE_MARK(3);   // ids + word constants + evaluation
+#ifdef MPTC_PHASE_TIMING
+      if (tid == 0) { PHASE_ADD(10, U0); PHASE_ADD(11, 1); }
+#endif
+      // the far rows, every target, all warps (scan order: j downwards, i downwards)
+      for (int g = wid; g < n; g += kWarps) {
+        if (!((todo_mask >> g) & 1u)) continue;
+        WinnerState ws;
+        winner_init(ws);
+        // uc = g + W - 1 - col: positions run right to left
+        scan_window<false>(ws, sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, kNear + 1, min(R - 1, by) + 1, lane, 0, 0, kMaxWords);
+        winner_warp_reduce(ws);
+        if (lane == 0) s_partial[g] = ws;
+      }
+      // ---- phase B2: the near rows and the own row's left part, as they are NOW.  warp r looks at how
+      // far row by - r (r = 0: the own row) has got; that much is loaded, looked up / added to the word
+      // table (a near row's words are mostly in the table already: same picture region), evaluated and
+      // scanned here by all warps; the rest is followed by the merger warps of phase D. --------------------
+      if (wid <= kNear) {
+        const int r = wid, end = r == 0 ? x0 : need;
+        int avail = end;
+        if (r < R && !(r == 0 && split == 1) && by - r >= 0 && io.tagged(by - r)) {
+          const unsigned long long *pr = wf + (size_t)(by - r) * v.bw;
+          avail = lo;
+          for (int c0 = lo; c0 < end; c0 += 32) {
+            const int c = c0 + lane;
+            const bool valid = c < end && (uint32_t)(ld_entry(pr + c) >> 32) == epoch;
+            const unsigned inv = ~__ballot_sync(0xffffffffu, valid);
+            const int p = inv ? __ffs(inv) - 1 : 32;
+            avail = min(c0 + p, end);
+            if (p < 32) break;
+          }
+        }
+        if (lane == 0) s_avail[r] = avail;
+      }
+      __syncthreads();
+      const int near_rows = min(kNear, R - 1);
+      for (int p = tid; p < (near_rows + 1) * UW; p += kThreads) {
+        const int r = p / UW, uc = p - r * UW;
+        const int j = by - r, i = x0 - sa + uc;
+        if (r == 0 && i >= x0) continue;                       // the group itself: set in phase B / by the decider
+        const bool valid = i >= 0 && i < v.bw && j >= 0 && i < s_avail[r];
+        sm.pos_uid[p] = valid ? wordset_insert(sm.keys, hmask, hshift, HT, &s_special, &s_count, sm.slot_uid, sm.ulist, io.word(j, i)) : kNone;
+      }
+      __syncthreads();
+      const int U1 = s_count;
+      if (U1 + 8 > kMaxWords) {   // (rare) the near rows filled the table: the chunked path starts over
+        if (__popc(todo_mask) >= kChunkedTodo) overflow_group();
+        else direct_targets(0, true);
+        continue;
+      }
+      for (int p = tid; p < (near_rows + 1) * UW; p += kThreads) {
+        const int r = p / UW, uc = p - r * UW;
+        if (r == 0 && x0 - sa + uc >= x0) continue;
+        const uint16_t slot = sm.pos_uid[p];
+        sm.pos_uid[p] = (slot != kNone) ? sm.slot_uid[slot] : (uint16_t)kMaxWords;
+      }
+      for (int u = U0 + tid; u < U1; u += kThreads) word_info(sm.ulist[u], sm.info[u]);
+      __syncthreads();
+      for (int u = U0 + wid; u < U1; u += kWarps)
+        sm.err[u * 33 + lane] = eval_uniform(t, sm.ulist[u], sm.info[u], sm.lut5, sm.lut6);
+      __syncthreads();
+      // scan what there is of the near rows and of the own row left of the group, into the far rows' partial
+      for (int g = wid; g < n; g += kWarps) {
+        if (!((todo_mask >> g) & 1u)) continue;
+        WinnerState ws;
+        winner_init(ws);
+        scan_window<false>(ws, sm.pos_uid + g + W - 1, UW, -1, sm.err + g, W, 1, min(near_rows, by) + 1, lane, 0, 0, kMaxWords);
+        for (int l = lane; l < sa; l += 32)      // own row: position i = x0 + g - 1 - l, scan column sa + l
+          if (l >= g && x0 + g - 1 - l >= 0)
+            winner_update_fast(ws, sm.err[(int)sm.pos_uid[g + sa - 1 - l] * 33 + g], (uint32_t)(sa + l));
+        winner_warp_reduce(ws);
+        if (lane == 0) {
+          WinnerState o = s_partial[g];
+          winner_merge(o, ws);
+          s_partial[g] = o;
+        }
+      }
+      __syncthreads();
+      PHASE_MARK(4);   // rows above
+      TRACE(2);
+
+      // ---- phase D: the group's own row.  warp 0 decides, warps 1 .. kNear follow the rows above, warp
+      // kNear + 1 the own row's left part (decided by the partner CTA); the rest waits at the barrier. ----
+      const int *err_lane = sm.err + lane;
+      const uint32_t own_word = t.own_word;
+
+      // Looks `word` up (any lane, any word): its id, -1 if absent, -2 if the table overflowed.
+      auto find_word = [&](uint32_t word) -> int {
+        uint32_t h;
+        if (word == kEmpty) {
+          if (vld(&s_special) == 0) return -1;
+          h = (uint32_t)HT;
+        } else {
+          h = (word * 0x9E3779B1u) >> hshift;
+          for (;;) {
+            const uint32_t kv = vld32(&sm.keys[h]);
+            if (kv == word) break;
+            if (kv == kEmpty) return -1;
+            h = (h + 1u) & hmask;
+          }
+        }
+        uint16_t u;
+        while ((u = vld16(&sm.slot_uid[h])) == kNotReady) { }   // another warp is evaluating it right now
+        return u == kOverflowUid ? -2 : (int)u;
+      };
+      // Warp-collective, `word` warp-uniform: the word's id; a word that is not in the table yet is added
+      // and evaluated for the 32 targets by the calling warp.  -2 if the table is full.
+      auto ensure_word = [&](uint32_t word) -> int {
+        int uid = -1, claimed = 0;
+        uint32_t h = 0;
+        if (lane == 0) {
+          if (word == kEmpty) {
+            h = (uint32_t)HT;
+            claimed = atomicCAS(&s_special, 0, 1) == 0;
+          } else {
+            h = (word * 0x9E3779B1u) >> hshift;
+            for (;;) {
+              const uint32_t old = atomicCAS(&sm.keys[h], kEmpty, word);
+              if (old == kEmpty) { claimed = 1; break; }
+              if (old == word) break;
+              h = (h + 1u) & hmask;
+            }
+          }
+          if (claimed) {
+            PHASE_ADD(12, 1);
+            uid = atomicAdd(&s_count, 1);
+            if (uid >= kMaxWords) {
+              *reinterpret_cast<volatile uint16_t *>(&sm.slot_uid[h]) = kOverflowUid;
+              uid = -2;
+            }
+          } else {
+            uint16_t u;
+            while ((u = vld16(&sm.slot_uid[h])) == kNotReady) { }
+            uid = u == kOverflowUid ? -2 : (int)u;
+          }
+        }
+        claimed = __shfl_sync(0xffffffffu, claimed, 0);
+        uid = __shfl_sync(0xffffffffu, uid, 0);
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (claimed && uid >= 0) {
+          if (lane == 0) {
+            sm.ulist[uid] = word;
+            word_info(word, sm.info[uid]);
+          }
+          __syncwarp();
+          sm.err[uid * 33 + lane] = eval_uniform(t, word, sm.info[uid], sm.lut5, sm.lut6);
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) *reinterpret_cast<volatile uint16_t *>(&sm.slot_uid[h]) = (uint16_t)uid;
+        }
+        return uid;
+      };
+
+      if (wid == 0) {
+        // ---- decider: lane l owns target l: its WinnerState and its current candidate decision live in
+        // registers.  When block g is final its word is PUSHED to the <= sa targets on its right (one
+        // table read + a handful of selects per lane), so step g only costs: broadcast lane g's candidate
+        // -> table read -> selects.  The pushes reach target l in DECREASING scan position (block g sits at
+        // row 0, column sa + (l - g) - 1 of l's scan, and row 0 is scanned first), so every pushed candidate
+        // is the earliest one seen so far.  With the reference's rule:
+        //   err <= 0  -> it becomes the first non-positive candidate; the winner is then the "last row with
+        //                a negative" candidate if one exists in a row above, else this candidate itself;
+        //   err  > 0  -> it only matters while no non-positive candidate exists, and then wins ties
+        //                against everything scanned later (err <= best so far).
+        WinnerState ws;            // everything target `lane` has seen so far (rows above, partials, pushes)
+        winner_init(ws);
+        if (todo) ws = s_partial[lane];
+        int cand_uid = 0, cand_dec = 0, best_e = 0, ln_uid = 0, ln_dec = 0;
+        bool found = true, has_first = false, ln_valid = false;
+        // (Re)derives the select-only state of the still undecided lanes (lane >= g) from ws.
+        auto derive = [&](int g) {
+          if (todo && lane < g) return;   // decided: cand_* are final
+          int row, col;
+          const int min_err = winner_resolve_fast(ws, row, col);
+          found = todo ? (min_err <= thr) : true;
+          cand_dec = (row << 8) | col;
+#ifdef MPTC_DEBUG_ROWS
+          if (todo && found && (unsigned)(row * UW + lane + W - 1 - col) >= (unsigned)NP)
+            printf("k_intra_rows: bad winner position row %d col %d lane %d by %d x0 %d g %d first %x lastneg %x best %x\n", row, col, lane, by, x0, g, ws.first, ws.lastneg, ws.best);
+#endif
+          cand_uid = todo ? (int)vld16(&sm.pos_uid[found ? row * UW + lane + W - 1 - col : 0])
+                          : (in_row ? (int)sm.pos_uid[sa + lane] : 0);   // already final since the inter search
+          has_first = ws.first < 0x80000000u;
+          best_e = min_err;                                 // only read while !has_first
+          ln_valid = ws.lastneg >= 0 && (ws.lastneg >> 7) >= 1;
+          const int lrow = ws.lastneg >> 7, lcol = 127 - (ws.lastneg & 127);
+          ln_dec = (lrow << 8) | lcol;
+          ln_uid = vld16(&sm.pos_uid[ln_valid ? lrow * UW + lane + W - 1 - lcol : 0]);
+        };
+        const bool zero_ok = 0 <= thr;
+        // shared-memory addresses of the hot loop's three accesses (plain 32-bit shared addresses: no
+        // generic-address arithmetic inside the loop)
+        const uint32_t err_lane_s = (uint32_t)__cvta_generic_to_shared(sm.err + lane);
+        const uint32_t ulist_s = (uint32_t)__cvta_generic_to_shared(sm.ulist);
+        const uint32_t my_row0_s = (uint32_t)__cvta_generic_to_shared(sm.pos_uid + sa + lane);
+        unsigned long long *my_entry = wf_row + gx;
+        // Everything of step g after lane g's word id is known.  The warp that runs this holds no pixel
+        // data (the evaluator warp adds new words, the refit happens after the barrier): the loop's
+        // addresses and parameters stay in registers.
+        auto finish_step = [&](int g, int uid, bool unique) {
+#ifdef MPTC_DEBUG_ROWS
+          if ((unsigned)uid > (unsigned)kMaxWords && lane == 0)
+            printf("k_intra_rows: bad uid %d at by %d x0 %d g %d unique %d safe_end? split %d\n", uid, by, x0, g, (int)unique, split);
+          if ((unsigned)uid > (unsigned)kMaxWords) uid = kMaxWords;
+#endif
+          const bool mine = lane == g;     // final from now on
+          cand_uid = mine ? uid : cand_uid;
+          found = found || mine;
+          cand_dec = (mine && unique) ? -1 : cand_dec;
+          // lane g: pos_uid[row 0][g] = uid (for later derive()s); hand the word over at once
+          asm volatile(
+              "{\n .reg .pred p;\n .reg .u32 w;\n .reg .u64 x;\n"
+              " setp.ne.s32 p, %0, 0;\n"
+              " @p st.shared.u16 [%1], %2;\n"
+              " @p ld.shared.u32 w, [%3];\n"
+              " @p mov.b64 x, {w, %4};\n"
+              " @p st.relaxed.gpu.global.u64 [%5], x;\n}"
+              ::"r"((int)mine), "r"(my_row0_s), "h"((unsigned short)uid), "r"(ulist_s + 4u * (uint32_t)uid), "r"(epoch), "l"(my_entry)
+              : "memory");
+          const int d = lane - g;                              // push to the <= sa targets on the right
+          int e;
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(e) : "r"(err_lane_s + 132u * (uint32_t)uid) : "memory");
+          const bool acc = (unsigned)(d - 1) < (unsigned)sa && todo && e != kRejectedSmall;
+          const bool nonpos = acc && e <= 0;
+          const bool better = acc && e > 0 && !has_first && e <= best_e;
+          const int c = sa + d - 1;
+          cand_uid = nonpos ? (ln_valid ? ln_uid : uid) : (better ? uid : cand_uid);
+          cand_dec = nonpos ? (ln_valid ? ln_dec : c) : (better ? c : cand_dec);
+          found = nonpos ? zero_ok : (better ? (e <= thr) : found);
+          best_e = better ? e : best_e;
+          has_first = has_first || nonpos;
+          winner_update_fast(ws, acc ? e : kRejectedSmall, acc ? (uint32_t)c : 0u);   // off the critical chain
+        };
+        int g = 0;
+        bool aborted = false;
+        const bool left_pending = s_avail[0] < x0;   // the partner CTA still owed words at load time
+#ifdef MPTC_PHASE_TIMING
+        const long long td0 = clock64();
+        long long t_near = 0;
+#endif
+        if (left_pending) {
+          while (vld(&s_near_done[0]) < n) {
+            if (vld(&s_overflow)) { aborted = true; break; }
+          }
+          // every lane polled on its own and may have seen a different moment: agree before going on
+          aborted = __any_sync(0xffffffffu, aborted);
+#ifdef MPTC_PHASE_TIMING
+          if (lane == 0) PHASE_ADD(6, clock64() - td0);
+#endif
+          // (no fence: the flag and the partials are read with volatile loads, which this thread issues in
+          // program order)
+          if (!aborted && todo) {
+            const volatile WinnerState *q = &s_near[0][lane];
+            WinnerState o;
+            o.first = q->first; o.lastneg = q->lastneg; o.best = q->best;
+            winner_merge(ws, o);
+          }
+        }
+        int safe_end = 0;          // targets < safe_end have merged the partials of all near rows
+        while (g < n && !aborted) {
+          if (g >= safe_end) {
+#ifdef MPTC_PHASE_TIMING
+            const long long tn0 = clock64();
+#endif
+            int m;
+            for (;;) {
+              m = vld(&s_near_done[1]);
+#pragma unroll
+              for (int r = 2; r <= kNear; ++r) m = min(m, vld(&s_near_done[r]));
+              if (m > g) break;
+              if (vld(&s_overflow)) { aborted = true; break; }
+            }
+            // the flags grow while the lanes poll them: the warp continues with lane 0's view, so that
+            // safe_end (the trip count of the hot loop and its shuffles) is the same in every lane
+            aborted = __any_sync(0xffffffffu, aborted);
+            if (aborted) break;
+            m = __shfl_sync(0xffffffffu, m, 0);
+#ifdef MPTC_PHASE_TIMING
+            t_near += clock64() - tn0;
+            if (lane == 0) PHASE_ADD(9, 1);
+#endif
+            if (lane >= safe_end && lane < m && todo) {
+#pragma unroll
+              for (int r = 1; r <= kNear; ++r) {
+                const volatile WinnerState *q = &s_near[r][lane];
+                WinnerState o;
+                o.first = q->first; o.lastneg = q->lastneg; o.best = q->best;
+                winner_merge(ws, o);
+              }
+            }
+            safe_end = m;
+            __syncwarp();          // row 0 of pos_uid: written by the lanes that decided, read by derive
+            derive(g);
+          }
+          // Hot loop: a lone warp is bound by instruction latency, so it is short and straight-line.
+          // Leaves as soon as a block turns out unique.
+#ifdef MPTC_PHASE_TIMING
+          if (g == 0) TRACE(3);
+#endif
+          int uid = 0;
+          for (; g < safe_end; ++g) {
+            uid = __shfl_sync(0xffffffffu, found ? cand_uid : kNeedOwn, g);   // lane g has all its pushes
+            if (uid == kNeedOwn) break;
+            finish_step(g, uid, false);
+#ifdef MPTC_PHASE_TIMING
+            if (lane == 0 && gop_i == 0 && by >= 100 && by < 108 && x0 + g < 512) g_rows_steps[(by - 100) * 512 + x0 + g] = gtime();
+#endif
+          }
+          if (g >= safe_end) continue;
+          // Rare: block g keeps its own initial word, which later targets may reuse; look it up / add it
+          // to the word table (evaluated for the 32 targets).  Warp-uniform.
+          // (the evaluator warp holds the pixels; this warp asks it and waits)
+          const uint32_t new_word = __shfl_sync(0xffffffffu, own_word, g);
+          if (lane == 0) {
+            s_req_word = new_word;
+            __threadfence_block();
+            vst(&s_req_state, 1);
+          }
+          while (vld(&s_req_state) != 2) { }
+          uid = vld(&s_req_uid);
+          __syncwarp();
+          if (lane == 0) vst(&s_req_state, 0);
+          if (uid < 0) { aborted = true; break; }
+          finish_step(g, uid, true);
+          ++g;
+        }
+        if (aborted) vst(&s_overflow, 1);
+        TRACE(4);
+#ifdef MPTC_PHASE_TIMING
+        if (lane == 0) { PHASE_ADD(7, t_near); PHASE_ADD(8, clock64() - td0); }
+#endif
+        if (lane == 0) {
+          vst(&s_gdone, g);
+          // executed work: every word of the table once per block of the group; rows above + own row scanned
+          atomicAdd(v.work + kWorkIntraEvals, (unsigned long long)min(vld(&s_count), kMaxWords) * (unsigned long long)n);
+          atomicAdd(v.work + kWorkIntraScanned, (unsigned long long)__popc(todo_mask) * (unsigned long long)(min(R - 1, by) * W + sa));
+          atomicAdd(v.work + kWorkIntraGroups, 1ull);
+        }
+        s_fin_uid[lane] = cand_uid;
+        s_fin_dec[lane] = cand_dec;
+        __syncwarp();
+        if (lane == 0) vst(&s_ddone, 1);
+      } else if (wid <= kNear + 1) {
+        // ---- merger of row by - r (r = 0: the own row left of the group) ----------------------------------
+        const int r = wid <= kNear ? wid : 0;
+        const int end = r == 0 ? x0 : need;                  // columns [lo, end) of that row are in the group's windows
+        int merged = s_avail[r];
+        WinnerState wr;
+        winner_init(wr);
+        int done = 0;
+        // targets < complete(merged) have everything of this row
+        auto complete = [&](int m) { return m >= end ? n : (r == 0 ? 0 : min(n, max(0, m - sa - x0 + 1))); };
+        auto publish = [&](int newc) {
+          if (lane >= done && lane < newc) {
+            volatile WinnerState *q = &s_near[r][lane];
+            q->first = wr.first; q->lastneg = wr.lastneg; q->best = wr.best;
+          }
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) vst(&s_near_done[r], newc);
+          done = newc;
+        };
+        publish(complete(merged));
+        if (merged < end) {
+          const unsigned long long *pr = wf + (size_t)(by - r) * v.bw;
+          bool stop = false;
+          while (merged < end && !stop) {
+            if (__any_sync(0xffffffffu, vld(&s_overflow) != 0)) break;
+            const int c = merged + lane;
+            const bool in = c < end;
+            const unsigned long long ent = in ? ld_entry(pr + c) : 0ull;
+            const bool valid = in && (uint32_t)(ent >> 32) == epoch;
+            const unsigned inv = ~__ballot_sync(0xffffffffu, valid);
+            const int p = inv ? __ffs(inv) - 1 : 32;        // leading entries that are there
+#ifdef MPTC_PHASE_TIMING
+            if (lane == 0 && r == 1) PHASE_ADD(14, 1);
+#endif
+            if (p == 0) { __nanosleep(20); continue; }
+#ifdef MPTC_PHASE_TIMING
+            if (lane == 0 && r == 1) { PHASE_ADD(13, 1); PHASE_ADD(15, p); }
+#endif
+            const bool active = lane < p;
+            const uint32_t word = (uint32_t)ent;
+            int uid = -1;
+            for (;;) {
+              if (active && uid == -1) uid = find_word(word);
+              const unsigned full = __ballot_sync(0xffffffffu, active && uid == -2);
+              const unsigned newm = __ballot_sync(0xffffffffu, active && uid == -1);
+              if (full) { stop = true; break; }
+              if (newm == 0u) break;
+              const int leader = __ffs(newm) - 1;
+              const uint32_t w = __shfl_sync(0xffffffffu, word, leader);
+              const int nu = ensure_word(w);
+              if (nu < 0) { stop = true; break; }
+              if (active && word == w) uid = nu;
+            }
+            if (stop) { vst(&s_overflow, 1); break; }
+            if (active) sm.pos_uid[r * UW + c - (x0 - sa)] = (uint16_t)uid;
+            // fold the new positions into every target's partial: column cc of row by-r is scan position
+            // (r, x0 + lane + sa - 1 - cc) of target `lane`
+            for (int q = 0; q < p; ++q) {
+              const int u = __shfl_sync(0xffffffffu, uid, q);
+              const int col = x0 + lane + sa - 1 - (merged + q);
+              const int e = err_lane[u * 33];
+              const bool acc = todo && col >= 0 && col < W && e != kRejectedSmall;
+              winner_update_fast(wr, acc ? e : kRejectedSmall, acc ? (uint32_t)((r << 7) | col) : 0u);
+            }
+            merged += p;
+            publish(complete(merged));
+          }
+        }
+      }
+      else if (wid == kEvalWarp) {
+        // ---- evaluator: the decider's rare "block keeps its own word" case needs that word in the table,
+        // evaluated for the 32 targets; this warp still holds the pixels ------------------------------------
+        for (;;) {
+          const int st = __shfl_sync(0xffffffffu, lane == 0 ? vld(&s_req_state) : 0, 0);   // one view for the warp
+          if (st == 1) {
+            __threadfence_block();
+            const int uid = ensure_word(*reinterpret_cast<volatile uint32_t *>(&s_req_word));
+            if (lane == 0) {
+              vst(&s_req_uid, uid);
+              __threadfence_block();
+              vst(&s_req_state, 2);
+            }
+            __syncwarp();
+          } else if (__shfl_sync(0xffffffffu, lane == 0 ? vld(&s_ddone) : 0, 0)) {
+            break;
+          } else {
+            __nanosleep(100);   // stay off the shared-memory pipe the decider depends on
+          }
+        }
+      }
+      __syncthreads();
+      PHASE_MARK(5);   // the group's own row
+      // ---- endpoints + motion for the decided blocks (nobody waits on these inside the kernel) ------
+      if (wid == kEvalWarp && todo && lane < s_gdone) {
+        const size_t b = (size_t)by * v.bw + gx;
+        const int dec = s_fin_dec[lane];
+        if (dec >= 0) {
+          const int row = dec >> 8, col = dec & 0xFF;
+          cur[b] = lane_winning_block(t, sm.ulist[s_fin_uid[lane]]);
+          motion[2 * b + 0] = (uint8_t)(2 * sa - 1 - col);   // x = (i - bx) + sa
+          motion[2 * b + 1] = (uint8_t)(2 * sa - 1 - row);   // y = (j - by) + 2sa - 1
+        } else {
+          motion[2 * b + 0] = 255;
+          motion[2 * b + 1] = 255;
+        }
+      }
+      if (s_overflow) {          // word table overflow: the rest of the group, one target at a time
+        const int gd = s_gdone;
+        __syncthreads();
+        direct_targets(gd, true);
+      }
+    }
+  }
+}
+
+#ifdef MPTC_PHASE_TIMING
+extern "C" void mptc_debug_rows_steps(unsigned long long *out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_rows_steps, sizeof(unsigned long long) * (size_t)n);
+}
+extern "C" void mptc_debug_rows_trace(unsigned long long *out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_rows_trace, sizeof(unsigned long long) * (size_t)n);
+}
+extern "C" void mptc_debug_rows_cycles(unsigned long long *out24, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out24, g_rows_cycles, sizeof(unsigned long long) * 24);
+  if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(g_rows_cycles, z, sizeof z); }
+}
+#endif
+
+bool launch_intra_rows(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket, int grid_cap,
+                       cudaStream_t s) {
+  static int max_optin = -1;
+  static int max_ctas_dev[kMaxDevices] = {0};
+  static size_t configured_dev[kMaxDevices] = {0};   // per device: one context per GPU may live in one process
+  static int split_intra = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t bytes = rows_smem_bytes(sa, nullptr, nullptr);
+  int max_ctas = 0;
+  {
+    std::lock_guard<std::mutex> lock(launch_cfg_mutex());
+    size_t &configured = configured_dev[dev & (kMaxDevices - 1)];
+    if (max_optin < 0) cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (bytes + 6144 > (size_t)max_optin) return false;
+    if (bytes > configured) {
+      if (cudaFuncSetAttribute(k_intra_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return false;
+      configured = bytes;
+      int per_sm = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intra_rows, kThreads, bytes);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      max_ctas_dev[dev & (kMaxDevices - 1)] = (per_sm < 1 ? 1 : per_sm) * sms;
+    }
+    max_ctas = max_ctas_dev[dev & (kMaxDevices - 1)];
+    if (split_intra < 0) {
+      const char *e = getenv("MPTC_ROW_SPLIT");
+      // three CTAs per row: one decides while two build (measured on 4 x 1080p intra frames, sa 16:
+      // 3.15 / 2.87 / 2.99 ms with 2 / 3 / 4 CTAs per row, profiles/r2_k3_sweep.txt)
+      split_intra = (e && *e) ? atoi(e) : 3;
+      if (split_intra < 1) split_intra = 1;
+    }
+  }
+  // Intra frames: `split` CTAs per row.  A CTA of a row waits for its partners, whose tickets are
+  // adjacent to its own (item = (row * n_gops + gop) * split + part), so `split` resident CTAs suffice.
+  int split = k_in_gop == 0 ? split_intra : 1;
+  if (grid_cap > 0 && grid_cap < split) split = 1;
+  const int items = n_gops * v.bh * split;
+  int grid = items < max_ctas ? items : max_ctas;
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+  if (grid < split) split = 1;
+  k_intra_rows<<<grid, kThreads, bytes, s>>>(v, k_in_gop, n_gops, sa, thr, split, ticket);
+  return true;
+}
+
+}  // namespace mptc

@@ -12,6 +12,8 @@
 //
 // No tensor cores: nothing here is a dense contraction (integer / ordered-FP32 work).
 #include "mptc_kernels.h"
+
+#include <cstdlib>
 #include "mptc_device.cuh"
 
 
@@ -542,7 +544,10 @@ void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int
 
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                             int max_ctas, int grid_cap, cudaStream_t s) {
-  if (launch_intra_wavefront_tiled(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
+  // MPTC_K3=progress selects the first-generation wavefront (progress counters + fences) for A/B runs
+  static const bool first_gen = [] { const char *e = getenv("MPTC_K3"); return e && e[0] == 'p'; }();
+  if (!first_gen && launch_intra_rows(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
+  if (first_gen && launch_intra_wavefront_tiled(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
   int items = n_gops * v.bh;  // direct (one target at a time) fallback for very large windows
   int grid = items < max_ctas ? items : max_ctas;
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;

@@ -25,7 +25,9 @@ struct SeqView {
   uint32_t *n_unique;      // [F]
   uint32_t *chunk_counts;  // [F][ceil(nb/1024)]  unique blocks per chunk (K4)
   uint8_t *planes;         // [F][6][pbh][pbw]
-  int *progress;           // [F][bh]   wavefront progress counters
+  int *progress;           // [F][bh]   wavefront progress counters (direct fallback kernel only)
+  unsigned long long *wordflag;  // [F][nb] {index word, epoch}: how the rows of the intra wavefront hand decisions over
+  uint32_t epoch;          // tag of this encode call in `wordflag` (entries of earlier calls are stale)
   unsigned long long *work; // executed-work counters of the search kernels (kWork*), one atomicAdd per tile / group
   size_t frame_bytes;
   int w, h, bw, bh, nb;
@@ -53,6 +55,8 @@ void launch_dxt1_fit(const SeqView &v, int f0, int fstride, int nf, cudaStream_t
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
 bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                                   int grid_cap, cudaStream_t s);
+bool launch_intra_rows(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket, int grid_cap,
+                       cudaStream_t s);
 bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
 // grid_cap > 0 limits the number of CTAs (rows in flight): a wavefront only keeps a few rows per
 // frame busy, and idle CTAs would block the SMs for kernels of other lanes.
