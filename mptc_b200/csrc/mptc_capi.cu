@@ -374,7 +374,9 @@ int run_encode(mptc_gpu_ctx *c, int first, int count, int gop, int sa, int thr, 
   if (int r = ensure_lanes(c, nl, gop)) return r;
   // CTAs per frame of the intra wavefront: with several lanes a full grid of (mostly waiting)
   // wavefront CTAs would keep the other lanes' kernels off the SMs
-  const int rows_intra = c->wave_rows_intra > 0 ? c->wave_rows_intra : (nl > 1 ? 32 : 0);
+  // (37 = a quarter of the SMs per lane with the default four lanes: 18.75 ms against 18.98 with 32 and
+  // 19.5 with 48, profiles/r2_sched_sweep.txt)
+  const int rows_intra = c->wave_rows_intra > 0 ? c->wave_rows_intra : (nl > 1 ? 37 : 0);
   const int rows_inter = c->wave_rows_inter;
   cudaStream_t s0 = c->s_compute;
   if (++c->epoch == 0) {   // wrapped: entries of 2^32 calls ago would look current
