@@ -207,9 +207,9 @@ __device__ __forceinline__ void winner_update_fast(WinnerState &s, int e, uint32
 // for this target.  Lanes stride over the flattened scan order, so there is no per-position
 // division.  kRemap handles the multi-chunk case: ids outside [c0, c0 + cn) read the
 // all-rejected row `dummy`.
-template <bool kRemap>
+template <bool kRemap, typename E = int>
 __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos, int stride, int cdir,
-                                            const int *errcol, int W, int row_begin, int row_end, int lane,
+                                            const E *errcol, int W, int row_begin, int row_end, int lane,
                                             int c0, int cn, int dummy) {
   if (W == 32) {
     // default search area (16): one window row per step, lane = column
@@ -222,7 +222,7 @@ __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos
         u -= c0;
         u = ((unsigned)u < (unsigned)cn) ? u : dummy;
       }
-      const int e = errcol[u * 33];
+      const int e = (int)errcol[u * 33];
       // (a per-row vote that skips the first / lastneg reductions for rows without an err_diff <= 0
       // candidate was measured: 17.6 vs 14.5 ms -- such rows are rare on the benchmark content)
       winner_update_fast(ws, e, p);
@@ -238,7 +238,7 @@ __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos
       u -= c0;
       u = ((unsigned)u < (unsigned)cn) ? u : dummy;
     }
-    winner_update_fast(ws, errcol[u * 33], (uint32_t)((row << 7) | col));
+    winner_update_fast(ws, (int)errcol[u * 33], (uint32_t)((row << 7) | col));
     col += cstep;
     row += rstep;
     if (col >= W) { col -= W; ++row; }

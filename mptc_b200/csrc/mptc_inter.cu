@@ -14,13 +14,23 @@
 #include "mptc_kernels.h"
 #include "mptc_uniform_eval.cuh"
 
+#include <type_traits>
+
 namespace mptc {
 
 namespace {
 
 constexpr int kTileX = 8, kTileY = 4;         // 32 targets per CTA: lane = ty*8 + tx
 constexpr int kThreads = 256, kWarps = kThreads / 32;
-constexpr int kChunk = 128;                   // distinct words evaluated per pass
+constexpr int kChunk = 128;                   // distinct words evaluated per pass (WordInfo / epk scratch)
+// Words per SCAN pass.  The winner rule only needs the sign of a negative err_diff, and exact positive
+// values only up to the threshold (a candidate above it can never be "found", dxt_image.cpp:890), so
+// with err_threshold < 32767 the (word, target) table holds int16 {-1, 0, min(err_diff, 32767)} and
+// twice the words fit the same shared memory: word-diverse tiles (large windows, err_threshold 0,
+// noise) walk their window scan half as often.  Larger thresholds keep the exact int32 table.
+template <bool kErr16> struct ErrTable { typedef int type; static constexpr int kWords = kChunk; };
+template <> struct ErrTable<true> { typedef int16_t type; static constexpr int kWords = 2 * kChunk; };
+constexpr int kErr16Max = 32767;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;      // hash-table empty marker (the real word
                                               // 0xFFFFFFFF lives in the extra slot HT)
 constexpr uint16_t kNoPos = 0xFFFFu;          // window position outside the frame
@@ -33,7 +43,7 @@ struct TileSmem {
   uint16_t *slot_uid;  // [HT+1]
   uint32_t *ulist;     // [NP]   dense list of distinct words
   WordInfo *info;      // [kChunk]
-  int *err;            // [kChunk + 1][33]; row kChunk = "rejected" for every target
+  void *err;           // [kWords + 1][33] int32 or int16; last row = "rejected" for every target
   uint32_t *epk;       // [kChunk][33]; the refitted endpoints of (word, target), packed 565 | 565 << 16
   uint8_t *lut5, *lut6;  // ToFiveBits / ToSixBits tables
 };
@@ -79,7 +89,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   {
     unsigned char *p = smem_raw;
     sm.info = reinterpret_cast<WordInfo *>(p); p += (size_t)kChunk * sizeof(WordInfo);
-    sm.err = reinterpret_cast<int *>(p);       p += (size_t)(kChunk + 1) * 33 * sizeof(int);
+    sm.err = p;                                p += (size_t)(kChunk + 1) * 33 * sizeof(int);   // == (2 kChunk + 1) * 33 * 2 rounded up
     sm.epk = reinterpret_cast<uint32_t *>(p);  p += (size_t)kChunk * 33 * sizeof(uint32_t);
     sm.lut5 = p; sm.lut6 = p + 256;            p += 512;
     sm.win = reinterpret_cast<uint32_t *>(p);  p += (size_t)NP * 4;
@@ -101,7 +111,6 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   for (int s = tid; s <= HT; s += kThreads) sm.keys[s] = kEmpty;
   sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
   sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
-  if (tid < 33) sm.err[kChunk * 33 + tid] = kRejectedSmall;
   if (tid == 0) { s_count = 0; s_special = 0; }
   __syncthreads();
 
@@ -175,59 +184,76 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   }
   __syncthreads();
 
-  // ---- phase 2: position -> dense word id ------------------------------------------------------
   const int U = s_count;
-  for (int p = tid; p < NP; p += kThreads) {
-    const uint16_t slot = sm.pos_uid[p];
-    // out-of-frame positions: the all-rejected row when everything fits one chunk, otherwise an
-    // id no chunk contains
-    sm.pos_uid[p] = (slot != kNoPos) ? sm.slot_uid[slot] : (uint16_t)(U <= kChunk ? kChunk : kNoPos);
-  }
-  // (visibility of pos_uid is guaranteed by the barrier after the coefficient pass below)
-
-  // ---- phases 3-5 per chunk of distinct words ----------------------------------------------
   WinnerState ws[kTileX * kTileY / kWarps];   // this warp scans targets wid, wid+8, wid+16, wid+24
 #pragma unroll
   for (int q = 0; q < kTileX * kTileY / kWarps; ++q) winner_init(ws[q]);
-
-  for (int c0 = 0; c0 < U; c0 += kChunk) {
-    const int cn = min(kChunk, U - c0);
-    for (int u = tid; u < cn; u += kThreads) word_info(sm.ulist[c0 + u], sm.info[u]);
-    __syncthreads();
-
-    // evaluate: warp = one distinct word, lane = target
-    for (int u = wid; u < cn; u += kWarps) {
-      const uint32_t word = sm.ulist[c0 + u];
-      uint32_t packed;
-      sm.err[u * 33 + lane] = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6, &packed);
-      sm.epk[u * 33 + lane] = packed;
+  // Phases 2-5 for one representation of the (word, target) table.  Tiles whose words fit one
+  // evaluation chunk -- all but a handful on ordinary content -- keep the exact int32 table (this path
+  // is the headline's and must not pay for the other); word-diverse tiles use the int16 table, which
+  // holds twice the words per scan pass (see ErrTable).
+  auto run = [&](auto tag) {
+    constexpr bool kErr16 = decltype(tag)::value;
+    typedef typename ErrTable<kErr16>::type E;
+    constexpr int kWords = ErrTable<kErr16>::kWords;
+    E *const err = static_cast<E *>(sm.err);
+    if (tid < 33) err[kWords * 33 + tid] = (E)(kErr16 ? kErr16Max : kRejectedSmall);
+    // ---- phase 2: position -> dense word id ------------------------------------------------------
+    for (int p = tid; p < NP; p += kThreads) {
+      const uint16_t slot = sm.pos_uid[p];
+      // out-of-frame positions: the all-rejected row when everything fits one chunk, otherwise an
+      // id no chunk contains
+      sm.pos_uid[p] = (slot != kNoPos) ? sm.slot_uid[slot] : (uint16_t)(U <= kWords ? kWords : kNoPos);
     }
-    __syncthreads();
+    // (visibility of pos_uid is guaranteed by the barrier after the coefficient pass below)
 
-    // scan: each target walks its own window in the reference's order (j up, i up).
-    // Positions outside the frame (and, when the words do not fit one chunk, words of other
-    // chunks) read the all-rejected row kChunk.
-    const bool single = (U <= kChunk);
+    // ---- phases 3-5 per chunk of distinct words ----------------------------------------------
+
+    for (int c0 = 0; c0 < U; c0 += kWords) {
+      const int cn = min(kWords, U - c0);
+      // evaluate in sub-chunks of kChunk words (the per-word constants' scratch): warp = one distinct word, lane = target
+      for (int s0 = 0; s0 < cn; s0 += kChunk) {
+        const int sn = min(kChunk, cn - s0);
+        if (s0 > 0) __syncthreads();            // the previous sub-chunk's constants are no longer read
+        for (int u = tid; u < sn; u += kThreads) word_info(sm.ulist[c0 + s0 + u], sm.info[u]);
+        __syncthreads();
+        for (int u = wid; u < sn; u += kWarps) {
+          const uint32_t word = sm.ulist[c0 + s0 + u];
+          uint32_t packed;
+          const int e = eval_uniform(t, word, sm.info[u], sm.lut5, sm.lut6, &packed);
+          err[(s0 + u) * 33 + lane] = (E)(kErr16 ? (e < 0 ? -1 : min(e, kErr16Max)) : e);
+          if (c0 + s0 == 0) sm.epk[u * 33 + lane] = packed;   // the first kChunk words: enough when U <= kChunk
+        }
+      }
+      __syncthreads();
+
+      // scan: each target walks its own window in the reference's order (j up, i up).
+      // Positions outside the frame (and, when the words do not fit one chunk, words of other
+      // chunks) read the all-rejected row kWords.
+      const bool single = (U <= kWords);
 #pragma unroll
-    for (int q = 0; q < kTileX * kTileY / kWarps; ++q) {
-      const int tt = wid + q * kWarps;
-      const int ttx = tt & (kTileX - 1), tty = tt >> 3;
-      if (tx0 + ttx >= v.bw || ty0 + tty >= v.bh) continue;   // warp-uniform
-      const uint16_t *pos = sm.pos_uid + tty * UW + ttx;
-      if (single) scan_window<false>(ws[q], pos, UW, 1, sm.err + tt, W, 0, W, lane, 0, 0, kChunk);
-      else        scan_window<true>(ws[q], pos, UW, 1, sm.err + tt, W, 0, W, lane, c0, cn, kChunk);
+      for (int q = 0; q < kTileX * kTileY / kWarps; ++q) {
+        const int tt = wid + q * kWarps;
+        const int ttx = tt & (kTileX - 1), tty = tt >> 3;
+        if (tx0 + ttx >= v.bw || ty0 + tty >= v.bh) continue;   // warp-uniform
+        const uint16_t *pos = sm.pos_uid + tty * UW + ttx;
+        if (single) scan_window<false, E>(ws[q], pos, UW, 1, err + tt, W, 0, W, lane, 0, 0, kWords);
+        else        scan_window<true, E>(ws[q], pos, UW, 1, err + tt, W, 0, W, lane, c0, cn, kWords);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
 
-  // executed work (bench.py's roofline): every distinct word once per valid target, every window
-  // position of every valid target once per chunk pass
-  if (tid == 0) {
-    const unsigned long long nt = (unsigned long long)(min(kTileX, v.bw - tx0) * min(kTileY, v.bh - ty0));
-    atomicAdd(v.work + kWorkInterEvals, nt * (unsigned long long)U);
-    atomicAdd(v.work + kWorkInterScanned, nt * (unsigned long long)(W * W) * (unsigned long long)((U + kChunk - 1) / kChunk));
-    atomicAdd(v.work + kWorkInterTiles, 1ull);
-  }
+    // executed work (bench.py's roofline): every distinct word once per valid target, every window
+    // position of every valid target once per chunk pass
+    if (tid == 0) {
+      const unsigned long long nt = (unsigned long long)(min(kTileX, v.bw - tx0) * min(kTileY, v.bh - ty0));
+      atomicAdd(v.work + kWorkInterEvals, nt * (unsigned long long)U);
+      atomicAdd(v.work + kWorkInterScanned, nt * (unsigned long long)(W * W) * (unsigned long long)((U + kWords - 1) / kWords));
+      atomicAdd(v.work + kWorkInterTiles, 1ull);
+    }
+  };
+  if (U <= kChunk || thr >= kErr16Max) run(std::false_type());
+  else run(std::true_type());
 
   // ---- phase 6: resolve and apply ------------------------------------------------------------
 #pragma unroll
