@@ -37,7 +37,6 @@ constexpr uint16_t kNoPos = 0xFFFFu;          // window position outside the fra
 
 struct TileSmem {
   // dynamic shared memory carve-up (all sizes depend on search_area)
-  uint32_t *win;       // [NP]   index word of each union-window position
   uint16_t *pos_uid;   // [NP]   hash slot, then dense id of that position's word
   uint32_t *keys;      // [HT+1] open-addressing table of words
   uint16_t *slot_uid;  // [HT+1]
@@ -60,16 +59,15 @@ __host__ __device__ inline size_t tile_smem_bytes(int sa, int *np_out, int *ht_o
   const int HT = round_up_pow2(NP + NP / 4);
   if (np_out) *np_out = NP;
   if (ht_out) *ht_out = HT;
-  size_t b = 0;
-  b += (size_t)kChunk * sizeof(WordInfo);          // info (16-byte aligned first)
-  b += (size_t)(kChunk + 1) * 33 * sizeof(int);    // err
-  b += (size_t)kChunk * 33 * sizeof(uint32_t);     // epk
+  // {keys, slot_uid} are dead once every position has its dense word id (phase 2); {info, err,
+  // epk} are only written after that: the two groups share the same bytes, which (with the window's words
+  // no longer kept: the winner's word is ulist[its id]) lets two CTAs per SM run at search_area 32.
+  const size_t a = (((size_t)(HT + 1) * 4 + (size_t)(HT + 1) * 2) + 15) & ~(size_t)15;   // keys, slot_uid
+  const size_t e = (size_t)kChunk * sizeof(WordInfo) + (size_t)(kChunk + 1) * 33 * sizeof(int) + (size_t)kChunk * 33 * sizeof(uint32_t);
+  size_t b = a > e ? a : e;
   b += 512;                                        // lut5, lut6
-  b += (size_t)NP * 4;                             // win
-  b += (size_t)(HT + 1) * 4;                       // keys
   b += (size_t)NP * 4;                             // ulist
   b += (size_t)NP * 2;                             // pos_uid
-  b += (size_t)(HT + 1) * 2;                       // slot_uid
   return (b + 15) & ~(size_t)15;
 }
 
@@ -88,15 +86,19 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   TileSmem sm;
   {
     unsigned char *p = smem_raw;
-    sm.info = reinterpret_cast<WordInfo *>(p); p += (size_t)kChunk * sizeof(WordInfo);
-    sm.err = p;                                p += (size_t)(kChunk + 1) * 33 * sizeof(int);   // == (2 kChunk + 1) * 33 * 2 rounded up
-    sm.epk = reinterpret_cast<uint32_t *>(p);  p += (size_t)kChunk * 33 * sizeof(uint32_t);
+    const size_t a = (((size_t)(HT + 1) * 4 + (size_t)(HT + 1) * 2) + 15) & ~(size_t)15;
+    const size_t e = (size_t)kChunk * sizeof(WordInfo) + (size_t)(kChunk + 1) * 33 * sizeof(int) + (size_t)kChunk * 33 * sizeof(uint32_t);
+    // phases 3-6 (16-byte aligned first) ...
+    sm.info = reinterpret_cast<WordInfo *>(p);
+    sm.err = p + (size_t)kChunk * sizeof(WordInfo);   // (kChunk + 1) * 33 int32 == (2 kChunk + 1) * 33 int16 rounded up
+    sm.epk = reinterpret_cast<uint32_t *>(p + (size_t)kChunk * sizeof(WordInfo) + (size_t)(kChunk + 1) * 33 * sizeof(int));
+    // ... over the same bytes as phases 0-2
+    sm.keys = reinterpret_cast<uint32_t *>(p);
+    sm.slot_uid = reinterpret_cast<uint16_t *>(p + (size_t)(HT + 1) * 4);
+    p += a > e ? a : e;
     sm.lut5 = p; sm.lut6 = p + 256;            p += 512;
-    sm.win = reinterpret_cast<uint32_t *>(p);  p += (size_t)NP * 4;
-    sm.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)(HT + 1) * 4;
     sm.ulist = reinterpret_cast<uint32_t *>(p); p += (size_t)NP * 4;
-    sm.pos_uid = reinterpret_cast<uint16_t *>(p); p += (size_t)NP * 2;
-    sm.slot_uid = reinterpret_cast<uint16_t *>(p);
+    sm.pos_uid = reinterpret_cast<uint16_t *>(p);
   }
 
   const int f = v.first + blockIdx.y * v.gop + k_in_gop;
@@ -154,7 +156,6 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
       uint16_t slot = kNoPos;
       if (ok[q]) {
         const uint32_t word = wv[q];
-        sm.win[p] = word;
         // the thread that claims a slot also hands out the word's dense id
         if (word == kEmpty) {
           if (atomicExch(&s_special, 1) == 0) {
@@ -197,7 +198,6 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     typedef typename ErrTable<kErr16>::type E;
     constexpr int kWords = ErrTable<kErr16>::kWords;
     E *const err = static_cast<E *>(sm.err);
-    if (tid < 33) err[kWords * 33 + tid] = (E)(kErr16 ? kErr16Max : kRejectedSmall);
     // ---- phase 2: position -> dense word id ------------------------------------------------------
     for (int p = tid; p < NP; p += kThreads) {
       const uint16_t slot = sm.pos_uid[p];
@@ -205,7 +205,8 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
       // id no chunk contains
       sm.pos_uid[p] = (slot != kNoPos) ? sm.slot_uid[slot] : (uint16_t)(U <= kWords ? kWords : kNoPos);
     }
-    // (visibility of pos_uid is guaranteed by the barrier after the coefficient pass below)
+    __syncthreads();   // slot_uid / keys are dead from here on: their bytes become info / err / epk
+    if (tid < 33) err[kWords * 33 + tid] = (E)(kErr16 ? kErr16Max : kRejectedSmall);
 
     // ---- phases 3-5 per chunk of distinct words ----------------------------------------------
 
@@ -273,7 +274,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     uint8_t flag = 0;
     if (min_err <= thr) {
       const int at = ((lane >> 3) + row) * UW + (lane & (kTileX - 1)) + col;
-      const uint32_t word = sm.win[at];
+      const uint32_t word = sm.ulist[sm.pos_uid[at]];   // (the window's words themselves are gone: see tile_smem_bytes)
       // the winner's endpoints were computed when its word was evaluated: with a single chunk of
       // words the table still holds them and the block needs no second refit
       uint64_t blk;
