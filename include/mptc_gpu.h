@@ -67,6 +67,20 @@ int mptc_gpu_reencode(mptc_gpu_ctx *ctx, const uint8_t *rgb, int w, int h, int i
                       uint64_t *initial_out, uint64_t *blocks_out, uint8_t *motion_out,
                       uint32_t *unique_out, uint32_t *n_unique);
 
+/* Replaces DXTImage::InterPixelSearch (dxt_image.cpp:776-832) for every block of one frame: the
+ * pixel-granular inter search over the offsets of DXTImage::SetPattern(search_area) (dxt_image.h:135-164).
+ * The reference never calls it (commented out of Reencode, dxt_image.cpp:930-951), so this is a
+ * stand-alone analysis call and the sequence encode does not use it.  cur_blocks = the frame's blocks at
+ * the time of the call (NULL: the stb fit of `rgb`, i.e. the state before Reencode); prev_blocks = the
+ * reference frame's final blocks.  Per block: min_err (0 if a candidate with err_diff <= 0 exists, else
+ * the smallest err_diff, INT32_MAX if nothing was accepted), motion = (i + 64, j + 64) of the winning
+ * offset, the winning index word, re_assigned.  Any output may be NULL.  The candidate word is the 16
+ * gathered indices as they are: the reference's Get4X4InterpolationBlock (:619-634) reads uninitialised
+ * memory on the way (see mptc_pixel.cu). */
+int mptc_gpu_inter_pixel_search(mptc_gpu_ctx *ctx, const uint8_t *rgb, int w, int h, int search_area,
+                                const uint64_t *cur_blocks, const uint64_t *prev_blocks, int32_t *min_err_out,
+                                uint8_t *motion_out, uint32_t *index_out, uint8_t *reassigned_out);
+
 /* Replaces CompressEndpoint up to (not including) the arithmetic coder: EndpointOne/TwoValues
  * -> RGB565toYCoCg667 -> FWavelet2D<.,64> -> MakeUnsigned -> Linearize (dxt_image.cpp:496-530,
  * codec.cpp:804-839, :598-614).  planes_out: 6*pbw*pbh bytes. */

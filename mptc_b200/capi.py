@@ -23,7 +23,7 @@ EXPORTS = [
     "mptc_gpu_host_alloc", "mptc_gpu_host_free", "mptc_gpu_last_candidate_count", "mptc_gpu_set_schedule",
     "mptc_gpu_encode_sequence_async", "mptc_gpu_wait_frame", "mptc_gpu_wait",
     "mptc_gpu_decode_sequence", "mptc_gpu_seq_decode_upload", "mptc_gpu_seq_decode",
-    "mptc_gpu_seq_decode_download", "mptc_gpu_last_decode_ms", "mptc_gpu_last_work_count",
+    "mptc_gpu_seq_decode_download", "mptc_gpu_last_decode_ms", "mptc_gpu_last_work_count", "mptc_gpu_inter_pixel_search",
 ]
 DECODE_STAGES = {"total": 0, "words": 1, "planes": 2, "rgb": 3}
 
@@ -78,6 +78,7 @@ def load():
     L.mptc_gpu_last_candidate_count.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.mptc_gpu_set_schedule.argtypes = [vp, ci, ci, ci]
     L.mptc_gpu_last_work_count.argtypes = [vp, C.POINTER(C.c_uint64), ci]
+    L.mptc_gpu_inter_pixel_search.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp]
     L.mptc_gpu_decode_sequence.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, ci, ci, ci, ci, ci, vp, vp]
     L.mptc_gpu_seq_decode_upload.argtypes = [vp, ci, ci, vp, vp, vp, C.c_size_t, vp]
     L.mptc_gpu_seq_decode.argtypes = [vp, ci, ci, ci, ci, ci]
@@ -204,6 +205,23 @@ class Context:
                                               blocks.ctypes.data, motion.ctypes.data, unique.ctypes.data,
                                               C.addressof(nu)))
         return {"initial": initial, "blocks": blocks, "motion": motion, "unique": unique[: nu.value].copy()}
+
+    def inter_pixel_search(self, rgb, search_area, prev_blocks, cur_blocks=None):
+        """DXTImage::InterPixelSearch for every block -> dict(min_err, motion, index, reassigned)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        h, w = rgb.shape[:2]
+        nb = (h // 4) * (w // 4)
+        prev_blocks = np.ascontiguousarray(prev_blocks, dtype=np.uint64)
+        if cur_blocks is not None:
+            cur_blocks = np.ascontiguousarray(cur_blocks, dtype=np.uint64)
+        out = {"min_err": np.empty(nb, np.int32), "motion": np.empty(2 * nb, np.uint8), "index": np.empty(nb, np.uint32),
+               "reassigned": np.empty(nb, np.uint8)}
+        self._check(self._L.mptc_gpu_inter_pixel_search(self._p, rgb.ctypes.data, w, h, search_area, _ptr(cur_blocks),
+                                                        prev_blocks.ctypes.data, out["min_err"].ctypes.data,
+                                                        out["motion"].ctypes.data, out["index"].ctypes.data,
+                                                        out["reassigned"].ctypes.data))
+        self.w = self.h = self.nb = 0   # the reserved sequence was re-purposed
+        return out
 
     def endpoint_planes(self, blocks, bw, bh) -> np.ndarray:
         blocks = np.ascontiguousarray(blocks, dtype=np.uint64)

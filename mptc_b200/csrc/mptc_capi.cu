@@ -38,6 +38,8 @@ struct mptc_gpu_ctx {
   uint32_t *d_unique = nullptr, *d_nunique = nullptr, *d_chunks = nullptr;
   int *d_progress = nullptr;
   unsigned long long *d_wordflag = nullptr;
+  int8_t *d_pattern = nullptr;   // K2p: pixel offsets of DXTImage::SetPattern for pattern_sa
+  int pattern_sa = 0, pattern_n = 0;
   uint32_t epoch = 0;            // one per encode call: validity tag of the wavefront's hand-over entries
   unsigned long long *d_cand = nullptr;
   int max_wave_ctas = 0;
@@ -476,6 +478,7 @@ void mptc_gpu_destroy(mptc_gpu_ctx *c) {
   cudaDeviceSynchronize();
   free_seq(c);
   cudaFree(c->d_cand);
+  cudaFree(c->d_pattern);
   for (void *p : c->pinned) if (p) cudaFreeHost(p);
   for (auto &L : c->lanes) {
     for (auto &e : L.stage_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -671,6 +674,51 @@ int mptc_gpu_reencode(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, int is_
   CU(c, cudaStreamSynchronize(s));
   if (unique_out && nu) CU(c, cudaMemcpy(unique_out, c->d_unique + off, (size_t)nu * 4, cudaMemcpyDeviceToHost));
   if (n_unique) *n_unique = nu;
+  return MPTC_OK;
+}
+
+int mptc_gpu_inter_pixel_search(mptc_gpu_ctx *c, const uint8_t *rgb, int w, int h, int search_area,
+                                const uint64_t *cur_blocks, const uint64_t *prev_blocks, int32_t *min_err_out,
+                                uint8_t *motion_out, uint32_t *index_out, uint8_t *reassigned_out) {
+  if (!c || !rgb || !prev_blocks) return MPTC_E_ARG;
+  if (int r = check_params(c, search_area, 1)) return r;
+  if (int r = mptc_gpu_seq_reserve(c, w, h, 2)) return r;
+  cudaStream_t s = c->s_compute;
+  if (c->pattern_sa != search_area) {   // the ring pattern of DXTImage::SetPattern, once per search area
+    std::vector<int8_t> pat((size_t)2 * inter_pixel_pattern(search_area, nullptr));
+    c->pattern_n = inter_pixel_pattern(search_area, pat.data());
+    CU(c, cudaStreamSynchronize(s));
+    cudaFree(c->d_pattern);
+    c->d_pattern = nullptr;
+    c->pattern_sa = 0;
+    CU(c, cudaMalloc(&c->d_pattern, pat.size()));
+    CU(c, cudaMemcpy(c->d_pattern, pat.data(), pat.size(), cudaMemcpyHostToDevice));
+    c->pattern_sa = search_area;
+  }
+  // slot 0 = the reference frame (only its final blocks matter), slot 1 = this frame
+  const size_t nb = (size_t)c->nb;
+  if (int r = mptc_gpu_seq_upload(c, rgb, 1, 1)) return r;
+  CU(c, cudaMemcpyAsync(c->d_final, prev_blocks, nb * 8, cudaMemcpyHostToDevice, s));
+  if (cur_blocks) {
+    CU(c, cudaMemcpyAsync(c->d_init + nb, cur_blocks, nb * 8, cudaMemcpyHostToDevice, s));
+  } else {   // the block's state before Reencode: the stb fit
+    SeqView v = view_of(c, 1, 1, 1);
+    launch_dxt1_fit(v, 1, 1, 1, s);
+    ++c->launches;
+  }
+  int32_t *d_err = reinterpret_cast<int32_t *>(c->d_unique);   // scratch: the sequence's result slots
+  uint32_t *d_index = c->d_unique + nb;
+  uint8_t *d_mo = c->d_motion + nb * 2, *d_re = c->d_flags + nb;
+  launch_inter_pixel_search(c->d_rgb + c->frame_bytes, w, h, search_area, c->pattern_n, c->d_pattern, c->d_init + nb, c->d_final,
+                            d_err, d_mo, d_index, d_re, s);
+  ++c->launches;
+  CU(c, cudaGetLastError());
+  if (min_err_out) CU(c, cudaMemcpyAsync(min_err_out, d_err, nb * 4, cudaMemcpyDeviceToHost, s));
+  if (motion_out) CU(c, cudaMemcpyAsync(motion_out, d_mo, nb * 2, cudaMemcpyDeviceToHost, s));
+  if (index_out) CU(c, cudaMemcpyAsync(index_out, d_index, nb * 4, cudaMemcpyDeviceToHost, s));
+  if (reassigned_out) CU(c, cudaMemcpyAsync(reassigned_out, d_re, nb, cudaMemcpyDeviceToHost, s));
+  CU(c, cudaStreamSynchronize(s));
+  c->encoded = false;   // the scratch slots no longer hold an encode's results
   return MPTC_OK;
 }
 

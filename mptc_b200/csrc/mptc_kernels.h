@@ -70,6 +70,12 @@ void launch_compact_unique(const SeqView &v, int sa, unsigned long long *cand_co
 void launch_endpoint_planes(const SeqView &v, int pbw, int pbh, int f0, int fstride, int nf, cudaStream_t s);
 int intra_wavefront_max_ctas(int device);
 
+// ---- K2p: pixel-granular inter search (mptc_pixel.cu) ------------------------------------------------
+int inter_pixel_pattern(int sa, int8_t *ij);   // DXTImage::SetPattern order; returns the number of offsets
+void launch_inter_pixel_search(const uint8_t *frame, int w, int h, int sa, int n_pat, const int8_t *pat,
+                               const uint64_t *cur_blocks, const uint64_t *prev_blocks, int32_t *min_err,
+                               uint8_t *motion, uint32_t *index, uint8_t *reassigned, cudaStream_t s);
+
 // ---- decoder side (mptc_decode.cu) -------------------------------------------------------
 // Frames [first, first + count) of the device-resident sequence, every gop-th one intra.
 struct DecView {

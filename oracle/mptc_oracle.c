@@ -397,6 +397,76 @@ int mptc_oracle_reencode(const uint8_t *rgb, int w, int h, int is_intra, int sa,
 /* Decoder-side index reconstruction (ReconstructDXTData, codec/codec.cpp:441-500): rebuilds
  * every block's interp word from the motion bytes, the unique list and the previous
  * frame's words.  Returns the number of unique words consumed, or -1 on a bad vector. */
+/* ---- DXTImage::InterPixelSearch (dxt_image.cpp:776-832; call site commented out at :930-951) ---------
+ * Pixel-granular inter search: candidate index words are 4x4 cut-outs of the previous frame's index
+ * picture at pixel offsets (i, j) in the order of DXTImage::SetPattern (dxt_image.h:135-164).
+ *
+ * UNDEFINED BEHAVIOUR IN THE REFERENCE: Get4X4InterpolationBlock (dxt_image.cpp:619-634) fills only
+ * the indices of a LogicalDXTBlock and passes it to LogicalToPhysical, which decides whether to flip
+ * the word (^= 0x55555555) from the block's UNINITIALISED endpoints / palette (:150-170).  Compiled
+ * with the canonical flags of oracle/Makefile (-O3 -DNDEBUG, as with -O0) g++ 13 leaves the word
+ * unflipped; -O2 flips every word (probed).  This restatement follows the canonical build: the 16
+ * gathered 2-bit indices packed as they are. */
+int mptc_oracle_ips_pattern(int sa, int8_t *ij /* 2 * count, may be NULL */) {
+  int n = 0;
+#define PUSH(x, y) do { if (ij) { ij[2 * n] = (int8_t)(x); ij[2 * n + 1] = (int8_t)(y); } ++n; } while (0)
+  PUSH(0, 0);
+  for (int level = 1; level < sa; ++level)
+    for (int cur = level; cur >= -level; --cur) {
+      if (cur == level) { for (int x = cur; x >= -cur; --x) PUSH(x, cur); }
+      else if (cur == -level) { for (int x = cur; x <= -cur; ++x) PUSH(x, cur); }
+      else { PUSH(level, cur); PUSH(-level, cur); }
+    }
+#undef PUSH
+  return n;
+}
+
+static uint32_t gather_word(const uint64_t *prev, int bw, int x, int y) { /* Get4X4InterpolationBlock, canonical build */
+  uint32_t word = 0;
+  for (int v = 0; v < 4; ++v)
+    for (int u = 0; u < 4; ++u) {
+      int px = x + u, py = y + v;
+      uint32_t interp = (uint32_t)(prev[(py >> 2) * bw + (px >> 2)] >> 32);
+      uint32_t idx = (interp >> (2 * ((py & 3) * 4 + (px & 3)))) & 3u; /* InterpolationValueAt :604-608 */
+      word |= idx << (2 * (4 * v + u));
+    }
+  return word;
+}
+
+void mptc_oracle_inter_pixel_search(const uint8_t *rgb, int w, int h, int sa, const uint64_t *cur_blocks,
+                                    const uint64_t *prev_blocks, int32_t *min_err_out, uint8_t *motion_out,
+                                    uint32_t *index_out, uint8_t *reassigned_out) {
+  const int bw = w / 4, bh = h / 4;
+  const int n = mptc_oracle_ips_pattern(sa, NULL);
+  int8_t *pat = (int8_t *)malloc((size_t)2 * n);
+  mptc_oracle_ips_pattern(sa, pat);
+  for (int b = 0; b < bw * bh; ++b) {
+    const int bx = b % bw, by = b / bw;
+    uint8_t px[16][3];
+    load_block(rgb, w, bx, by, px);
+    int min_err = INT_MAX, mx = 0, my = 0, re = 0;
+    uint32_t index = 0;
+    for (int k = 0; k < n; ++k) {
+      const int i = pat[2 * k], j = pat[2 * k + 1];
+      const int x = 4 * bx + i, y = 4 * by + j;
+      if (!(x >= 0 && x <= w - 4 && y >= 0 && y <= h - 4)) continue;              /* :795 */
+      const uint32_t word = gather_word(prev_blocks, bw, x, y);
+      int ed;
+      if (!mptc_oracle_eval_candidate(&px[0][0], cur_blocks[b], word, &ed, NULL)) continue;   /* :800-813 */
+      if (ed < min_err) {                                                            /* :816-825 */
+        min_err = ed; mx = i + 64; my = j + 64; index = word;
+        re = word != (uint32_t)(cur_blocks[b] >> 32);
+        if (ed <= 0) { min_err = 0; break; }
+      }
+    }
+    min_err_out[b] = min_err;
+    motion_out[2 * b] = (uint8_t)mx; motion_out[2 * b + 1] = (uint8_t)my;
+    index_out[b] = index;
+    reassigned_out[b] = (uint8_t)re;
+  }
+  free(pat);
+}
+
 int mptc_oracle_reconstruct_words(const uint8_t *motion, const uint32_t *unique, int n_unique,
                                   const uint32_t *prev_words, int bw, int bh, int sa, uint32_t *out) {
   int nu = 0;

@@ -32,6 +32,17 @@ int mptc_oracle_reencode(const uint8_t *rgb, int w, int h, int is_intra, int sea
 int mptc_oracle_eval_candidate(const uint8_t *pixels48, uint64_t own_block, uint32_t cand_word,
                                int *err_diff, uint64_t *new_block);
 
+/* DXTImage::InterPixelSearch (dxt_image.cpp:776-832) for every block of a frame, each against the
+ * previous frame's final blocks: min_err (INT_MAX if nothing was accepted), motion = (i + 64, j + 64)
+ * of the winning pixel offset, the winning index word and re_assigned.  cur_blocks = the frame's
+ * blocks at the time of the call (the initial stb fit when called before Reencode).  Follows the
+ * reference as compiled with the canonical flags (see the UB note in mptc_oracle.c). */
+void mptc_oracle_inter_pixel_search(const uint8_t *rgb, int w, int h, int sa, const uint64_t *cur_blocks,
+                                    const uint64_t *prev_blocks, int32_t *min_err_out, uint8_t *motion_out,
+                                    uint32_t *index_out, uint8_t *reassigned_out);
+/* DXTImage::SetPattern (dxt_image.h:135-164): the pixel offsets in search order; returns their count. */
+int mptc_oracle_ips_pattern(int sa, int8_t *ij);
+
 /* Decoder-side word reconstruction (ReconstructDXTData, codec.cpp:441-500); returns the
  * number of unique words consumed or -1 if a motion vector is invalid. */
 int mptc_oracle_reconstruct_words(const uint8_t *motion, const uint32_t *unique, int n_unique,

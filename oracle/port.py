@@ -39,6 +39,8 @@ def lib():
         L.mptc_oracle_tables.argtypes = [vp, vp]
         L.mptc_oracle_reconstruct_words.argtypes = [vp, vp, ci, vp, ci, ci, ci, vp]
         L.mptc_oracle_check_blocks.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci]
+        L.mptc_oracle_inter_pixel_search.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+        L.mptc_oracle_ips_pattern.argtypes = [ci, vp]
         L.mptc_oracle_encode_gops.restype = C.c_double
         L.mptc_oracle_encode_gops.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, vp, vp]
         _lib = L
@@ -68,6 +70,30 @@ def reencode(rgb, is_intra, search_area, err_threshold, init_blocks, prev_blocks
     n = lib().mptc_oracle_reencode(rgb.ctypes.data, w, h, int(is_intra), search_area, err_threshold,
                                    blocks.ctypes.data, pp, motion.ctypes.data, unique.ctypes.data)
     return blocks, motion, unique[:n].copy()
+
+
+def inter_pixel_search(rgb, search_area, cur_blocks, prev_blocks):
+    """DXTImage::InterPixelSearch for every block -> dict(min_err i32[nb], motion u8[2nb], index u32[nb],
+    reassigned u8[nb])."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    h, w = rgb.shape[:2]
+    cur = np.ascontiguousarray(cur_blocks, dtype=np.uint64)
+    prev = np.ascontiguousarray(prev_blocks, dtype=np.uint64)
+    nb = cur.size
+    out = {"min_err": np.empty(nb, np.int32), "motion": np.empty(2 * nb, np.uint8), "index": np.empty(nb, np.uint32),
+           "reassigned": np.empty(nb, np.uint8)}
+    lib().mptc_oracle_inter_pixel_search(rgb.ctypes.data, w, h, search_area, cur.ctypes.data, prev.ctypes.data,
+                                         out["min_err"].ctypes.data, out["motion"].ctypes.data, out["index"].ctypes.data,
+                                         out["reassigned"].ctypes.data)
+    return out
+
+
+def ips_pattern(search_area) -> np.ndarray:
+    """DXTImage::SetPattern: (n, 2) int8 pixel offsets (i, j) in search order."""
+    n = lib().mptc_oracle_ips_pattern(search_area, None)
+    out = np.empty((n, 2), np.int8)
+    lib().mptc_oracle_ips_pattern(search_area, out.ctypes.data)
+    return out
 
 
 def endpoint_planes(blocks, bw, bh) -> np.ndarray:

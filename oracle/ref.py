@@ -42,6 +42,8 @@ def lib():
         L.mptc_ref_compress_multi_unique.argtypes = [C.c_char_p, C.c_char_p, C.c_uint, C.c_int, C.c_uint, C.c_uint]
         L.mptc_ref_selfcheck_png.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.mptc_ref_write_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        L.mptc_ref_inter_pixel_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mptc_ref_inter_pixel_search_defined.argtypes = L.mptc_ref_inter_pixel_search.argtypes
         L.mptc_ref_quiet()
         _lib = L
     return _lib
@@ -79,6 +81,19 @@ class RefFrame:
         out = np.empty(n, dtype=np.uint32)
         if n:
             lib().mptc_ref_get_unique(self._p, out.ctypes.data)
+        return out
+
+    def inter_pixel_search(self, prev: "RefFrame", search_area: int, defined: bool = True):
+        """DXTImage::InterPixelSearch (dxt_image.cpp:776-832) for every block against `prev`.
+        defined=True: the loop over the reference's own CompressedBlock methods with the candidate word
+        built without the undefined behaviour of Get4X4InterpolationBlock (see oracle/ref_wrap.cpp);
+        defined=False: the compiled function as it is (its results depend on stack garbage)."""
+        nb = self.nb
+        out = {"min_err": np.empty(nb, np.int32), "motion": np.empty(2 * nb, np.uint8), "index": np.empty(nb, np.uint32),
+               "reassigned": np.empty(nb, np.uint8)}
+        fn = lib().mptc_ref_inter_pixel_search_defined if defined else lib().mptc_ref_inter_pixel_search
+        fn(self._p, prev._p, search_area, out["min_err"].ctypes.data, out["motion"].ctypes.data,
+                                          out["index"].ctypes.data, out["reassigned"].ctypes.data)
         return out
 
     def psnr_logical(self) -> float:

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <limits>
 #include <unistd.h>
 
 namespace MPTC {
@@ -290,6 +291,82 @@ int mptc_ref_decode_stream(const uint8_t *stream, int nbytes, uint64_t *blocks_o
     }
   }
   return (int)frame_number;
+}
+
+// DXTImage::InterPixelSearch (dxt_image.cpp:776-832) for every block of `p` against `prev`, with the
+// pattern of SetPattern(search_area) (dxt_image.h:135-164).  The function is compiled into the reference
+// but its call site in Reencode is commented out (:930-951).
+void mptc_ref_inter_pixel_search(void *p, void *prev, int search_area, int32_t *min_err_out, uint8_t *motion_out,
+                                 uint32_t *index_out, uint8_t *reassigned_out) {
+  RefFrame *f = static_cast<RefFrame *>(p);
+  RefFrame *r = static_cast<RefFrame *>(prev);
+  DXTImage::SetPattern(search_area);
+  const int nb = f->img->_num_blocks;
+  for (int b = 0; b < nb; ++b) {
+    MPTC::CompressedBlock blk;
+    bool re = false;
+    int32_t x = 0, y = 0;
+    uint32_t index = 0;
+    min_err_out[b] = f->img->InterPixelSearch(r->img, b, x, y, -1, index, blk, re);
+    motion_out[2 * b] = (uint8_t)x;
+    motion_out[2 * b + 1] = (uint8_t)y;
+    index_out[b] = index;
+    reassigned_out[b] = re ? 1 : 0;
+  }
+}
+
+// The same search with the reference's undefined behaviour removed.  Get4X4InterpolationBlock
+// (dxt_image.cpp:619-634) hands a LogicalDXTBlock whose endpoints and palette were never initialised to
+// LogicalToPhysical, which flips the gathered word (^= 0x55555555) or not depending on that stack
+// garbage (:150-170): inside InterPixelSearch the garbage is whatever the previous candidate left
+// there, so the compiled function's results are not a function of its inputs.  This variant runs the
+// loop of InterPixelSearch (:790-829) over the reference's own CompressedBlock methods
+// (AssignIndices, operator==, RecalculateEndpoints, Error, LogicalToPhysical) with the candidate word
+// built from InterpolationValueAt (:604-608) directly -- the 16 gathered indices, never flipped.
+void mptc_ref_inter_pixel_search_defined(void *p, void *prev, int search_area, int32_t *min_err_out,
+                                         uint8_t *motion_out, uint32_t *index_out, uint8_t *reassigned_out) {
+  RefFrame *f = static_cast<RefFrame *>(p);
+  RefFrame *r = static_cast<RefFrame *>(prev);
+  DXTImage::SetPattern(search_area);
+  DXTImage &img = *f->img;
+  for (int b = 0; b < img._num_blocks; ++b) {
+    const int block_x = b % img._blocks_width, block_y = b / img._blocks_width;
+    MPTC::CompressedBlock blk;
+    blk._logical = img._logical_blocks[b];
+    blk._uncompressed = img.Get4X4ColorsBlock(4 * block_x, 4 * block_y);
+    const int orig_err = static_cast<int>(blk.Error());
+    int min_err = std::numeric_limits<int>::max();
+    int32_t mx = 0, my = 0;
+    uint32_t index = 0;
+    bool re = false;
+    for (auto val : DXTImage::_search_pattern) {
+      const int i = std::get<0>(val), j = std::get<1>(val);
+      const int x = 4 * block_x + i, y = 4 * block_y + j;
+      if (!(x >= 0 && x <= img._width - 4 && y >= 0 && y <= img._height - 4)) continue;
+      uint32_t indices = 0;
+      for (int v = 0; v < 4; ++v)
+        for (int u = 0; u < 4; ++u) indices |= (uint32_t)r->img->InterpolationValueAt(x + u, y + v) << (2 * (4 * v + u));
+      MPTC::CompressedBlock blk2 = blk;
+      blk2.AssignIndices(indices);
+      bool reset = false;
+      if (!(blk2 == blk)) {
+        blk2.RecalculateEndpoints();
+        reset = true;
+        PhysicalDXTBlock maybe = MPTC::LogicalToPhysical(blk2._logical);
+        if (!(maybe.interp == indices && blk2._logical.palette[3][3] == 0xFF)) continue;
+      }
+      const int err_diff = static_cast<int>(blk2.Error()) - orig_err;
+      if (err_diff < min_err) {
+        min_err = err_diff; mx = i + 64; my = j + 64; index = indices; re = reset;
+        if (err_diff <= 0) { min_err = 0; break; }
+      }
+    }
+    min_err_out[b] = min_err;
+    motion_out[2 * b] = (uint8_t)mx;
+    motion_out[2 * b + 1] = (uint8_t)my;
+    index_out[b] = index;
+    reassigned_out[b] = re ? 1 : 0;
+  }
 }
 
 // Proves the supplied raw constructor == the reference's PNG constructor

@@ -89,9 +89,34 @@ def decode_fixture():
     print("wrote decode fixture", blocks.shape)
 
 
+def inter_pixel_fixture():
+    """DXTImage::InterPixelSearch (dxt_image.cpp:776-832), every block of the second frame of two small
+    sequences against the first frame's final blocks: the loop run over the reference's own
+    CompressedBlock methods with the candidate word built without the undefined behaviour of
+    Get4X4InterpolationBlock (oracle/ref_wrap.cpp, mptc_ref_inter_pixel_search_defined)."""
+    out = {}
+    for name, (w, h, seed, sa) in {"a": (128, 96, 11, 4), "b": (96, 64, 5, 16)}.items():
+        fr = make_sequence(w, h, 2, seed=seed)
+        a = ref.RefFrame(fr[0], True, sa, 50)
+        a.reencode(None)
+        b = ref.RefFrame(fr[1], False, sa, 50)
+        r = b.inter_pixel_search(a, sa)
+        ub = b.inter_pixel_search(a, sa, defined=False)
+        out[f"{name}_params"] = np.array([w, h, seed, sa], dtype=np.int64)
+        out[f"{name}_prev"] = a.blocks()
+        out[f"{name}_cur"] = b.blocks()
+        for k, v in r.items():
+            out[f"{name}_{k}"] = v
+        out[f"{name}_ub_agrees"] = np.array(int((ub["index"] == r["index"]).sum()))   # for the record
+    np.savez_compressed(os.path.join(HERE, "inter_pixel_search.npz"), **out)
+    print("wrote inter_pixel_search")
+
+
 def main():
     if "--decode-only" in sys.argv:
         return decode_fixture()
+    if "--inter-pixel-only" in sys.argv:
+        return inter_pixel_fixture()
     assert ref.available(), "build oracle/_ref first: make -C oracle ref"
     assert ref.selfcheck_png(make_sequence(64, 64, 1)[0]) == 0
     for name, cfg in CASES.items():
@@ -120,6 +145,7 @@ def main():
                         frames_sha=np.array(sha(frames)), stream=np.frombuffer(stream, dtype=np.uint8))
     print("wrote stream", len(stream), "bytes")
     decode_fixture()
+    inter_pixel_fixture()
 
 
 if __name__ == "__main__":

@@ -147,3 +147,20 @@ def test_decoded_pictures_match_the_reference_decoder():
         rgb = port.decode_rgb(decoded[i], w, h)
         assert sha(rgb) == str(d["rgb_sha"][i]), f"frame {i}"
     assert np.array_equal(port.decode_rgb(decoded[-1], w, h)[:16], d["rgb_last_rows"])
+
+
+def test_inter_pixel_search_port_equals_reference_fixture():
+    """mptc_oracle_inter_pixel_search against the fixture produced by the reference's own CompressedBlock
+    methods (DXTImage::InterPixelSearch, dxt_image.cpp:776-832, with the undefined behaviour of
+    Get4X4InterpolationBlock removed: tests/golden/gen_golden.py inter_pixel_fixture)."""
+    from mptc_b200.synth import make_sequence
+    g = load("inter_pixel_search")
+    for name in ("a", "b"):
+        w, h, seed, sa = [int(x) for x in g[f"{name}_params"]]
+        fr = make_sequence(w, h, 2, seed=seed)
+        assert np.array_equal(port.dxt1_fit(fr[1]), g[f"{name}_cur"])
+        got = port.inter_pixel_search(fr[1], sa, g[f"{name}_cur"], g[f"{name}_prev"])
+        for k in ("min_err", "motion", "index", "reassigned"):
+            assert np.array_equal(got[k], g[f"{name}_{k}"]), (name, k)
+        n = port.ips_pattern(sa)
+        assert n.shape[0] == 1 + 4 * sa * (sa - 1) and tuple(n[0]) == (0, 0) and np.abs(n).max() == sa - 1

@@ -76,3 +76,18 @@ def test_decoder_restatement_equals_reference_decoder():
     assert np.array_equal(port.decode_stream(stream), blocks)
     for i in range(n):
         assert np.array_equal(port.decode_rgb(blocks[i], w, h), rgb[i])
+
+
+def test_inter_pixel_search_port_vs_reference_methods():
+    """The C restatement against the loop of DXTImage::InterPixelSearch run over the reference's own
+    CompressedBlock methods (defined variant, oracle/ref_wrap.cpp)."""
+    from mptc_b200.synth import make_sequence
+    for w, h, sa, seed in [(64, 48, 2, 1), (128, 64, 8, 3), (64, 64, 20, 9)]:
+        fr = make_sequence(w, h, 2, seed=seed)
+        a = ref.RefFrame(fr[0], True, sa, 50)
+        a.reencode(None)
+        b = ref.RefFrame(fr[1], False, sa, 50)
+        want = b.inter_pixel_search(a, sa)
+        got = port.inter_pixel_search(fr[1], sa, b.blocks(), a.blocks())
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (w, h, sa, k)
