@@ -21,6 +21,8 @@
 #include "mptc_kernels.h"
 #include "mptc_device.cuh"
 
+#include <cstdlib>
+
 namespace mptc {
 
 namespace {
@@ -215,10 +217,13 @@ k_inverse_planes(DecView v) {
 // ------------------------------------------------------------------------------------------
 constexpr int kRun = 128;
 
-template <bool VEC16>
+// Store modes of the staged rows: 0 = 4-byte words (any width), 1 = 16-byte words, 2 = one bulk
+// asynchronous copy per pixel row (cp.async.bulk shared -> global, issued by one thread: the copy
+// engine streams the 1536-byte row while the CTA retires).  1 and 2 need w % 16 == 0.
+template <int MODE>
 __global__ void __launch_bounds__(kRun)
 k_dxt1_to_rgb(DecView v, int runs_x, int n_runs) {
-  __shared__ __align__(16) uint32_t rows[2][4][kRun * 3];
+  __shared__ __align__(128) uint32_t rows[2][4][kRun * 3];
   int buf = 0;
   for (int run = blockIdx.x; run < n_runs; run += gridDim.x, buf ^= 1) {
     const int fi = run / (runs_x * v.bh), rr = run - fi * runs_x * v.bh;
@@ -245,9 +250,22 @@ k_dxt1_to_rgb(DecView v, int runs_x, int n_runs) {
         rows[buf][j][3 * threadIdx.x + 2] = (c[2] >> 16) | (c[3] << 8);
       }
     }
+    if (MODE == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the rows, for the copy engine
     __syncthreads();   // one barrier per run: the next run fills the other buffer
     uint8_t *frame = v.rgb + (size_t)f * v.w * v.h * 3;
-    if (VEC16) {       // w % 16 == 0: every run row starts 16-byte aligned, 3*nrun/4 uint4 per row
+    if (MODE == 2) {   // every run row is a 16-byte aligned multiple of 16 bytes, contiguous in the frame
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint8_t *dst = frame + ((size_t)(4 * by + j) * v.w + 4 * bx0) * 3;
+          const uint32_t src = (uint32_t)__cvta_generic_to_shared(rows[buf][j]);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(12 * nrun) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // the buffer two runs back (and, before the CTA retires, this one) must have been read
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else if (MODE == 1) {   // 3*nrun/4 uint4 per row
       const int per_row = 3 * nrun / 4;
       for (int i = threadIdx.x; i < 4 * per_row; i += kRun) {
         const int j = i / per_row, c = i - j * per_row;
@@ -301,10 +319,15 @@ int launch_dxt1_to_rgb(const DecView &v, cudaStream_t s) {
   const int runs_x = (v.bw + kRun - 1) / kRun;
   const long long n_runs = (long long)runs_x * v.bh * v.count;
   // one run per CTA: measured 3.2 TB/s against 2.95 TB/s for 16 persistent CTAs per SM looping over
-  // runs and 3.1 TB/s with 4-byte stores (profiles/micro/rgb_ab.py; write-only fill peak 3.86 TB/s)
+  // runs and 3.1 TB/s with 4-byte stores (profiles/micro/rgb_ab.py).  Round 2: the rows leave through
+  // cp.async.bulk (UBLKCP in the SASS) instead of 16-byte stores: 3.27 -> 4.26 TB/s = 0.65 of the
+  // measured copy peak; 86 % of the traffic are writes, 3.65 TB/s of them against the 3.86 TB/s a
+  // write-only fill reaches on the same box (profiles/micro/write_bw.py) -- 94 % of the write ceiling.
   const int ctas = (int)(n_runs < 0x7fffffff ? n_runs : 0x7fffffff);
-  if (v.w % 16 == 0) k_dxt1_to_rgb<true><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
-  else k_dxt1_to_rgb<false><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
+  static const int mode16 = [] { const char *e = getenv("MPTC_RGB_STORE"); return (e && e[0] == 'v') ? 1 : 2; }();   // v = 16-byte words
+  if (v.w % 16 != 0) k_dxt1_to_rgb<0><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
+  else if (mode16 == 2) k_dxt1_to_rgb<2><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
+  else k_dxt1_to_rgb<1><<<ctas, kRun, 0, s>>>(v, runs_x, (int)n_runs);
   return 1;
 }
 
