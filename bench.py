@@ -498,6 +498,26 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         }
         # BASELINE configs[2] geometry: 4K, host entropy coding overlapped (4 GOPs per GPU)
         legs["4k"] = leg(3840, 2160, 4 * GOP, 4 * GOP * rank, SA, THR, "clean", True, parity=True)
+        # BASELINE configs[4]: 4K x 600 frames in all, GOP-sharded over the GPUs (strong scaling).  Only under
+        # torchrun (the whole job on one GPU is 15 GB of frames); the single-GPU yardstick is the `4k` leg
+        # of the N = 1 run (same geometry, >= 4 GOPs per GPU, no collective).
+        n_gops_total = 600 // GOP
+        if world > 1 and n_gops_total % world == 0:
+            per_rank = n_gops_total // world * GOP
+            x = measure(3840, 2160, per_rank, per_rank * rank, SA, THR, "clean", steps=2, warmup=1, want_stream=True,
+                        want_parity=(rank == 0))
+            pix = 600 * 3840 * 2160
+            legs["4k600_strong"] = {
+                "workload": f"3840x2160 synthetic x600 frames in all = {per_rank} frames/GPU, search_area={SA}, "
+                            f"err_threshold={THR}, gop={GOP}", "scaling": "strong", "unit": UNIT,
+                "value": pix / (x["step_ms"] * 1e-3) / 1e6, "ms_per_step": x["step_ms"],
+                "e2e": pix / (x["e2e_ms"] * 1e-3) / 1e6, "e2e_ms_per_step": x["e2e_ms"],
+                "e2e_stream": pix / (x["stream_ms"] * 1e-3) / 1e6,
+                "h2d_gb_per_s_per_rank": x["h2d_bytes"] / (x["e2e_ms"] * 1e-3) / 1e9,
+                "d2h_gb_per_s_per_rank": x["d2h_bytes"] / (x["e2e_ms"] * 1e-3) / 1e9,
+                "parity": x.get("parity"),
+                "single_gpu_reference": "legs.4k of the N=1 run (Mpixel/s of one GPU on the same geometry)"}
+            release(x)
 
     if rank != 0:
         if world > 1:
