@@ -61,7 +61,7 @@ def to_json(rep, frames_per_launch, source):
     best = {}
     for r in rows[2:]:
         d = {h: (u, v) for h, u, v in zip(hdr, units, r)}
-        stage = "inter" if "k_inter_search" in r[name_col] else ("intra" if "k_intra_wavefront" in r[name_col] else None)
+        stage = "inter" if "k_inter_search" in r[name_col] else ("intra" if ("k_intra_rows" in r[name_col] or "k_intra_wavefront" in r[name_col]) else None)
         if stage is None:
             continue
         t = float(d["gpu__time_duration.sum"][1].replace(",", ""))
