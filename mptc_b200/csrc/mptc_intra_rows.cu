@@ -158,8 +158,13 @@ __device__ __forceinline__ uint16_t wordset_insert(uint32_t *keys, uint32_t hmas
 
 #ifdef MPTC_PHASE_TIMING
 __device__ unsigned long long g_rows_cycles[24];
+#if MPTC_PHASE_TIMING == 2   // light: only the globaltimer trace (no atomics, no clock64 in the decider)
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_ADD(i, x) do { } while (0)
+#else
 #define PHASE_MARK(i) do { if (tid == 0) { long long now_ = clock64(); atomicAdd(&g_rows_cycles[i], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
 #define PHASE_ADD(i, x) atomicAdd(&g_rows_cycles[i], (unsigned long long)(x))
+#endif
 // wavefront trace of the launch's first frame: per (row, group) the times (globaltimer, ns) at which the
 // group started waiting for the far rows, started loading, started its own row, made its first and its
 // last decision
@@ -831,7 +836,7 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
         int g = 0;
         bool aborted = false;
         const bool left_pending = s_avail[0] < x0;   // the partner CTA still owed words at load time
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
         const long long td0 = clock64();
         long long t_near = 0;
 #endif
@@ -841,7 +846,7 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
           }
           // every lane polled on its own and may have seen a different moment: agree before going on
           aborted = __any_sync(0xffffffffu, aborted);
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
           if (lane == 0) PHASE_ADD(6, clock64() - td0);
 #endif
           // (no fence: the flag and the partials are read with volatile loads, which this thread issues in
@@ -856,7 +861,7 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
         int safe_end = 0;          // targets < safe_end have merged the partials of all near rows
         while (g < n && !aborted) {
           if (g >= safe_end) {
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
             const long long tn0 = clock64();
 #endif
             int m;
@@ -872,7 +877,7 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
             aborted = __any_sync(0xffffffffu, aborted);
             if (aborted) break;
             m = __shfl_sync(0xffffffffu, m, 0);
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
             t_near += clock64() - tn0;
             if (lane == 0) PHASE_ADD(9, 1);
 #endif
@@ -899,7 +904,7 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
             uid = __shfl_sync(0xffffffffu, found ? cand_uid : kNeedOwn, g);   // lane g has all its pushes
             if (uid == kNeedOwn) break;
             finish_step(g, uid, false);
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
             if (lane == 0 && gop_i == 0 && by >= 100 && by < 108 && x0 + g < 512) g_rows_steps[(by - 100) * 512 + x0 + g] = gtime();
 #endif
           }
@@ -923,7 +928,7 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
         }
         if (aborted) vst(&s_overflow, 1);
         TRACE(4);
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
         if (lane == 0) { PHASE_ADD(7, t_near); PHASE_ADD(8, clock64() - td0); }
 #endif
         if (lane == 0) {
@@ -969,11 +974,11 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
             const bool valid = in && (uint32_t)(ent >> 32) == epoch;
             const unsigned inv = ~__ballot_sync(0xffffffffu, valid);
             const int p = inv ? __ffs(inv) - 1 : 32;        // leading entries that are there
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
             if (lane == 0 && r == 1) PHASE_ADD(14, 1);
 #endif
             if (p == 0) { __nanosleep(20); continue; }
-#ifdef MPTC_PHASE_TIMING
+#if defined(MPTC_PHASE_TIMING) && MPTC_PHASE_TIMING == 1
             if (lane == 0 && r == 1) { PHASE_ADD(13, 1); PHASE_ADD(15, p); }
 #endif
             const bool active = lane < p;

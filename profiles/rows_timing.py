@@ -31,11 +31,14 @@ if not TIMED:
     print("intra ms per launch (no MPTC_PHASE_TIMING build):", ms, "split", os.environ.get("MPTC_ROW_SPLIT", "default"))
     sys.exit(0)
 L.mptc_debug_rows_cycles(buf, 0)
+LIGHT = buf[11] == 0   # an MPTC_PHASE_TIMING=2 build: only the trace
+if LIGHT:
+    print("intra ms per launch (trace-only build):", ms)
 g = max(buf[11], 1)
 print("intra ms", round(ctx.last_encode_ms("intra"), 3), "fast-path groups", buf[11], "avg distinct words/group", round(buf[10] / g, 1))
 names = ["loop/todo", "A: far rows + snapshot + clear", "B: window load + hash", "C: ids + constants + evaluation", "C: rows above scan",
          "D: own row (barrier to barrier)"]
-tot = sum(buf[i] for i in range(6))
+tot = max(sum(buf[i] for i in range(6)), 1)
 for i, nm in enumerate(names):
     print(f"{nm:34s} {buf[i] / g:10.0f} cycles/group  {100.0 * buf[i] / tot:5.1f}%")
 print(f"decider per group: loop {buf[8] / g:.0f} cycles, of which waiting for the partner's left part {buf[6] / g:.0f}, "
@@ -65,6 +68,8 @@ if os.environ.get("TRACE"):
     print(f"decision span inside a group (first to last decision): mean {(a[:, :, 4] - a[:, :, 3]).mean():.2f} us")
     print(f"build (load start to own-row start): mean {(a[:, :, 2] - a[:, :, 1]).mean():.2f} us; far wait mean {(a[:, :, 1] - a[:, :, 0]).mean():.2f} us; "
           f"own-row start to first decision mean {(a[:, :, 3] - a[:, :, 2]).mean():.2f} us")
+    if LIGHT:
+        sys.exit(0)
     st = (C.c_ulonglong * (8 * 512))()
     L.mptc_debug_rows_steps(st, 8 * 512)
     s = (np.frombuffer(st, dtype=np.uint64).reshape(8, 512)[:, : W // 4].astype(np.float64) - t0) / 1e3
