@@ -542,7 +542,7 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     ev, stale = ncu_evidence(dominant)
     traffic = ev["dram_bytes_per_frame"] * n_gops if ev and "dram_bytes_per_frame" in ev else None
     roofline = {
-        "kernel": "k_inter_search_tiled" if dominant == "inter" else "k_intra_wavefront_tiled",
+        "kernel": "k_inter_search_tiled" if dominant == "inter" else "k_intra_rows",
         "measured": "CUDA events around each launch in a one-lane pass of the same workload (kernels serialised)",
         "share_of_step": k_ms / serial_total, "serial_step_ms": serial_total, "serial_stage_ms": serial_ms,
         "bound": "issue", "achieved": achieved, "peak": issue_peak, "unit": "Tslot/s", "frac": achieved / issue_peak,

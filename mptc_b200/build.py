@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MPTC_LIB") or os.path.join(HERE, "libmptc_b200.so")   # MPTC_LIB: A/B builds (profiling)
 
-SOURCES = ["mptc_kernels.cu", "mptc_inter.cu", "mptc_intra.cu", "mptc_intra_rows.cu", "mptc_sparse.cu", "mptc_pixel.cu", "mptc_decode.cu", "mptc_capi.cu", "mptc_host.cpp"]
+SOURCES = ["mptc_kernels.cu", "mptc_inter.cu", "mptc_intra_rows.cu", "mptc_sparse.cu", "mptc_pixel.cu", "mptc_decode.cu", "mptc_capi.cu", "mptc_host.cpp"]
 HEADERS = ["mptc_kernels.h", "mptc_device.cuh", "mptc_uniform_eval.cuh", "mptc_host.h", os.path.join("..", "..", "include", "mptc_gpu.h"),
            os.path.join("..", "..", "include", "mptc_codec.h")]
 

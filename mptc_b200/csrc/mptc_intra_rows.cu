@@ -5,7 +5,7 @@
 // Dependency: block (x, y) reads the FINAL index words of (x-sa..x-1, y) and of
 // (x-sa..x+sa-1, y-1..y-2sa+1).  One CTA walks one block row left to right (two CTAs per row on intra
 // frames, alternating groups), a group of 32 targets at a time (lane = target), exactly as the first
-// generation (mptc_intra.cu) did: de-duplicate the union window's words, evaluate every distinct word
+// generation (round 1's mptc_intra.cu) did: de-duplicate the union window's words, evaluate every distinct word
 // once per target, scan the rows above with all warps.  What changed is how a row learns what the
 // rows next to it decided -- the 13.5 us a row used to trail the row above by were a fence, a progress
 // counter in global memory, a polled acquire load and a merge loop on the decider warp

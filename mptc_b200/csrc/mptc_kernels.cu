@@ -5,7 +5,7 @@
 //                          direct form (one CTA per target); the tiled form is in mptc_inter.cu
 //   K3 k_intra_wavefront   DXTImage::IntraSearch + winner apply, raster     (codec/dxt_image.cpp:652-713, :912-955)
 //                          dependency resolved by a row-staggered wavefront; direct form, the tiled
-//                          form is in mptc_intra.cu, the leftover kernel of inter frames in mptc_sparse.cu
+//                          form is in mptc_intra_rows.cu, the leftover kernel of inter frames in mptc_sparse.cu
 //   K4 k_compact_count /   _unique_palette push_backs as an ordered prefix  (codec/dxt_image.cpp:953-954)
 //      k_compact_unique    sum over chunks of 1024 blocks
 //   K5 k_endpoint_planes   RGB565 -> YCoCg667 -> 64x64 5/3 wavelet -> u8    (codec/codec.cpp:804-839, wavelet.cpp:30-131)
@@ -544,10 +544,7 @@ void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int
 
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
                             int max_ctas, int grid_cap, cudaStream_t s) {
-  // MPTC_K3=progress selects the first-generation wavefront (progress counters + fences) for A/B runs
-  static const bool first_gen = [] { const char *e = getenv("MPTC_K3"); return e && e[0] == 'p'; }();
-  if (!first_gen && launch_intra_rows(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
-  if (first_gen && launch_intra_wavefront_tiled(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
+  if (launch_intra_rows(v, k_in_gop, n_gops, sa, thr, ticket, grid_cap, s)) return;
   int items = n_gops * v.bh;  // direct (one target at a time) fallback for very large windows
   int grid = items < max_ctas ? items : max_ctas;
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;

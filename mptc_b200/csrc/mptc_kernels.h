@@ -53,8 +53,6 @@ cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
 // K1/K4/K5 run over frames f0, f0 + fstride, ... (nf of them).
 void launch_dxt1_fit(const SeqView &v, int f0, int fstride, int nf, cudaStream_t s);
 void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
-bool launch_intra_wavefront_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,
-                                  int grid_cap, cudaStream_t s);
 bool launch_intra_rows(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket, int grid_cap,
                        cudaStream_t s);
 bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);

@@ -2,7 +2,7 @@
 // left over (DXTImage::Reencode, codec/dxt_image.cpp:910-955, reached when :890 fails).
 //
 // On ordinary content these are a few dozen to a few thousand blocks per frame, scattered over
-// the frame, so the row wavefront (mptc_intra.cu) would spend its time handing rows from CTA to
+// the frame, so the row wavefront (mptc_intra_rows.cu) would spend its time handing rows from CTA to
 // CTA.  Here every leftover block is one work item and dependencies are tracked per BLOCK:
 //   * every CTA builds the frame's raster-ordered directory of leftover blocks itself: the rows
 //     flagged by K2 in row_todo and a prefix sum of their leftover counts (item -> row by binary
