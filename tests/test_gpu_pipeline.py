@@ -133,3 +133,23 @@ def test_two_devices_in_one_process():
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("lanes,wave_rows,gop,w", [(1, 1, 1, 320), (1, 1, 2, 512), (2, 1, 1, 320), (4, 2, 1, 272)])
+def test_fewer_wavefront_ctas_than_gops(ctx, lanes, wave_rows, gop, w):
+    """rows wider than one group are shared by several CTAs; with a grid no larger than
+    the number of GOPs every resident CTA used to hold a first-part ticket and nobody could pick up the
+    partner's.  The parts of a row now hold adjacent tickets.  Here: up to 10 GOPs per launch, one or two
+    CTAs per frame, rows of 3 - 4 groups."""
+    h, n, sa, thr = 48, 10, 4, 50
+    frames = make_sequence(w, h, n, seed=21)
+    ref = oracle_sequence(frames, sa, thr, gop)
+    ctx.set_schedule(lanes, wave_rows, wave_rows)
+    try:
+        out = ctx.encode_sequence(frames, sa, thr, gop)
+    finally:
+        ctx.set_schedule(0, 0, 0)
+    for i in range(n):
+        blocks, motion, unique = ref[i]
+        assert np.array_equal(out["blocks"][i], blocks), f"frame {i}"
+        assert np.array_equal(out["motion"][i], motion), f"frame {i}"
