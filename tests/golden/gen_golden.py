@@ -89,6 +89,21 @@ def decode_fixture():
     print("wrote decode fixture", blocks.shape)
 
 
+STREAM_CASES = {"stream_256x256_sa4_gop2": (256, 256, 4, 77, 4, 50, 2), "stream_512x256_sa16_gop4": (512, 256, 8, 41, 16, 50, 4)}
+
+
+def stream_fixtures(only=None):
+    """The bytes the reference's own CompressMultiUnique (codec.cpp:1307) writes for a PNG directory."""
+    for name, (w, h, n, seed, sa, thr, gop) in STREAM_CASES.items():
+        if only and name != only:
+            continue
+        frames = make_sequence(w, h, n, seed=seed)
+        stream = reference_stream(frames, sa, thr, gop)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), params=np.array([w, h, n, seed, sa, thr, gop]),
+                            frames_sha=np.array(sha(frames)), stream=np.frombuffer(stream, dtype=np.uint8))
+        print("wrote", name, len(stream), "bytes")
+
+
 def inter_pixel_fixture():
     """DXTImage::InterPixelSearch (dxt_image.cpp:776-832), every block of the second frame of two small
     sequences against the first frame's final blocks: the loop run over the reference's own
@@ -117,6 +132,8 @@ def main():
         return decode_fixture()
     if "--inter-pixel-only" in sys.argv:
         return inter_pixel_fixture()
+    if "--stream2-only" in sys.argv:
+        return stream_fixtures("stream_512x256_sa16_gop4")
     assert ref.available(), "build oracle/_ref first: make -C oracle ref"
     assert ref.selfcheck_png(make_sequence(64, 64, 1)[0]) == 0
     for name, cfg in CASES.items():
@@ -138,12 +155,8 @@ def main():
         out["enc_" + k] = np.frombuffer(ref.arith_encode(s), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, "arith.npz"), **out)
     print("wrote arith")
-    # whole-stream fixture: 256x256 x 4 frames, sa 4, thr 50, gop 2 (two groups)
-    frames = make_sequence(256, 256, 4, seed=77)
-    stream = reference_stream(frames, 4, 50, 2)
-    np.savez_compressed(os.path.join(HERE, "stream_256x256_sa4_gop2.npz"), params=np.array([256, 256, 4, 77, 4, 50, 2]),
-                        frames_sha=np.array(sha(frames)), stream=np.frombuffer(stream, dtype=np.uint8))
-    print("wrote stream", len(stream), "bytes")
+    # whole-stream fixtures: 256x256 x 4 frames, sa 4, thr 50, gop 2 (two groups); 512x256 x 8 frames, sa 16, gop 4
+    stream_fixtures()
     decode_fixture()
     inter_pixel_fixture()
 

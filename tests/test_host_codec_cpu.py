@@ -32,11 +32,13 @@ def test_frame_payload_equals_reference(threads):
         assert [int(x) for x in sizes] == [int(x) for x in g[f"sizes_{i}"]]
 
 
-@pytest.mark.parametrize("threads", [1, 4])
-def test_stream_assembly_equals_reference_stream(threads):
+@pytest.mark.parametrize("threads,fixture", [(1, "stream_256x256_sa4_gop2"), (4, "stream_256x256_sa4_gop2"),
+                                             (3, "stream_512x256_sa16_gop4")])
+def test_stream_assembly_equals_reference_stream(threads, fixture):
     """Per-frame results come from the oracle here (CPU); the assembled stream must equal what the
-    reference's CompressMultiUnique wrote for the same frames."""
-    g = load("stream_256x256_sa4_gop2")
+    reference's CompressMultiUnique wrote for the same frames (two fixtures: 256x256 sa 4 gop 2 and
+    512x256 sa 16 gop 4 -- the default window, four-frame groups)."""
+    g = load(fixture)
     w, h, n, seed, sa, thr, gop = [int(x) for x in g["params"]]
     frames = make_sequence(w, h, n, seed=seed)
     assert sha(frames) == str(g["frames_sha"])
