@@ -806,6 +806,10 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
           if ((unsigned)uid > (unsigned)kMaxWords) uid = kMaxWords;
 #endif
           const bool mine = lane == g;     // final from now on
+          // the table read every lane's selects wait for goes out first; lane g's hand-over (a dependent
+          // shared load feeding a global store) is issued behind it and is nobody's critical path
+          int e;
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(e) : "r"(err_lane_s + 132u * (uint32_t)uid) : "memory");
           cand_uid = mine ? uid : cand_uid;
           found = found || mine;
           cand_dec = (mine && unique) ? -1 : cand_dec;
@@ -820,8 +824,6 @@ k_intra_rows(SeqView v, int k_in_gop, int n_gops, int sa, int thr, int split, in
               ::"r"((int)mine), "r"(my_row0_s), "h"((unsigned short)uid), "r"(ulist_s + 4u * (uint32_t)uid), "r"(epoch), "l"(my_entry)
               : "memory");
           const int d = lane - g;                              // push to the <= sa targets on the right
-          int e;
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(e) : "r"(err_lane_s + 132u * (uint32_t)uid) : "memory");
           const bool acc = (unsigned)(d - 1) < (unsigned)sa && todo && e != kRejectedSmall;
           const bool nonpos = acc && e <= 0;
           const bool better = acc && e > 0 && !has_first && e <= best_e;
