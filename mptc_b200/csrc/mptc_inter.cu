@@ -73,6 +73,18 @@ __host__ __device__ inline size_t tile_smem_bytes(int sa, int *np_out, int *ht_o
 
 }  // namespace
 
+#ifdef MPTC_K2_PHASE_TIMING
+__device__ unsigned long long g_k2_cycles[12];
+#define K2_MARK(i) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_k2_cycles[i], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+extern "C" void mptc_debug_k2_cycles(unsigned long long *out12, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out12, g_k2_cycles, sizeof(unsigned long long) * 12);
+  if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_k2_cycles, z, sizeof z); }
+}
+#else
+#define K2_MARK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 2)
 k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,12 +121,16 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
   const uint64_t *prev = v.final_blocks + (size_t)(f - 1) * v.nb;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
+#ifdef MPTC_K2_PHASE_TIMING
+  long long t_mark_ = clock64();
+#endif
   // ---- phase 0: clear the hash table -------------------------------------------------------
   for (int s = tid; s <= HT; s += kThreads) sm.keys[s] = kEmpty;
   sm.lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
   sm.lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
   if (tid == 0) { s_count = 0; s_special = 0; }
   __syncthreads();
+  K2_MARK(0);   // clear
 
   // ---- phase 1: load the union window (all loads of a thread first, so their latencies overlap),
   // this lane's target block, then insert the words --------------------------------------------
@@ -149,6 +165,9 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
         t.own_block = 0; t.own_word = 0; t.orig_err = 0;
       }
     }
+    // (Measured and dropped, profiles/r2_k2_phases.txt: electing one lane per distinct word of a warp with
+    // __match_any_sync before the insert, and looking at the slot before paying for the atomic -- this
+    // phase is the latency of the window and pixel loads, not the atomics.)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int p = p0 + q * kThreads + tid;
@@ -184,6 +203,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     }
   }
   __syncthreads();
+  K2_MARK(1);   // window load + hash
 
   const int U = s_count;
   WinnerState ws[kTileX * kTileY / kWarps];   // this warp scans targets wid, wid+8, wid+16, wid+24
@@ -206,6 +226,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
       sm.pos_uid[p] = (slot != kNoPos) ? sm.slot_uid[slot] : (uint16_t)(U <= kWords ? kWords : kNoPos);
     }
     __syncthreads();   // slot_uid / keys are dead from here on: their bytes become info / err / epk
+    K2_MARK(2);   // ids
     if (tid < 33) err[kWords * 33 + tid] = (E)(kErr16 ? kErr16Max : kRejectedSmall);
 
     // ---- phases 3-5 per chunk of distinct words ----------------------------------------------
@@ -218,6 +239,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
         if (s0 > 0) __syncthreads();            // the previous sub-chunk's constants are no longer read
         for (int u = tid; u < sn; u += kThreads) word_info(sm.ulist[c0 + s0 + u], sm.info[u]);
         __syncthreads();
+        K2_MARK(3);   // per-word constants
         for (int u = wid; u < sn; u += kWarps) {
           const uint32_t word = sm.ulist[c0 + s0 + u];
           uint32_t packed;
@@ -227,6 +249,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
         }
       }
       __syncthreads();
+      K2_MARK(4);   // evaluation
 
       // scan: each target walks its own window in the reference's order (j up, i up).
       // Positions outside the frame (and, when the words do not fit one chunk, words of other
@@ -242,6 +265,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
         else        scan_window<true, E>(ws[q], pos, UW, 1, err + tt, W, 0, W, lane, c0, cn, kWords);
       }
       __syncthreads();
+      K2_MARK(5);   // window scan
     }
 
     // executed work (bench.py's roofline): every distinct word once per valid target, every window
@@ -268,6 +292,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     }
   }
   __syncthreads();
+  K2_MARK(6);   // resolve
   if (wid == 0 && t_valid) {
     const int min_err = s_res_err[lane];
     const int row = s_res_pos[lane] >> 8, col = s_res_pos[lane] & 0xFF;
@@ -289,6 +314,7 @@ k_inter_search_tiled(SeqView v, int k_in_gop, int sa, int thr) {
     v.flags[(size_t)f * v.nb + tb] = flag;
     if (!flag) v.row_todo[(size_t)f * v.bh + tby] = 1;   // the intra wavefront has work in this row
   }
+  K2_MARK(7);   // apply
 }
 
 // Returns false when the tile's shared memory does not fit (very large search_area): the
