@@ -203,11 +203,11 @@ __device__ __forceinline__ void winner_update_fast(WinnerState &s, int e, uint32
 }
 
 // Scans rows [row_begin, row_end) of one target's W-wide window.  The word id of window
-// position (row, col) is pos[row * stride + cdir * col]; errcol[id * 33] is that word's err_diff
+// position (row, col) is pos[row * stride + cdir * col]; errcol[id * kStride] is that word's err_diff
 // for this target.  Lanes stride over the flattened scan order, so there is no per-position
 // division.  kRemap handles the multi-chunk case: ids outside [c0, c0 + cn) read the
 // all-rejected row `dummy`.
-template <bool kRemap, typename E = int>
+template <bool kRemap, typename E = int, int kStride = 33>
 __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos, int stride, int cdir,
                                             const E *errcol, int W, int row_begin, int row_end, int lane,
                                             int c0, int cn, int dummy) {
@@ -222,7 +222,7 @@ __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos
         u -= c0;
         u = ((unsigned)u < (unsigned)cn) ? u : dummy;
       }
-      const int e = (int)errcol[u * 33];
+      const int e = (int)errcol[u * kStride];
       // (a per-row vote that skips the first / lastneg reductions for rows without an err_diff <= 0
       // candidate was measured: 17.6 vs 14.5 ms -- such rows are rare on the benchmark content)
       winner_update_fast(ws, e, p);
@@ -238,7 +238,7 @@ __device__ __forceinline__ void scan_window(WinnerState &ws, const uint16_t *pos
       u -= c0;
       u = ((unsigned)u < (unsigned)cn) ? u : dummy;
     }
-    winner_update_fast(ws, (int)errcol[u * 33], (uint32_t)((row << 7) | col));
+    winner_update_fast(ws, (int)errcol[u * kStride], (uint32_t)((row << 7) | col));
     col += cstep;
     row += rstep;
     if (col >= W) { col -= W; ++row; }
@@ -272,14 +272,10 @@ __device__ __forceinline__ void winner_merge(WinnerState &s, const WinnerState &
 }
 
 __device__ __forceinline__ void winner_warp_reduce(WinnerState &s) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    WinnerState o;
-    o.first = __shfl_xor_sync(0xffffffffu, s.first, d);
-    o.lastneg = __shfl_xor_sync(0xffffffffu, s.lastneg, d);
-    o.best = __shfl_xor_sync(0xffffffffu, s.best, d);
-    winner_merge(s, o);
-  }
+  // REDUX.MIN / REDUX.MAX: one instruction per component instead of five shuffle + min rounds
+  s.first = __reduce_min_sync(0xffffffffu, s.first);
+  s.lastneg = __reduce_max_sync(0xffffffffu, s.lastneg);
+  s.best = __reduce_min_sync(0xffffffffu, s.best);
 }
 
 // Returns the search's return value (min_err) and the winning (row, col); INT_MAX if nothing

@@ -1,0 +1,418 @@
+// mptc_inter_wide.cu -- K2, second generation: 16x16 targets per CTA, one 8x4 sub-tile per warp.
+//
+// Same restatement as mptc_inter.cu (DXTImage::InterBlockSearch + the winner apply in Reencode,
+// codec/dxt_image.cpp:715-774, :885-908) and the same three ideas -- de-duplicate the window's index
+// words, evaluate each DISTINCT word once per target with the word warp-uniform (mptc_uniform_eval.cuh),
+// then let every target walk its own window through the (word id -> err_diff) table with the
+// order-independent winner scan (WinnerState) -- but arranged so that the per-tile
+// overhead is paid once per 256 targets instead of once per 32:
+//
+//   * K2 of round 1 gave a CTA 32 targets: all eight warps held THE SAME 32 targets in registers (eight
+//     copies of the pixel loads, conversions and own-error computation), shared the words of one 39x35
+//     union window (one hash build, one id pass, one set of per-word constants per 32 targets) and met at
+//     seven barriers per tile.  Measured per tile (profiles/r2_k2_phases.txt): 33 % of the time in the
+//     phases before the first evaluation.
+//   * Here a CTA takes 16x16 targets.  Warp w owns the 8x4 sub-tile (w & 1, w >> 1): its 32 targets live in
+//     its lanes' registers and nowhere else.  The hash build, the id pass and the per-word constants cover
+//     the 47x47 union window of all 256 targets (2209 positions instead of 8 x 1365), after which each
+//     warp works alone: it marks the words that occur in ITS sub-tile's 39x35 window, evaluates those
+//     against its 32 targets into a warp-private table, scans its targets' windows, and applies its
+//     winners -- no CTA barrier after the per-word constants.
+//   * The table is int16 {-1, 0, min(err_diff, 32767)} (the winner rule needs the sign of a negative
+//     err_diff and exact positive values only up to the threshold, dxt_image.cpp:890): 128 words x 36 x
+//     8 warps fit two CTAs per SM.  (Thresholds >= 32767 keep round 1's kernel and its int32 table.)
+//   * The scan walks COLUMNS of targets: the four targets (x, y0 .. y0+3) of a sub-tile column look at the
+//     same union-window positions one row apart, so one id read and one 8-byte table read (the four
+//     targets' entries of a word are adjacent: table[word][x][y]) serve four window positions.  The
+//     scan is bound by shared-memory wavefronts (random-bank table reads), not by issue slots: this cuts
+//     them by about three.
+//   * A tile whose union window holds more than 128 distinct words (word-diverse content: noise,
+//     err_threshold 0) is put on a list instead, and a second launch (k_inter_search_listed) runs round 1's
+//     tile search (mptc_inter_tile.cuh), whose window -- and therefore word count -- is that of 32 targets,
+//     over the listed tiles' 8x4 sub-tiles.
+//
+// Results are bit-identical to the position-by-position loop (tests/test_gpu_parity_small.py,
+// tests/test_gpu_full_golden.py run through whichever K2 the launcher picks; MPTC_K2=tiled|wide forces one).
+#include "mptc_inter_tile.cuh"
+
+namespace mptc {
+
+namespace {
+
+constexpr int kSubX = 8, kSubY = 4;            // a warp's targets: lane = ly * 8 + lx
+constexpr int kSubsX = 2, kSubsY = 4;          // sub-tiles per CTA
+constexpr int kTileX = kSubX * kSubsX, kTileY = kSubY * kSubsY;   // 16 x 16 targets
+constexpr int kWarps = kSubsX * kSubsY, kThreads = kWarps * 32;
+constexpr int kBatch = 9;                      // window loads in flight per thread (2209 positions / 256 threads at search_area 16)
+constexpr int kWords = 128;                    // distinct words a tile may hold on this path
+constexpr int kRow = 36;                       // int16 entries per table row: [lx][ly], 8-byte aligned rows, 18 words: odd multiple of 2 banks
+constexpr int kErr16Max = 32767;
+constexpr size_t kErrBytesPerWarp = (size_t)(kWords + 1) * kRow * 2;   // + the all-rejected row
+constexpr size_t kNeedBytesPerWarp = 144;      // kWords flags + the dummy id's, rounded to 16
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;       // hash-table empty marker (the real word 0xFFFFFFFF lives in slot HT)
+constexpr uint16_t kNoPos = 0xFFFFu;           // window position outside the frame
+
+static_assert(kErrBytesPerWarp % 8 == 0, "table rows are read with 8-byte loads");
+
+__host__ __device__ inline int wide_round_up_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+struct WideLayout {
+  int NP, HT;
+  size_t off_keys, off_slot_uid;                       // phases 0-2 ...
+  size_t off_info, off_err, off_need, off_wlist;       // ... share their bytes with phases 3-5
+  size_t off_lut, off_ulist, off_pos, bytes;
+};
+
+__host__ __device__ inline WideLayout wide_layout(int sa) {
+  WideLayout L;
+  const int UW = 2 * sa + kTileX - 1, UH = 2 * sa + kTileY - 1;
+  L.NP = UW * UH;
+  L.HT = wide_round_up_pow2(L.NP + L.NP / 4);
+  const size_t a = (((size_t)(L.HT + 1) * 4 + (size_t)(L.HT + 1) * 2) + 15) & ~(size_t)15;
+  L.off_keys = 0;
+  L.off_slot_uid = (size_t)(L.HT + 1) * 4;
+  L.off_info = 0;
+  L.off_err = (size_t)kWords * sizeof(WordInfo);
+  L.off_need = L.off_err + kWarps * kErrBytesPerWarp;
+  L.off_wlist = L.off_need + kWarps * kNeedBytesPerWarp;
+  const size_t e = L.off_wlist + (size_t)kWarps * kWords;
+  size_t b = a > e ? a : e;
+  L.off_lut = b;   b += 512;
+  L.off_ulist = b; b += (size_t)L.NP * 4;
+  L.off_pos = b;   b += (size_t)L.NP * 2;
+  L.bytes = (b + 15) & ~(size_t)15;
+  return L;
+}
+
+// One union-window row of a column of four targets: target y's window row is R - y.  e = the four
+// targets' table entries of the word at (R, column); kMask = which of the four have row R in their window.
+template <int kMask>
+__device__ __forceinline__ void column_step(WinnerState (&ws)[4], uint2 e, uint32_t p) {
+  if (kMask & 1) winner_update_fast(ws[0], (int)(int16_t)(e.x & 0xFFFFu), p);
+  if (kMask & 2) winner_update_fast(ws[1], (int)e.x >> 16, p);
+  if (kMask & 4) winner_update_fast(ws[2], (int)(int16_t)(e.y & 0xFFFFu), p);
+  if (kMask & 8) winner_update_fast(ws[3], (int)e.y >> 16, p);
+}
+
+}  // namespace
+
+#ifdef MPTC_K2_PHASE_TIMING
+__device__ unsigned long long g_k2w_cycles[12];
+#define K2W_MARK(i) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_k2w_cycles[i], (unsigned long long)(now_ - t_mark_)); t_mark_ = now_; } } while (0)
+extern "C" void mptc_debug_k2w_cycles(unsigned long long *out12, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out12, g_k2w_cycles, sizeof(unsigned long long) * 12);
+  if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_k2w_cycles, z, sizeof z); }
+}
+#else
+#define K2W_MARK(i) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_count, s_special;
+
+  const int W = 2 * sa;
+  const int UW = W + kTileX - 1;
+  const WideLayout L = wide_layout(sa);
+  const int NP = L.NP, HT = L.HT;
+  uint32_t *const keys = reinterpret_cast<uint32_t *>(smem_raw + L.off_keys);
+  uint16_t *const slot_uid = reinterpret_cast<uint16_t *>(smem_raw + L.off_slot_uid);
+  WordInfo *const info = reinterpret_cast<WordInfo *>(smem_raw + L.off_info);
+  uint8_t *const lut5 = smem_raw + L.off_lut, *const lut6 = lut5 + 256;
+  uint32_t *const ulist = reinterpret_cast<uint32_t *>(smem_raw + L.off_ulist);
+  uint16_t *const pos_uid = reinterpret_cast<uint16_t *>(smem_raw + L.off_pos);
+
+  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
+  if (f >= v.first + v.count) return;
+  const int tiles_x = (v.bw + kTileX - 1) / kTileX;
+  const int tx0 = (blockIdx.x % tiles_x) * kTileX, ty0 = (blockIdx.x / tiles_x) * kTileY;
+  const int ux0 = tx0 - sa, uy0 = ty0 - sa;   // union-window origin in block coordinates
+  const uint64_t *prev = v.final_blocks + (size_t)(f - 1) * v.nb;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // this warp's sub-tile inside the CTA's tile, and this lane's target
+  const int sx0 = (wid & (kSubsX - 1)) * kSubX, sy0 = (wid / kSubsX) * kSubY;
+  const int lx = lane & (kSubX - 1), ly = lane >> 3;
+  const int tbx = tx0 + sx0 + lx, tby = ty0 + sy0 + ly;
+  const bool t_valid = tbx < v.bw && tby < v.bh;
+  const int tb = tby * v.bw + tbx;
+  const int n_valid = max(0, min(kSubX, v.bw - tx0 - sx0)) * max(0, min(kSubY, v.bh - ty0 - sy0));   // warp-uniform
+  int16_t *const err = reinterpret_cast<int16_t *>(smem_raw + L.off_err + (size_t)wid * kErrBytesPerWarp);
+  uint8_t *const need = smem_raw + L.off_need + (size_t)wid * kNeedBytesPerWarp;
+  uint8_t *const wlist = smem_raw + L.off_wlist + (size_t)wid * kWords;
+
+#ifdef MPTC_K2_PHASE_TIMING
+  long long t_mark_ = clock64();
+#endif
+  // ---- phase 0: clear the hash table -------------------------------------------------------
+  for (int s = tid; s <= HT; s += kThreads) keys[s] = kEmpty;
+  lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
+  lut6[tid] = (uint8_t)snap_bits<0xFC, 2, 6>(tid);
+  if (tid == 0) { s_count = 0; s_special = 0; }
+  __syncthreads();
+  K2W_MARK(0);   // clear
+
+  // ---- phase 1: load the union window (all loads of a thread first, so their latencies overlap),
+  // this lane's target block, then insert the words --------------------------------------------
+  const uint32_t hmask = (uint32_t)HT - 1u;
+  const int hshift = 32 - __ffs(HT) + 1;   // HT = 2^(ffs-1)
+  const uint32_t uw_magic = 0xFFFFFFFFu / (uint32_t)UW + 1u;   // p / UW == umulhi(p, magic) for p < 2^16
+  LaneTarget t;
+  for (int p0 = 0; p0 < NP; p0 += kBatch * kThreads) {
+    uint32_t wv[kBatch];
+    bool ok[kBatch];
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int p = p0 + q * kThreads + tid;
+      const int ur = (int)__umulhi((uint32_t)p, uw_magic), uc = p - ur * UW;
+      const int i = ux0 + uc, j = uy0 + ur;
+      ok[q] = p < NP && i >= 0 && j >= 0 && i < v.bw && j < v.bh;
+      wv[q] = ok[q] ? (uint32_t)(__ldg(prev + (size_t)j * v.bw + i) >> 32) : 0u;
+    }
+    if (p0 == 0) {   // the target's pixel loads go out behind the first batch of window loads
+      if (t_valid) {
+        load_lane_target(t, v.rgb + v.frame_bytes * f, v.w, tbx, tby, v.init_blocks[(size_t)f * v.nb + tb]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 48; ++k) t.pf[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) t.pl[k] = 0u;
+        t.own_block = 0; t.own_word = 0; t.orig_err = 0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kBatch; ++q) {
+      const int p = p0 + q * kThreads + tid;
+      if (p >= NP) break;
+      uint16_t slot = kNoPos;
+      if (ok[q]) {
+        const uint32_t word = wv[q];
+        // the thread that claims a slot also hands out the word's dense id
+        if (word == kEmpty) {
+          if (atomicExch(&s_special, 1) == 0) {
+            const int uid = atomicAdd(&s_count, 1);
+            slot_uid[HT] = (uint16_t)uid;
+            ulist[uid] = kEmpty;
+          }
+          slot = (uint16_t)HT;
+        } else {
+          uint32_t h = (word * 0x9E3779B1u) >> hshift;
+          for (;;) {
+            const uint32_t old = atomicCAS(&keys[h], kEmpty, word);
+            if (old == kEmpty) {
+              const int uid = atomicAdd(&s_count, 1);
+              slot_uid[h] = (uint16_t)uid;
+              ulist[uid] = word;
+              break;
+            }
+            if (old == word) break;
+            h = (h + 1u) & hmask;
+          }
+          slot = (uint16_t)h;
+        }
+      }
+      pos_uid[p] = slot;
+    }
+  }
+  __syncthreads();
+  K2W_MARK(1);   // window load + hash
+
+  const int U = s_count;
+  if (U > kWords) {
+    // word-diverse tile: listed for k_inter_search_listed, which spreads its eight 8x4 sub-tiles over the
+    // GPU (handled here, one after the other, such a tile was the launch's tail: 4x an ordinary tile)
+    if (tid == 0) {
+      int *list = v.tile_list + (size_t)f * v.tile_list_stride;
+      list[1 + atomicAdd(list, 1)] = (int)blockIdx.x;
+    }
+    return;
+  }
+
+  // ---- phase 2: position -> dense word id (out-of-frame positions: the all-rejected row) ----------
+  for (int p = tid; p < NP; p += kThreads) {
+    const uint16_t slot = pos_uid[p];
+    pos_uid[p] = (slot != kNoPos) ? slot_uid[slot] : (uint16_t)kWords;
+  }
+  __syncthreads();   // slot_uid / keys are dead from here on: their bytes become info / err / need / wlist
+  K2W_MARK(2);   // ids
+
+  // ---- phase 3: per-word constants for the CTA; each warp lists the words of ITS sub-tile's window ----
+  for (int u = tid; u < U; u += kThreads) word_info(ulist[u], info[u]);
+  for (int u = lane; u < kRow; u += 32) err[kWords * kRow + u] = (int16_t)kErr16Max;   // the all-rejected row
+  const uint16_t *const sub = pos_uid + sy0 * UW + sx0;   // the sub-tile's window: (W + 7) x (W + 3) positions
+  const int SW = W + kSubX - 1, SH = W + kSubY - 1;
+  int n_need = 0;
+  if (n_valid > 0) {
+    for (int u = lane; u < (int)kNeedBytesPerWarp / 4; u += 32) reinterpret_cast<uint32_t *>(need)[u] = 0u;
+    __syncwarp();
+    // plain byte stores (equal values may race); the dummy id kWords has a flag of its own
+    for (int c = lane; c < SW; c += 32) {
+      const uint16_t *q = sub + c;
+#pragma unroll 5
+      for (int r = 0; r < SH; ++r) need[q[r * UW]] = 1;
+    }
+    __syncwarp();
+    for (int base = 0; base < U; base += 32) {
+      const bool nd = base + lane < U && need[base + lane];
+      const unsigned m = __ballot_sync(0xffffffffu, nd);
+      if (nd) wlist[n_need + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(base + lane);
+      n_need += __popc(m);
+    }
+  }
+  __syncthreads();   // the constants are there (and, for the warp, its list)
+  K2W_MARK(3);   // per-word constants + lists
+
+  if (n_valid > 0) {
+    // ---- phase 4: evaluate the listed words against this warp's 32 targets ------------------------
+    int16_t *const my_err = err + lx * kSubY + ly;
+    for (int i = 0; i < n_need; ++i) {
+      const int u = wlist[i];
+      const int e = eval_uniform(t, ulist[u], info[u], lut5, lut6);
+      my_err[u * kRow] = (int16_t)(e < 0 ? -1 : min(e, kErr16Max));
+    }
+    __syncwarp();
+    K2W_MARK(4);   // evaluation (warp 0's)
+
+    // ---- phase 5: scan.  Every target walks its own window in the reference's order (j up, i up) ----
+    WinnerState mine;          // lane = target
+    winner_init(mine);
+    if (W == 32) {
+      // lane = window column; the four targets of a sub-tile column share every id and table read.
+      // Positions are keyed by the UNION row R (target y's own row is R - y: subtracted after the reduction).
+#pragma unroll 1
+      for (int ttx = 0; ttx < kSubX; ++ttx) {
+        if (tx0 + sx0 + ttx >= v.bw) break;    // warp-uniform
+        WinnerState ws[4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) winner_init(ws[y]);
+        const uint16_t *q = sub + ttx + lane;
+        const unsigned char *tab = reinterpret_cast<const unsigned char *>(err + ttx * kSubY);
+        uint32_t p = (uint32_t)lane;
+        auto entries = [&](int R) { return *reinterpret_cast<const uint2 *>(tab + (size_t)q[R * UW] * (kRow * 2)); };
+        column_step<1>(ws, entries(0), p);  p += 128u;
+        column_step<3>(ws, entries(1), p);  p += 128u;
+        column_step<7>(ws, entries(2), p);  p += 128u;
+#pragma unroll 4
+        for (int R = 3; R < 32; ++R, p += 128u) column_step<15>(ws, entries(R), p);
+        column_step<14>(ws, entries(32), p);  p += 128u;
+        column_step<12>(ws, entries(33), p);  p += 128u;
+        column_step<8>(ws, entries(34), p);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          if (ty0 + sy0 + y >= v.bh) break;    // warp-uniform
+          winner_warp_reduce(ws[y]);
+          if (lane == y * kSubX + ttx) {       // back to the target's own rows
+            const uint32_t d = (uint32_t)y << 7;
+            ws[y].first -= d;  ws[y].lastneg -= (int)d;  ws[y].best -= d;
+            mine = ws[y];
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int tt = 0; tt < kSubX * kSubY; ++tt) {
+        const int ttx = tt & (kSubX - 1), tty = tt >> 3;
+        if (tx0 + sx0 + ttx >= v.bw || ty0 + sy0 + tty >= v.bh) continue;   // warp-uniform
+        WinnerState ws;
+        winner_init(ws);
+        scan_window<false, int16_t, kRow>(ws, sub + tty * UW + ttx, UW, 1, err + ttx * kSubY + tty, W, 0, W, lane, 0, 0, kWords);
+        winner_warp_reduce(ws);
+        if (lane == tt) mine = ws;
+      }
+    }
+    K2W_MARK(5);   // window scan (warp 0's)
+
+    // ---- phase 6: resolve and apply (lane = target) ---------------------------------------------
+    if (t_valid) {
+      int row, col;
+      const int min_err = winner_resolve_fast(mine, row, col);
+      uint8_t flag = 0;
+      if (min_err <= thr) {
+        const uint32_t word = ulist[sub[(ly + row) * UW + lx + col]];
+        v.final_blocks[(size_t)f * v.nb + tb] = lane_winning_block(t, word);
+        v.motion[((size_t)f * v.nb + tb) * 2 + 0] = (uint8_t)(col | 0x80);   // x = (i - bx) + sa
+        v.motion[((size_t)f * v.nb + tb) * 2 + 1] = (uint8_t)(row | 0x80);   // y = (j - by) + sa
+        flag = 1;
+      }
+      v.flags[(size_t)f * v.nb + tb] = flag;
+      if (!flag) v.row_todo[(size_t)f * v.bh + tby] = 1;   // the intra wavefront has work in this row
+    }
+    // executed work (bench.py's roofline): every word a warp evaluated once per valid target, every
+    // window position of every valid target once
+    if (lane == 0) {
+      atomicAdd(v.work + kWorkInterEvals, (unsigned long long)n_need * (unsigned long long)n_valid);
+      atomicAdd(v.work + kWorkInterScanned, (unsigned long long)n_valid * (unsigned long long)(W * W));
+      if (wid == 0) atomicAdd(v.work + kWorkInterTiles, 1ull);
+    }
+    K2W_MARK(6);   // resolve + apply
+  }
+}
+
+// The word-diverse tiles k_inter_search_wide listed, by round 1's 8x4 tile search: CTA i of a frame takes the
+// sub-tiles i, i + gridDim.x, ... of the list (eight per listed tile).
+__global__ void __launch_bounds__(tile32::kThreads, 2)
+k_inter_search_listed(SeqView v, int k_in_gop, int sa, int thr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
+  if (f >= v.first + v.count) return;
+  const int *list = v.tile_list + (size_t)f * v.tile_list_stride;
+  const int n = list[0] * kWarps;
+  const int tiles_x = (v.bw + kTileX - 1) / kTileX;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int tile = list[1 + i / kWarps], sub_i = i % kWarps;
+    const int bx0 = (tile % tiles_x) * kTileX + (sub_i & (kSubsX - 1)) * kSubX;
+    const int by0 = (tile / tiles_x) * kTileY + (sub_i / kSubsX) * kSubY;
+    if (bx0 >= v.bw || by0 >= v.bh) continue;
+    if (i != (int)blockIdx.x) __syncthreads();   // the shared memory starts over
+    tile32::search_tile(v, f, bx0, by0, sa, thr, smem_raw);
+  }
+}
+
+int inter_tile_list_stride(int bw, int bh) { return 1 + ((bw + kTileX - 1) / kTileX) * ((bh + kTileY - 1) / kTileY); }
+
+// Returns false when the kernel does not apply (nothing launched): the caller then uses the round-1 tiling.
+// two_per_sm_only: decline unless two CTAs fit an SM.
+bool launch_inter_search_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, bool two_per_sm_only, cudaStream_t s) {
+  static int max_optin = -1, max_sm = -1, n_sm = 0;
+  static size_t configured[kMaxDevices] = {0}, configured_listed[kMaxDevices] = {0};
+  const WideLayout L = wide_layout(sa);
+  const size_t bytes32 = tile32::tile_smem_bytes(sa, nullptr, nullptr);
+  if (L.NP >= 0xFFFF) return false;            // 16-bit word ids
+  if (thr >= kErr16Max) return false;          // the int16 table clamps at 32767
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  {
+    std::lock_guard<std::mutex> lock(launch_cfg_mutex());
+    if (max_optin < 0) {
+      cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cur_dev);
+      cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cur_dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cur_dev);
+    }
+    if (L.bytes + 1024 > (size_t)max_optin || bytes32 + 1024 > (size_t)max_optin) return false;
+    if (two_per_sm_only && 2 * (L.bytes + 1024 + 64) > (size_t)max_sm) return false;
+    size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
+    if (L.bytes > conf) {
+      if (cudaFuncSetAttribute(k_inter_search_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes) != cudaSuccess)
+        return false;
+      conf = L.bytes;
+    }
+    size_t &conf32 = configured_listed[cur_dev & (kMaxDevices - 1)];
+    if (bytes32 > conf32) {
+      if (cudaFuncSetAttribute(k_inter_search_listed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes32) != cudaSuccess)
+        return false;
+      conf32 = bytes32;
+    }
+  }
+  const int tiles = ((v.bw + kTileX - 1) / kTileX) * ((v.bh + kTileY - 1) / kTileY);
+  k_inter_search_wide<<<dim3(tiles, n_gops), kThreads, L.bytes, s>>>(v, k_in_gop, sa, thr);
+  const int ctas = min(tiles * kWarps, 2 * n_sm);
+  k_inter_search_listed<<<dim3(ctas, n_gops), tile32::kThreads, bytes32, s>>>(v, k_in_gop, sa, thr);
+  return true;
+}
+
+}  // namespace mptc

@@ -13,6 +13,8 @@
 // No tensor cores: nothing here is a dense contraction (integer / ordered-FP32 work).
 #include "mptc_kernels.h"
 
+#include <cstring>
+
 #include <cstdlib>
 #include "mptc_device.cuh"
 
@@ -536,10 +538,20 @@ void launch_dxt1_fit(const SeqView &v, int f0, int fstride, int nf, cudaStream_t
                                   v.init_blocks + (size_t)f0 * v.nb, v.final_blocks + (size_t)f0 * v.nb, fstride);
 }
 
-void launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
-  if (launch_inter_search_tiled(v, k_in_gop, n_gops, sa, thr, s)) return;
+// K2 dispatch: the 16x16-target kernel (mptc_inter_wide.cu) while two of its CTAs fit an SM, else the
+// 8x4-target kernel of round 1 (mptc_inter.cu), else the wide kernel at one CTA per SM, else one CTA per
+// target.  MPTC_K2 = wide | tiled forces the choice (A/B measurements, and the parity tests of both).
+int launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s) {
+  static const int forced = [] {
+    const char *e = getenv("MPTC_K2");
+    return !e ? 0 : (!strcmp(e, "wide") ? 1 : (!strcmp(e, "tiled") ? 2 : 0));
+  }();
+  if (forced != 2 && launch_inter_search_wide(v, k_in_gop, n_gops, sa, thr, /*two_per_sm_only=*/forced == 0, s)) return 2;
+  if (launch_inter_search_tiled(v, k_in_gop, n_gops, sa, thr, s)) return 1;
+  if (forced == 0 && launch_inter_search_wide(v, k_in_gop, n_gops, sa, thr, false, s)) return 2;
   dim3 grid(v.nb, n_gops);  // direct (one CTA per target) fallback for very large windows
   k_inter_search<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, sa, thr);
+  return 1;
 }
 
 void launch_intra_wavefront(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket,

@@ -11,7 +11,7 @@ sys.path.insert(0, os.getcwd())
 from mptc_b200 import capi  # noqa: E402
 from mptc_b200.synth import make_frame  # noqa: E402
 
-W, H, N, SA, THR, GOP = 1920, 1080, 60, 16, 50, 15
+W, H, N, SA, THR, GOP = 1920, 1080, 60, int(os.environ.get("SA", "16")), int(os.environ.get("THR", "50")), 15
 pin = capi.PinnedArray((N, H, W, 3), np.uint8)
 for f in range(N):
     pin.array[f] = make_frame(W, H, f)
@@ -30,4 +30,4 @@ for _ in range(4):
     ctx.seq_encode(0, N, SA, THR, GOP)
     t = {k: round(ctx.last_encode_ms(k), 3) for k in ("total", "fit", "inter", "intra")}
     st = t if st is None or t["total"] < st["total"] else st
-print(f"step {best:.3f} ms  one-lane {st}  results {h}")
+print(f"K2={os.environ.get('MPTC_K2', 'default')} sa {SA} thr {THR}: step {best:.3f} ms  one-lane {st}  results {h}  work {ctx.last_work_count()}")
