@@ -38,8 +38,6 @@ struct mptc_gpu_ctx {
   uint32_t *d_unique = nullptr, *d_nunique = nullptr, *d_chunks = nullptr;
   int *d_progress = nullptr;
   unsigned long long *d_wordflag = nullptr;
-  int *d_tile_list = nullptr;
-  int tile_list_stride = 0;
   int8_t *d_pattern = nullptr;   // K2p: pixel offsets of DXTImage::SetPattern for pattern_sa
   int pattern_sa = 0, pattern_n = 0;
   uint32_t epoch = 0;            // one per encode call: validity tag of the wavefront's hand-over entries
@@ -125,8 +123,8 @@ void build_match_table(uint8_t *table, int bits) {
 void free_seq(mptc_gpu_ctx *c) {
   cudaFree(c->d_rgb); cudaFree(c->d_init); cudaFree(c->d_final); cudaFree(c->d_motion);
   cudaFree(c->d_flags); cudaFree(c->d_planes); cudaFree(c->d_unique); cudaFree(c->d_nunique);
-  cudaFree(c->d_progress); cudaFree(c->d_row_todo); cudaFree(c->d_chunks); cudaFree(c->d_wordflag); cudaFree(c->d_tile_list);
-  c->d_wordflag = nullptr; c->d_tile_list = nullptr;
+  cudaFree(c->d_progress); cudaFree(c->d_row_todo); cudaFree(c->d_chunks); cudaFree(c->d_wordflag);
+  c->d_wordflag = nullptr;
   c->d_chunks = nullptr;
   c->d_rgb = nullptr; c->d_init = c->d_final = nullptr; c->d_motion = c->d_flags = c->d_planes = nullptr;
   c->d_unique = c->d_nunique = nullptr; c->d_progress = nullptr; c->d_row_todo = nullptr;
@@ -173,7 +171,7 @@ SeqView view_of(const mptc_gpu_ctx *c, int first, int count, int gop) {
   SeqView v;
   v.rgb = c->d_rgb; v.init_blocks = c->d_init; v.final_blocks = c->d_final; v.motion = c->d_motion;
   v.flags = c->d_flags; v.row_todo = c->d_row_todo; v.unique = c->d_unique; v.n_unique = c->d_nunique; v.chunk_counts = c->d_chunks; v.planes = c->d_planes;
-  v.progress = c->d_progress; v.wordflag = c->d_wordflag; v.epoch = c->epoch; v.tile_list = c->d_tile_list; v.tile_list_stride = c->tile_list_stride; v.work = c->d_cand; v.frame_bytes = c->frame_bytes;
+  v.progress = c->d_progress; v.wordflag = c->d_wordflag; v.epoch = c->epoch; v.work = c->d_cand; v.frame_bytes = c->frame_bytes;
   v.w = c->w; v.h = c->h; v.bw = c->bw; v.bh = c->bh; v.nb = c->nb;
   v.first = first; v.count = count; v.gop = gop;
   return v;
@@ -211,6 +209,11 @@ int check_params(mptc_gpu_ctx *c, int sa, int gop) {
   return MPTC_OK;
 }
 
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 int ensure_lanes(mptc_gpu_ctx *c, int n, int gop) {
   while ((int)c->lanes.size() < n) {
     Lane L;
@@ -229,10 +232,6 @@ int ensure_lanes(mptc_gpu_ctx *c, int n, int gop) {
   return MPTC_OK;
 }
 
-int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
 
 // Host buffers of an end-to-end call; all optional.
 struct HostIO {
@@ -285,7 +284,6 @@ int lane_prologue(mptc_gpu_ctx *c, Lane &L, int gop) {
   CU(c, cudaMemsetAsync(c->d_progress + (size_t)L.f0 * c->bh, 0, sizeof(int) * (size_t)L.n * c->bh, s));
   CU(c, cudaMemsetAsync(c->d_flags + (size_t)L.f0 * c->nb, 0, (size_t)L.n * c->nb, s));
   CU(c, cudaMemsetAsync(c->d_row_todo + (size_t)L.f0 * c->bh, 0, (size_t)L.n * c->bh, s));
-  CU(c, cudaMemsetAsync(c->d_tile_list + (size_t)L.f0 * c->tile_list_stride, 0, sizeof(int) * (size_t)L.n * c->tile_list_stride, s));
   return MPTC_OK;
 }
 
@@ -312,6 +310,9 @@ int enqueue_step(mptc_gpu_ctx *c, Lane &L, int k, int gop, int sa, int thr, bool
     stage_end(c, e, s);
   }
   if (k > 0) {
+    // (Measured and dropped, profiles/r2_k2_wide.txt: K2 on a low-priority stream of its own so that the
+    // lanes' short kernels overtake the other lanes' queued K2 CTAs -- the GPU no longer drains between
+    // rounds of frames, but the K2 CTAs then share their SMs with more of the short kernels: same step time.)
     StageEvent &e = stage_begin(L, 2, s);
     const int n_kernels = launch_inter_search(v, k, L.n_gops, sa, thr, s);
     stage_end(c, e, s, n_kernels);
@@ -538,8 +539,6 @@ int mptc_gpu_seq_reserve(mptc_gpu_ctx *c, int w, int h, int n_frames) {
   CU(c, cudaMalloc(&c->d_planes, F * c->plane_bytes));
   CU(c, cudaMalloc(&c->d_progress, F * c->bh * sizeof(int)));
   CU(c, cudaMalloc(&c->d_wordflag, F * nb * sizeof(unsigned long long)));
-  c->tile_list_stride = inter_tile_list_stride(c->bw, c->bh);
-  CU(c, cudaMalloc(&c->d_tile_list, F * c->tile_list_stride * sizeof(int)));
   CU(c, cudaMemset(c->d_wordflag, 0, F * nb * sizeof(unsigned long long)));   // epoch 0 is never used
   c->epoch = 0;
   c->cap_frames = n_frames;

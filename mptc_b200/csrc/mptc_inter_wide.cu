@@ -18,22 +18,27 @@
 //     warp works alone: it marks the words that occur in ITS sub-tile's 39x35 window, evaluates those
 //     against its 32 targets into a warp-private table, scans its targets' windows, and applies its
 //     winners -- no CTA barrier after the per-word constants.
-//   * The table is int16 {-1, 0, min(err_diff, 32767)} (the winner rule needs the sign of a negative
-//     err_diff and exact positive values only up to the threshold, dxt_image.cpp:890): 128 words x 36 x
-//     8 warps fit two CTAs per SM.  (Thresholds >= 32767 keep round 1's kernel and its int32 table.)
+//   * The table holds {-1, 0, min(err_diff, max)} (the winner rule needs the sign of a negative err_diff and
+//     exact positive values only up to the threshold, dxt_image.cpp:890): int8 entries (max 127) for
+//     thresholds below 127 -- 224 words x 36 targets x 8 warps fit two CTAs per SM --, int16 entries
+//     (max 32767, 128 words) above.  (Thresholds >= 32767 keep round 1's kernel and its int32 table.)
 //   * The scan walks COLUMNS of targets: the four targets (x, y0 .. y0+3) of a sub-tile column look at the
 //     same union-window positions one row apart, so one id read and one 8-byte table read (the four
 //     targets' entries of a word are adjacent: table[word][x][y]) serve four window positions.  The
 //     scan is bound by shared-memory wavefronts (random-bank table reads), not by issue slots: this cuts
 //     them by about three.
-//   * A tile whose union window holds more than 128 distinct words (word-diverse content: noise,
-//     err_threshold 0) is put on a list instead, and a second launch (k_inter_search_listed) runs round 1's
-//     tile search (mptc_inter_tile.cuh), whose window -- and therefore word count -- is that of 32 targets,
-//     over the listed tiles' 8x4 sub-tiles.
+//   * A tile whose union window holds more distinct words than the table (word-diverse content: noise,
+//     err_threshold 0) is handed, sub-tile by sub-tile, to round 1's tile search (mptc_inter_tile.cuh),
+//     whose window -- and therefore word count -- is that of 32 targets.  (A second launch that spread
+//     such tiles' sub-tiles over the GPU was measured and dropped: with four lanes of frames in flight it
+//     only lengthened every lane's chain of kernels; profiles/r2_k2_wide.txt.)
 //
 // Results are bit-identical to the position-by-position loop (tests/test_gpu_parity_small.py,
 // tests/test_gpu_full_golden.py run through whichever K2 the launcher picks; MPTC_K2=tiled|wide forces one).
 #include "mptc_inter_tile.cuh"
+
+#include <cstdio>
+#include <cstdlib>
 
 namespace mptc {
 
@@ -44,15 +49,14 @@ constexpr int kSubsX = 2, kSubsY = 4;          // sub-tiles per CTA
 constexpr int kTileX = kSubX * kSubsX, kTileY = kSubY * kSubsY;   // 16 x 16 targets
 constexpr int kWarps = kSubsX * kSubsY, kThreads = kWarps * 32;
 constexpr int kBatch = 9;                      // window loads in flight per thread (2209 positions / 256 threads at search_area 16)
-constexpr int kWords = 128;                    // distinct words a tile may hold on this path
-constexpr int kRow = 36;                       // int16 entries per table row: [lx][ly], 8-byte aligned rows, 18 words: odd multiple of 2 banks
-constexpr int kErr16Max = 32767;
-constexpr size_t kErrBytesPerWarp = (size_t)(kWords + 1) * kRow * 2;   // + the all-rejected row
-constexpr size_t kNeedBytesPerWarp = 144;      // kWords flags + the dummy id's, rounded to 16
+constexpr int kRow = 36;                       // table entries per word: [lx][ly] + 4 pad; rows of 9 / 18 words: an odd multiple of 1 / 2 banks
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;       // hash-table empty marker (the real word 0xFFFFFFFF lives in slot HT)
 constexpr uint16_t kNoPos = 0xFFFFu;           // window position outside the frame
 
-static_assert(kErrBytesPerWarp % 8 == 0, "table rows are read with 8-byte loads");
+// Table entry types: E = int8_t for err_threshold < 127, int16_t below 32767.
+template <typename E> struct Table;
+template <> struct Table<int8_t>  { static constexpr int kWords = 224, kMax = 127; };     // word ids fit the uint8 lists
+template <> struct Table<int16_t> { static constexpr int kWords = 128, kMax = 32767; };
 
 __host__ __device__ inline int wide_round_up_pow2(int x) {
   int p = 1;
@@ -64,39 +68,55 @@ struct WideLayout {
   int NP, HT;
   size_t off_keys, off_slot_uid;                       // phases 0-2 ...
   size_t off_info, off_err, off_need, off_wlist;       // ... share their bytes with phases 3-5
+  size_t err_per_warp, need_per_warp;
   size_t off_lut, off_ulist, off_pos, bytes;
 };
 
+template <typename E>
 __host__ __device__ inline WideLayout wide_layout(int sa) {
+  constexpr int kWords = Table<E>::kWords;
   WideLayout L;
   const int UW = 2 * sa + kTileX - 1, UH = 2 * sa + kTileY - 1;
   L.NP = UW * UH;
   L.HT = wide_round_up_pow2(L.NP + L.NP / 4);
   const size_t a = (((size_t)(L.HT + 1) * 4 + (size_t)(L.HT + 1) * 2) + 15) & ~(size_t)15;
+  L.err_per_warp = ((size_t)(kWords + 1) * kRow * sizeof(E) + 15) & ~(size_t)15;   // + the all-rejected row
+  L.need_per_warp = (size_t)kWords + 16;                                           // + the dummy id's flag
   L.off_keys = 0;
   L.off_slot_uid = (size_t)(L.HT + 1) * 4;
   L.off_info = 0;
   L.off_err = (size_t)kWords * sizeof(WordInfo);
-  L.off_need = L.off_err + kWarps * kErrBytesPerWarp;
-  L.off_wlist = L.off_need + kWarps * kNeedBytesPerWarp;
+  L.off_need = L.off_err + kWarps * L.err_per_warp;
+  L.off_wlist = L.off_need + kWarps * L.need_per_warp;
   const size_t e = L.off_wlist + (size_t)kWarps * kWords;
   size_t b = a > e ? a : e;
   L.off_lut = b;   b += 512;
-  L.off_ulist = b; b += (size_t)L.NP * 4;
+  L.off_ulist = b; b += (size_t)(kWords + 2) * 4;      // only the words of a tile that stays on this path
   L.off_pos = b;   b += (size_t)L.NP * 2;
   L.bytes = (b + 15) & ~(size_t)15;
+  const size_t t32 = tile32::tile_smem_bytes(sa, nullptr, nullptr);   // the word-diverse path's carve-up of the same bytes
+  if (t32 > L.bytes) L.bytes = t32;
   return L;
 }
 
 // One union-window row of a column of four targets: target y's window row is R - y.  e = the four
 // targets' table entries of the word at (R, column); kMask = which of the four have row R in their window.
 template <int kMask>
-__device__ __forceinline__ void column_step(WinnerState (&ws)[4], uint2 e, uint32_t p) {
+__device__ __forceinline__ void column_step(WinnerState (&ws)[4], uint2 e, uint32_t p) {   // int16 entries
   if (kMask & 1) winner_update_fast(ws[0], (int)(int16_t)(e.x & 0xFFFFu), p);
   if (kMask & 2) winner_update_fast(ws[1], (int)e.x >> 16, p);
   if (kMask & 4) winner_update_fast(ws[2], (int)(int16_t)(e.y & 0xFFFFu), p);
   if (kMask & 8) winner_update_fast(ws[3], (int)e.y >> 16, p);
 }
+template <int kMask>
+__device__ __forceinline__ void column_step(WinnerState (&ws)[4], uint32_t e, uint32_t p) {   // int8 entries
+  if (kMask & 1) winner_update_fast(ws[0], (int)(int8_t)(e & 0xFFu), p);
+  if (kMask & 2) winner_update_fast(ws[1], (int)(int8_t)((e >> 8) & 0xFFu), p);
+  if (kMask & 4) winner_update_fast(ws[2], (int)(int8_t)((e >> 16) & 0xFFu), p);
+  if (kMask & 8) winner_update_fast(ws[3], (int)e >> 24, p);
+}
+__device__ __forceinline__ uint2 load_entries(const int16_t *row) { return *reinterpret_cast<const uint2 *>(row); }
+__device__ __forceinline__ uint32_t load_entries(const int8_t *row) { return *reinterpret_cast<const uint32_t *>(row); }
 
 }  // namespace
 
@@ -108,18 +128,41 @@ extern "C" void mptc_debug_k2w_cycles(unsigned long long *out12, int reset) {
   cudaMemcpyFromSymbol(out12, g_k2w_cycles, sizeof(unsigned long long) * 12);
   if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(g_k2w_cycles, z, sizeof z); }
 }
+// per CTA since the last reset, in order of completion: {start ns, end ns, SM | distinct words << 16 | tile << 32}
+constexpr unsigned kTraceCap = 1u << 16;
+__device__ unsigned long long g_k2w_trace[3 * kTraceCap];
+__device__ unsigned g_k2w_trace_n;
+extern "C" int mptc_debug_k2w_trace(unsigned long long *out, int cap_entries, int reset) {
+  cudaDeviceSynchronize();
+  unsigned n = 0;
+  cudaMemcpyFromSymbol(&n, g_k2w_trace_n, sizeof n);
+  if (n > kTraceCap) n = kTraceCap;
+  if ((int)n > cap_entries) n = (unsigned)cap_entries;
+  if (out && n) cudaMemcpyFromSymbol(out, g_k2w_trace, sizeof(unsigned long long) * 3 * n);
+  if (reset) { const unsigned z = 0; cudaMemcpyToSymbol(g_k2w_trace_n, &z, sizeof z); }
+  return (int)n;
+}
+__device__ __forceinline__ unsigned long long k2w_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned k2w_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define K2W_TRACE_BEGIN() const unsigned long long trace_t0_ = k2w_now()
+#define K2W_TRACE_END(words) do { if (tid == 0) { const unsigned i_ = atomicAdd(&g_k2w_trace_n, 1u); if (i_ < kTraceCap) { g_k2w_trace[3 * i_] = trace_t0_; \
+    g_k2w_trace[3 * i_ + 1] = k2w_now(); g_k2w_trace[3 * i_ + 2] = k2w_smid() | ((unsigned long long)(words) << 16) | ((unsigned long long)blockIdx.x << 32); } } } while (0)
 #else
 #define K2W_MARK(i) do { } while (0)
+#define K2W_TRACE_BEGIN() do { } while (0)
+#define K2W_TRACE_END(words) do { } while (0)
 #endif
 
+template <typename E>
 __global__ void __launch_bounds__(kThreads, 2)
 k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
+  constexpr int kWords = Table<E>::kWords, kMax = Table<E>::kMax;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_count, s_special;
 
   const int W = 2 * sa;
   const int UW = W + kTileX - 1;
-  const WideLayout L = wide_layout(sa);
+  const WideLayout L = wide_layout<E>(sa);
   const int NP = L.NP, HT = L.HT;
   uint32_t *const keys = reinterpret_cast<uint32_t *>(smem_raw + L.off_keys);
   uint16_t *const slot_uid = reinterpret_cast<uint16_t *>(smem_raw + L.off_slot_uid);
@@ -142,13 +185,14 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
   const bool t_valid = tbx < v.bw && tby < v.bh;
   const int tb = tby * v.bw + tbx;
   const int n_valid = max(0, min(kSubX, v.bw - tx0 - sx0)) * max(0, min(kSubY, v.bh - ty0 - sy0));   // warp-uniform
-  int16_t *const err = reinterpret_cast<int16_t *>(smem_raw + L.off_err + (size_t)wid * kErrBytesPerWarp);
-  uint8_t *const need = smem_raw + L.off_need + (size_t)wid * kNeedBytesPerWarp;
+  E *const err = reinterpret_cast<E *>(smem_raw + L.off_err + (size_t)wid * L.err_per_warp);
+  uint8_t *const need = smem_raw + L.off_need + (size_t)wid * L.need_per_warp;
   uint8_t *const wlist = smem_raw + L.off_wlist + (size_t)wid * kWords;
 
 #ifdef MPTC_K2_PHASE_TIMING
   long long t_mark_ = clock64();
 #endif
+  K2W_TRACE_BEGIN();
   // ---- phase 0: clear the hash table -------------------------------------------------------
   for (int s = tid; s <= HT; s += kThreads) keys[s] = kEmpty;
   lut5[tid] = (uint8_t)snap_bits<0xF8, 4, 5>(tid);   // kThreads == 256
@@ -197,7 +241,7 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
           if (atomicExch(&s_special, 1) == 0) {
             const int uid = atomicAdd(&s_count, 1);
             slot_uid[HT] = (uint16_t)uid;
-            ulist[uid] = kEmpty;
+            if (uid <= kWords) ulist[uid] = kEmpty;
           }
           slot = (uint16_t)HT;
         } else {
@@ -207,7 +251,7 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
             if (old == kEmpty) {
               const int uid = atomicAdd(&s_count, 1);
               slot_uid[h] = (uint16_t)uid;
-              ulist[uid] = word;
+              if (uid <= kWords) ulist[uid] = word;
               break;
             }
             if (old == word) break;
@@ -224,12 +268,14 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
 
   const int U = s_count;
   if (U > kWords) {
-    // word-diverse tile: listed for k_inter_search_listed, which spreads its eight 8x4 sub-tiles over the
-    // GPU (handled here, one after the other, such a tile was the launch's tail: 4x an ordinary tile)
-    if (tid == 0) {
-      int *list = v.tile_list + (size_t)f * v.tile_list_stride;
-      list[1 + atomicAdd(list, 1)] = (int)blockIdx.x;
+    // word-diverse tile: round 1's search, one 8x4 sub-tile after the other, by the whole CTA
+    for (int sub_i = 0; sub_i < kWarps; ++sub_i) {
+      const int bx0 = tx0 + (sub_i & (kSubsX - 1)) * kSubX, by0 = ty0 + (sub_i / kSubsX) * kSubY;
+      if (bx0 >= v.bw || by0 >= v.bh) continue;
+      __syncthreads();                         // the shared memory changes hands
+      tile32::search_tile(v, f, bx0, by0, sa, thr, smem_raw);
     }
+    K2W_TRACE_END(U);
     return;
   }
 
@@ -243,12 +289,12 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
 
   // ---- phase 3: per-word constants for the CTA; each warp lists the words of ITS sub-tile's window ----
   for (int u = tid; u < U; u += kThreads) word_info(ulist[u], info[u]);
-  for (int u = lane; u < kRow; u += 32) err[kWords * kRow + u] = (int16_t)kErr16Max;   // the all-rejected row
+  for (int u = lane; u < kRow; u += 32) err[kWords * kRow + u] = (E)kMax;   // the all-rejected row
   const uint16_t *const sub = pos_uid + sy0 * UW + sx0;   // the sub-tile's window: (W + 7) x (W + 3) positions
   const int SW = W + kSubX - 1, SH = W + kSubY - 1;
   int n_need = 0;
   if (n_valid > 0) {
-    for (int u = lane; u < (int)kNeedBytesPerWarp / 4; u += 32) reinterpret_cast<uint32_t *>(need)[u] = 0u;
+    for (int u = lane; u < (int)L.need_per_warp / 4; u += 32) reinterpret_cast<uint32_t *>(need)[u] = 0u;
     __syncwarp();
     // plain byte stores (equal values may race); the dummy id kWords has a flag of its own
     for (int c = lane; c < SW; c += 32) {
@@ -269,11 +315,11 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
 
   if (n_valid > 0) {
     // ---- phase 4: evaluate the listed words against this warp's 32 targets ------------------------
-    int16_t *const my_err = err + lx * kSubY + ly;
+    E *const my_err = err + lx * kSubY + ly;
     for (int i = 0; i < n_need; ++i) {
       const int u = wlist[i];
       const int e = eval_uniform(t, ulist[u], info[u], lut5, lut6);
-      my_err[u * kRow] = (int16_t)(e < 0 ? -1 : min(e, kErr16Max));
+      my_err[u * kRow] = (E)(e < 0 ? -1 : min(e, kMax));
     }
     __syncwarp();
     K2W_MARK(4);   // evaluation (warp 0's)
@@ -291,9 +337,9 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
 #pragma unroll
         for (int y = 0; y < 4; ++y) winner_init(ws[y]);
         const uint16_t *q = sub + ttx + lane;
-        const unsigned char *tab = reinterpret_cast<const unsigned char *>(err + ttx * kSubY);
+        const E *tab = err + ttx * kSubY;
         uint32_t p = (uint32_t)lane;
-        auto entries = [&](int R) { return *reinterpret_cast<const uint2 *>(tab + (size_t)q[R * UW] * (kRow * 2)); };
+        auto entries = [&](int R) { return load_entries(tab + (int)q[R * UW] * kRow); };
         column_step<1>(ws, entries(0), p);  p += 128u;
         column_step<3>(ws, entries(1), p);  p += 128u;
         column_step<7>(ws, entries(2), p);  p += 128u;
@@ -320,7 +366,7 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
         if (tx0 + sx0 + ttx >= v.bw || ty0 + sy0 + tty >= v.bh) continue;   // warp-uniform
         WinnerState ws;
         winner_init(ws);
-        scan_window<false, int16_t, kRow>(ws, sub + tty * UW + ttx, UW, 1, err + ttx * kSubY + tty, W, 0, W, lane, 0, 0, kWords);
+        scan_window<false, E, kRow>(ws, sub + tty * UW + ttx, UW, 1, err + ttx * kSubY + tty, W, 0, W, lane, 0, 0, kWords);
         winner_warp_reduce(ws);
         if (lane == tt) mine = ws;
       }
@@ -351,39 +397,17 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
     }
     K2W_MARK(6);   // resolve + apply
   }
+  K2W_TRACE_END(U);   // (warp 0's end)
 }
-
-// The word-diverse tiles k_inter_search_wide listed, by round 1's 8x4 tile search: CTA i of a frame takes the
-// sub-tiles i, i + gridDim.x, ... of the list (eight per listed tile).
-__global__ void __launch_bounds__(tile32::kThreads, 2)
-k_inter_search_listed(SeqView v, int k_in_gop, int sa, int thr) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int f = v.first + blockIdx.y * v.gop + k_in_gop;
-  if (f >= v.first + v.count) return;
-  const int *list = v.tile_list + (size_t)f * v.tile_list_stride;
-  const int n = list[0] * kWarps;
-  const int tiles_x = (v.bw + kTileX - 1) / kTileX;
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const int tile = list[1 + i / kWarps], sub_i = i % kWarps;
-    const int bx0 = (tile % tiles_x) * kTileX + (sub_i & (kSubsX - 1)) * kSubX;
-    const int by0 = (tile / tiles_x) * kTileY + (sub_i / kSubsX) * kSubY;
-    if (bx0 >= v.bw || by0 >= v.bh) continue;
-    if (i != (int)blockIdx.x) __syncthreads();   // the shared memory starts over
-    tile32::search_tile(v, f, bx0, by0, sa, thr, smem_raw);
-  }
-}
-
-int inter_tile_list_stride(int bw, int bh) { return 1 + ((bw + kTileX - 1) / kTileX) * ((bh + kTileY - 1) / kTileY); }
 
 // Returns false when the kernel does not apply (nothing launched): the caller then uses the round-1 tiling.
 // two_per_sm_only: decline unless two CTAs fit an SM.
-bool launch_inter_search_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, bool two_per_sm_only, cudaStream_t s) {
-  static int max_optin = -1, max_sm = -1, n_sm = 0;
-  static size_t configured[kMaxDevices] = {0}, configured_listed[kMaxDevices] = {0};
-  const WideLayout L = wide_layout(sa);
-  const size_t bytes32 = tile32::tile_smem_bytes(sa, nullptr, nullptr);
+template <typename E>
+static bool launch_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, bool two_per_sm_only, cudaStream_t s) {
+  static int max_optin = -1, max_sm = -1;
+  static size_t configured[kMaxDevices] = {0};
+  const WideLayout L = wide_layout<E>(sa);
   if (L.NP >= 0xFFFF) return false;            // 16-bit word ids
-  if (thr >= kErr16Max) return false;          // the int16 table clamps at 32767
   int cur_dev = 0;
   cudaGetDevice(&cur_dev);
   {
@@ -391,28 +415,34 @@ bool launch_inter_search_wide(const SeqView &v, int k_in_gop, int n_gops, int sa
     if (max_optin < 0) {
       cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cur_dev);
       cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cur_dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cur_dev);
     }
-    if (L.bytes + 1024 > (size_t)max_optin || bytes32 + 1024 > (size_t)max_optin) return false;
+    if (L.bytes + 1024 > (size_t)max_optin) return false;
     if (two_per_sm_only && 2 * (L.bytes + 1024 + 64) > (size_t)max_sm) return false;
     size_t &conf = configured[cur_dev & (kMaxDevices - 1)];
     if (L.bytes > conf) {
-      if (cudaFuncSetAttribute(k_inter_search_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes) != cudaSuccess)
+      if (cudaFuncSetAttribute(k_inter_search_wide<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes) != cudaSuccess)
         return false;
+      // two CTAs need nearly all of the SM's shared memory: ask for the largest carve-out outright
+      cudaFuncSetAttribute(k_inter_search_wide<E>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (getenv("MPTC_DEBUG_OCC")) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_inter_search_wide<E>, kThreads, L.bytes);
+        fprintf(stderr, "mptc: k_inter_search_wide<int%d>: %zu B dynamic shared memory, %d CTAs per SM (sa %d)\n",
+                (int)sizeof(E) * 8, L.bytes, per_sm, sa);
+      }
       conf = L.bytes;
-    }
-    size_t &conf32 = configured_listed[cur_dev & (kMaxDevices - 1)];
-    if (bytes32 > conf32) {
-      if (cudaFuncSetAttribute(k_inter_search_listed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes32) != cudaSuccess)
-        return false;
-      conf32 = bytes32;
     }
   }
   const int tiles = ((v.bw + kTileX - 1) / kTileX) * ((v.bh + kTileY - 1) / kTileY);
-  k_inter_search_wide<<<dim3(tiles, n_gops), kThreads, L.bytes, s>>>(v, k_in_gop, sa, thr);
-  const int ctas = min(tiles * kWarps, 2 * n_sm);
-  k_inter_search_listed<<<dim3(ctas, n_gops), tile32::kThreads, bytes32, s>>>(v, k_in_gop, sa, thr);
+  k_inter_search_wide<E><<<dim3(tiles, n_gops), kThreads, L.bytes, s>>>(v, k_in_gop, sa, thr);
   return true;
+}
+
+bool launch_inter_search_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, bool two_per_sm_only, cudaStream_t s) {
+  static const bool no_int8 = getenv("MPTC_K2_NO_INT8") != nullptr;   // A/B measurements
+  if (thr < Table<int8_t>::kMax && !no_int8 && launch_wide<int8_t>(v, k_in_gop, n_gops, sa, thr, two_per_sm_only, s)) return true;
+  if (thr < Table<int16_t>::kMax) return launch_wide<int16_t>(v, k_in_gop, n_gops, sa, thr, two_per_sm_only, s);
+  return false;
 }
 
 }  // namespace mptc

@@ -546,9 +546,9 @@ int launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int 
     const char *e = getenv("MPTC_K2");
     return !e ? 0 : (!strcmp(e, "wide") ? 1 : (!strcmp(e, "tiled") ? 2 : 0));
   }();
-  if (forced != 2 && launch_inter_search_wide(v, k_in_gop, n_gops, sa, thr, /*two_per_sm_only=*/forced == 0, s)) return 2;
+  if (forced != 2 && launch_inter_search_wide(v, k_in_gop, n_gops, sa, thr, /*two_per_sm_only=*/forced == 0, s)) return 1;
   if (launch_inter_search_tiled(v, k_in_gop, n_gops, sa, thr, s)) return 1;
-  if (forced == 0 && launch_inter_search_wide(v, k_in_gop, n_gops, sa, thr, false, s)) return 2;
+  if (forced == 0 && launch_inter_search_wide(v, k_in_gop, n_gops, sa, thr, false, s)) return 1;
   dim3 grid(v.nb, n_gops);  // direct (one CTA per target) fallback for very large windows
   k_inter_search<<<grid, kSearchThreads, 0, s>>>(v, k_in_gop, sa, thr);
   return 1;

@@ -28,8 +28,6 @@ struct SeqView {
   int *progress;           // [F][bh]   wavefront progress counters (direct fallback kernel only)
   unsigned long long *wordflag;  // [F][nb] {index word, epoch}: how the rows of the intra wavefront hand decisions over
   uint32_t epoch;          // tag of this encode call in `wordflag` (entries of earlier calls are stale)
-  int *tile_list;          // [F][tile_list_stride] K2: [0] = number of word-diverse 16x16 tiles, then their tile ids
-  int tile_list_stride;    //   (inter_tile_list_stride(bw, bh); zeroed per encode call)
   unsigned long long *work; // executed-work counters of the search kernels (kWork*), one atomicAdd per tile / group
   size_t frame_bytes;
   int w, h, bw, bh, nb;
@@ -56,11 +54,9 @@ cudaError_t upload_tables(const uint8_t *omatch5, const uint8_t *omatch6);
 void launch_dxt1_fit(const SeqView &v, int f0, int fstride, int nf, cudaStream_t s);
 // Returns the number of kernels launched.
 int launch_inter_search(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
-int inter_tile_list_stride(int bw, int bh);
 bool launch_intra_rows(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, int *ticket, int grid_cap,
                        cudaStream_t s);
 bool launch_inter_search_tiled(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, cudaStream_t s);
-// (two launches: the 16x16-tile kernel, then the listed word-diverse tiles by the 8x4 tile search)
 bool launch_inter_search_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, bool two_per_sm_only, cudaStream_t s);
 // grid_cap > 0 limits the number of CTAs (rows in flight): a wavefront only keeps a few rows per
 // frame busy, and idle CTAs would block the SMs for kernels of other lanes.

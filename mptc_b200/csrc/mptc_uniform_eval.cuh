@@ -103,7 +103,8 @@ __device__ __forceinline__ uint32_t div3(uint32_t x) { return __umulhi(x, 0x5555
 __device__ __forceinline__ uint32_t plane_error(const uint32_t *plane, uint32_t palch, const uint32_t *sel, uint32_t sum) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const uint32_t c = __byte_perm(palch, 0u, sel[r]);
+    uint32_t c;   // __byte_perm masks the selector first; the nibbles here are 0..3 by construction
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(c) : "r"(palch), "r"(0u), "r"(sel[r]));
     const uint32_t d = __vabsdiffu4(plane[r], c);
     sum = __dp4a(d, d, sum);
   }

@@ -41,7 +41,7 @@ for name in sequence_cases():
     res[name] = sha(out["blocks"]) + sha(out["motion"])
 rng = np.random.default_rng(7)
 noise = rng.integers(0, 256, (3, 256, 512, 3), dtype=np.uint8)
-for sa, thr in ((16, 50), (16, 0), (8, 40000), (5, 50), (20, 10)):
+for sa, thr in ((16, 50), (16, 0), (8, 40000), (5, 50), (20, 10), (16, 200), (7, 5000)):
     out = encode(noise, sa, thr, 3)
     res["noise_sa%%d_thr%%d" %% (sa, thr)] = sha(out["blocks"]) + sha(out["motion"])
 frames = np.stack([make_frame(1920, 1080, f) for f in range(15)])
