@@ -542,7 +542,7 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
     ev, stale = ncu_evidence(dominant)
     traffic = ev["dram_bytes_per_frame"] * n_gops if ev and "dram_bytes_per_frame" in ev else None
     roofline = {
-        "kernel": "k_inter_search_tiled" if dominant == "inter" else "k_intra_rows",
+        "kernel": ("k_inter_search_wide<int8_t>" if (SA <= 16 and THR < 127) else "k_inter_search_tiled") if dominant == "inter" else "k_intra_rows",
         "measured": "CUDA events around each launch in a one-lane pass of the same workload (kernels serialised)",
         "share_of_step": k_ms / serial_total, "serial_step_ms": serial_total, "serial_stage_ms": serial_ms,
         "bound": "issue", "achieved": achieved, "peak": issue_peak, "unit": "Tslot/s", "frac": achieved / issue_peak,
@@ -553,7 +553,7 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
         "units_per_launch": evals / max(k_launches, 1), "launches_per_step": k_launches,
         "avg_launch_ms": k_ms / max(k_launches, 1), "algo_slots_per_unit": ALGO_SLOTS_PER_CANDIDATE,
         "scan_slots_per_position": SCAN_SLOTS_PER_POSITION,
-        "distinct_words_per_tile": work["inter_evals"] / max(1, 32 * work["inter_tiles"]),
+        "evaluations_per_target_block": work["inter_evals"] / max(1, n_gops * (GOP - 1) * nb),
         # what the same time would score if every window position were evaluated, as the reference does
         # and as SURVEY.md 8(d) counts: the de-duplication's gain, not a roofline fraction
         "nominal_candidates_per_step": nominal,

@@ -108,15 +108,49 @@ __device__ __forceinline__ void column_step(WinnerState (&ws)[4], uint2 e, uint3
   if (kMask & 4) winner_update_fast(ws[2], (int)(int16_t)(e.y & 0xFFFFu), p);
   if (kMask & 8) winner_update_fast(ws[3], (int)e.y >> 16, p);
 }
-template <int kMask>
-__device__ __forceinline__ void column_step(WinnerState (&ws)[4], uint32_t e, uint32_t p) {   // int8 entries
-  if (kMask & 1) winner_update_fast(ws[0], (int)(int8_t)(e & 0xFFu), p);
-  if (kMask & 2) winner_update_fast(ws[1], (int)(int8_t)((e >> 8) & 0xFFu), p);
-  if (kMask & 4) winner_update_fast(ws[2], (int)(int8_t)((e >> 16) & 0xFFu), p);
-  if (kMask & 8) winner_update_fast(ws[3], (int)e >> 24, p);
-}
 __device__ __forceinline__ uint2 load_entries(const int16_t *row) { return *reinterpret_cast<const uint2 *>(row); }
 __device__ __forceinline__ uint32_t load_entries(const int8_t *row) { return *reinterpret_cast<const uint32_t *>(row); }
+
+// Table entry of an err_diff.  int16: {-1, 0, min(e, 32767)}.  int8: bit 7 = "negative", bits 0-6 = min(max(e, 0), 127),
+// i.e. 0x80 for a negative err_diff -- read as a signed byte that is still negative, which is all winner_update_fast
+// needs -- and the form the packed scan below takes apart.
+__device__ __forceinline__ int16_t encode_entry(int e, int16_t) { return (int16_t)(e < 0 ? -1 : min(e, 32767)); }
+__device__ __forceinline__ int8_t encode_entry(int e, int8_t) { return (int8_t)(e < 0 ? -128 : min(e, 127)); }
+
+// The int8 column scan keeps, per lane (= window column) and for the four targets of a sub-tile column at once:
+//   key  (16 bits per target, two registers): min over the rows of (c << 6 | R), c = the entry's low 7 bits, R = the
+//        union-window row.  A lane that saw an err_diff <= 0 ends with c == 0 and R = its first such row (the
+//        reference's `first`); otherwise with its smallest positive err_diff and that one's first row (`best`) --
+//        `best` is only consulted when no candidate is <= 0, so one minimum serves both.
+//   last (8 bits per target, one register): R + 1 of the last row with a negative entry, 0 = none (rows ascend, so the
+//        newest negative row simply replaces the byte).
+// 18 instructions per four window positions instead of 39 with one WinnerState per target.
+struct PackedColumn {
+  uint32_t key01, key23, last;
+};
+template <int kMask>   // which of the four targets have union row R inside their window
+__device__ __forceinline__ void packed_step(PackedColumn &pc, uint32_t w, uint32_t rr, uint32_t r1) {
+  if (kMask != 15) {   // rows above / below a target's window: "rejected, not negative"
+    constexpr uint32_t keep = (kMask & 1 ? 0xFFu : 0u) | (kMask & 2 ? 0xFF00u : 0u) | (kMask & 4 ? 0xFF0000u : 0u) | (kMask & 8 ? 0xFF000000u : 0u);
+    w = (w & keep) | (0x7F7F7F7Fu & ~keep);
+  }
+  const uint32_t h01 = __byte_perm(w, 0u, 0x4140), h23 = __byte_perm(w, 0u, 0x4342);   // bytes -> halves
+  pc.key01 = __vminu2(pc.key01, (h01 & 0x007F007Fu) * 64u + rr);
+  pc.key23 = __vminu2(pc.key23, (h23 & 0x007F007Fu) * 64u + rr);
+  const uint32_t n = (w & 0x80808080u) >> 7;             // 1 per byte with a negative entry
+  pc.last = (pc.last & ~(n * 255u)) | (n * r1);
+}
+// One target's result of a packed column scan as a WinnerState in the target's own rows (y = its row in the sub-tile).
+__device__ __forceinline__ WinnerState unpack_column(const PackedColumn &pc, int y, int lane) {
+  const uint32_t key = ((y & 2) ? pc.key23 : pc.key01) >> (16 * (y & 1)) & 0xFFFFu;
+  const uint32_t lastb = (pc.last >> (8 * y)) & 0xFFu;
+  const uint32_t c = key >> 6, p = (((key & 63u) - (uint32_t)y) << 7) | (uint32_t)lane;
+  WinnerState ws;
+  ws.first = c == 0u ? p : 0xFFFFFFFFu;
+  ws.best = ((c + 65536u) << 14) | p;
+  ws.lastneg = lastb ? (int)(((lastb - 1u - (uint32_t)y) << 7) | (127u - (uint32_t)lane)) : -1;
+  return ws;
+}
 
 }  // namespace
 
@@ -319,7 +353,7 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
     for (int i = 0; i < n_need; ++i) {
       const int u = wlist[i];
       const int e = eval_uniform(t, ulist[u], info[u], lut5, lut6);
-      my_err[u * kRow] = (E)(e < 0 ? -1 : min(e, kMax));
+      my_err[u * kRow] = encode_entry(e, E());
     }
     __syncwarp();
     K2W_MARK(4);   // evaluation (warp 0's)
@@ -329,33 +363,53 @@ k_inter_search_wide(SeqView v, int k_in_gop, int sa, int thr) {
     winner_init(mine);
     if (W == 32) {
       // lane = window column; the four targets of a sub-tile column share every id and table read.
-      // Positions are keyed by the UNION row R (target y's own row is R - y: subtracted after the reduction).
 #pragma unroll 1
       for (int ttx = 0; ttx < kSubX; ++ttx) {
         if (tx0 + sx0 + ttx >= v.bw) break;    // warp-uniform
-        WinnerState ws[4];
-#pragma unroll
-        for (int y = 0; y < 4; ++y) winner_init(ws[y]);
         const uint16_t *q = sub + ttx + lane;
         const E *tab = err + ttx * kSubY;
-        uint32_t p = (uint32_t)lane;
         auto entries = [&](int R) { return load_entries(tab + (int)q[R * UW] * kRow); };
-        column_step<1>(ws, entries(0), p);  p += 128u;
-        column_step<3>(ws, entries(1), p);  p += 128u;
-        column_step<7>(ws, entries(2), p);  p += 128u;
+        if constexpr (sizeof(E) == 1) {
+          PackedColumn pc = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u};
+          uint32_t rr = 0u, r1 = 1u;           // R in both halves; R + 1
+          packed_step<1>(pc, entries(0), rr, r1);  rr += 0x00010001u; ++r1;
+          packed_step<3>(pc, entries(1), rr, r1);  rr += 0x00010001u; ++r1;
+          packed_step<7>(pc, entries(2), rr, r1);  rr += 0x00010001u; ++r1;
 #pragma unroll 4
-        for (int R = 3; R < 32; ++R, p += 128u) column_step<15>(ws, entries(R), p);
-        column_step<14>(ws, entries(32), p);  p += 128u;
-        column_step<12>(ws, entries(33), p);  p += 128u;
-        column_step<8>(ws, entries(34), p);
+          for (int R = 3; R < 32; ++R, rr += 0x00010001u, ++r1) packed_step<15>(pc, entries(R), rr, r1);
+          packed_step<14>(pc, entries(32), rr, r1);  rr += 0x00010001u; ++r1;
+          packed_step<12>(pc, entries(33), rr, r1);  rr += 0x00010001u; ++r1;
+          packed_step<8>(pc, entries(34), rr, r1);
 #pragma unroll
-        for (int y = 0; y < 4; ++y) {
-          if (ty0 + sy0 + y >= v.bh) break;    // warp-uniform
-          winner_warp_reduce(ws[y]);
-          if (lane == y * kSubX + ttx) {       // back to the target's own rows
-            const uint32_t d = (uint32_t)y << 7;
-            ws[y].first -= d;  ws[y].lastneg -= (int)d;  ws[y].best -= d;
-            mine = ws[y];
+          for (int y = 0; y < 4; ++y) {
+            if (ty0 + sy0 + y >= v.bh) break;    // warp-uniform
+            WinnerState ws = unpack_column(pc, y, lane);
+            winner_warp_reduce(ws);
+            if (lane == y * kSubX + ttx) mine = ws;
+          }
+        } else {
+          // Positions are keyed by the UNION row R (target y's own row is R - y: subtracted after the reduction).
+          WinnerState ws[4];
+#pragma unroll
+          for (int y = 0; y < 4; ++y) winner_init(ws[y]);
+          uint32_t p = (uint32_t)lane;
+          column_step<1>(ws, entries(0), p);  p += 128u;
+          column_step<3>(ws, entries(1), p);  p += 128u;
+          column_step<7>(ws, entries(2), p);  p += 128u;
+#pragma unroll 4
+          for (int R = 3; R < 32; ++R, p += 128u) column_step<15>(ws, entries(R), p);
+          column_step<14>(ws, entries(32), p);  p += 128u;
+          column_step<12>(ws, entries(33), p);  p += 128u;
+          column_step<8>(ws, entries(34), p);
+#pragma unroll
+          for (int y = 0; y < 4; ++y) {
+            if (ty0 + sy0 + y >= v.bh) break;    // warp-uniform
+            winner_warp_reduce(ws[y]);
+            if (lane == y * kSubX + ttx) {       // back to the target's own rows
+              const uint32_t d = (uint32_t)y << 7;
+              ws[y].first -= d;  ws[y].lastneg -= (int)d;  ws[y].best -= d;
+              mine = ws[y];
+            }
           }
         }
       }

@@ -12,7 +12,7 @@ MPTC_LANES=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra-l
 MPTC_LANES=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-legs > gpurun_out/${TAG}_launches.log 2>&1
 MPTC_LANES=1 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_inter_search_tiled|k_intra_rows|k_intra_sparse' --launch-skip 4 -c 4 -f -o gpurun_out/${TAG}_search \
+    -k regex:'k_inter_search_wide|k_inter_search_tiled|k_intra_rows|k_intra_sparse' --launch-skip 4 -c 4 -f -o gpurun_out/${TAG}_search \
     python profiles/prof_cmd.py > gpurun_out/${TAG}_search.log 2>&1
 MPTC_LANES=1 ncu --set full --clock-control none --import-source on \
     -k regex:'k_dxt1_fit|k_endpoint_planes|k_compact_unique|k_compact_count' --launch-skip 4 -c 4 -f -o gpurun_out/${TAG}_stream \

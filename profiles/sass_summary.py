@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
-KERNELS = ["k_inter_search_tiled", "k_intra_rows", "k_dxt1_to_rgb", "k_inter_pixel_search", "k_dxt1_fit", "k_endpoint_planes"]
+KERNELS = ["k_inter_search_wide", "k_inter_search_tiled", "k_intra_rows", "k_dxt1_to_rgb", "k_inter_pixel_search", "k_dxt1_fit", "k_endpoint_planes"]
 txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "mptc_b200", "libmptc_b200.so")], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
 out = [f"opcode histograms of the sm_100a SASS (cuobjdump -sass mptc_b200/libmptc_b200.so), {TAG}\n"]
