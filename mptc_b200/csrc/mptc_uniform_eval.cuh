@@ -150,8 +150,13 @@ __device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, 
     b1 = min(__float2uint_rz(__fadd_rn(q4, 0.5f)), 255u); b2 = min(__float2uint_rz(__fadd_rn(q5, 0.5f)), 255u);
   }
   r1 = lut5[r1]; r2 = lut5[r2]; g1 = lut6[g1]; g2 = lut6[g2]; b1 = lut5[b1]; b2 = lut5[b2];
-  const uint32_t pk1 = ((r1 & 0xF8u) << 8) | ((g1 & 0xFCu) << 3) | (b1 >> 3);
-  const uint32_t pk2 = ((r2 & 0xF8u) << 8) | ((g2 & 0xFCu) << 3) | (b2 >> 3);
+  // Pack565(ep1) > Pack565(ep2) (dxt_image.cpp:344) compares (r5, g6, b5) lexicographically: the same order as
+  // the three bytes (r, g, b) with the bits Pack565 drops masked off.  (Not the unmasked bytes: ToFiveBits /
+  // ToSixBits as written return values such as 12 whose low bits are not a replica of the high ones.)  The 565
+  // words themselves are only assembled when the caller wants them.  Bytes 1-3 of the six values are zero:
+  // selector nibbles 1 and 5 fetch a zero byte.
+  const uint32_t key1 = __byte_perm(__byte_perm(b1, g1, 0x1140), r1, 0x5410) & 0x00F8FCF8u;   // b | g << 8 | r << 16
+  const uint32_t key2 = __byte_perm(__byte_perm(b2, g2, 0x1140), r2, 0x5410) & 0x00F8FCF8u;
   // palette per channel, entry v in byte v: ep1, ep2, (2*ep1+ep2)/3, (ep1+2*ep2)/3
   const uint32_t palr = r1 | (r2 << 8) | (div3(2u * r1 + r2) << 16) | (div3(r1 + 2u * r2) << 24);
   const uint32_t palg = g1 | (g2 << 8) | (div3(2u * g1 + g2) << 16) | (div3(g1 + 2u * g2) << 24);
@@ -159,9 +164,13 @@ __device__ __forceinline__ int eval_uniform(const LaneTarget &t, uint32_t word, 
   uint32_t sum = plane_error(t.pl + 0, palr, wi.sel, 0u);
   sum = plane_error(t.pl + 4, palg, wi.sel, sum);
   sum = plane_error(t.pl + 8, palb, wi.sel, sum);
-  if (packed_out) *packed_out = pk1 | (pk2 << 16);
+  if (packed_out) {
+    const uint32_t pk1 = ((r1 & 0xF8u) << 8) | ((g1 & 0xFCu) << 3) | (b1 >> 3);
+    const uint32_t pk2 = ((r2 & 0xF8u) << 8) | ((g2 & 0xFCu) << 3) | (b2 >> 3);
+    *packed_out = pk1 | (pk2 << 16);
+  }
   int e = (int)(sum / 48u) - t.orig_err;
-  e = (pk1 > pk2) ? e : kRejectedSmall;
+  e = (key1 > key2) ? e : kRejectedSmall;
   return (word == t.own_word) ? 0 : e;
 }
 
