@@ -40,7 +40,10 @@ constexpr int kG = 32;                        // targets per group
 #define MPTC_K3R_THREADS 512
 #endif
 constexpr int kThreads = MPTC_K3R_THREADS, kWarps = kThreads / 32;
-constexpr int kCtasPerSm = kThreads <= 256 ? 2 : 1;
+#ifndef MPTC_K3R_CTAS_PER_SM
+#define MPTC_K3R_CTAS_PER_SM (MPTC_K3R_THREADS <= 256 ? 2 : 1)
+#endif
+constexpr int kCtasPerSm = MPTC_K3R_CTAS_PER_SM;
 // distinct words per group on the fast path (with two CTAs per SM the tables of both must fit the SM's
 // 228 KB of shared memory)
 constexpr int kMaxWords = kCtasPerSm == 2 ? 240 : 256;
