@@ -86,27 +86,81 @@ def measured_peaks():
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions: an NVML polling thread (a sample every few
+    milliseconds -- the timed regions of the default run are only ~0.2 s long, too short for `nvidia-smi -lms`,
+    whose first sample arrives after ~0.1 s), with `nvidia-smi` as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, device_index: int):
         self.dev = device_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []       # (sm MHz, reasons bitmask)
+        self.sm_max = None
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.dev < len(ids) and ids[self.dev].isdigit():
+                return int(ids[self.dev])
+        return self.dev
+
+    def _one(self, nv, h):
+        try:
+            self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                 int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            import pynvml as nv
+            import threading
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+            self._nv, self._h = nv, h
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    self._one(nv, h)
+                    self.stop_flag.wait(0.004)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.dev), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.dev), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._one(self._nv, self._h)      # one more while the last step's kernels have only just ended
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                bits = 0
+                for _, b in self.samples:
+                    bits |= b
+                out.update(sm_mhz=float(np.median([x for x, _ in self.samples])), sm_max_mhz=self.sm_max,
+                           samples=len(self.samples), reasons=sorted(n for m, n in self.REASONS if bits & m), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -133,7 +187,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm), reasons=sorted(reasons))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm), reasons=sorted(reasons), source="nvidia-smi")
         return out
 
 
@@ -635,7 +689,7 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mptc_b200", choices=["mptc_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
