@@ -537,7 +537,8 @@ def gpu_arm(args, rank: int, world: int, local_rank: int):
                              f"search_area={sa}, err_threshold={thr}, gop={GOP}",
                  "value": pix / (x["step_ms"] * 1e-3) / 1e6, "ms_per_step": x["step_ms"],
                  "e2e": pix / (x["e2e_ms"] * 1e-3) / 1e6, "unit": UNIT, "n_unique": x["n_unique_sum"],
-                 "distinct_words_per_inter_tile": x["work"]["inter_evals"] / max(1, 32 * x["work"]["inter_tiles"])}
+                 # distinct index words a target block's window holds on average = evaluations per target block
+                 "evaluations_per_target_block": x["work"]["inter_evals"] / max(1, (h // 4) * (w // 4) * (n_frames - (n_frames + GOP - 1) // GOP))}
             if stream:
                 o["e2e_stream"] = pix / (x["stream_ms"] * 1e-3) / 1e6
             if "parity" in x:
