@@ -71,6 +71,11 @@ int mptc_assemble_stream(int n_frames, int w, int h, const mptc_gpu_params *p, c
  * Adaptive_Data_Model(257), Arithmetic_Codec::decode (arithmetic_codec.cpp:391-444).
  * MPTC_E_DATA if the code runs out or decodes a symbol outside 0..255. */
 int mptc_arith_decode(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n);
+/* k (1..8) independent streams -- e.g. the motion stream and the endpoint-plane streams of a frame, which
+ * EntropyDecode handles one after the other -- decoded in one interleaved loop on the calling thread: each symbol
+ * costs a 32-bit division and a dependent table walk, and with several chains in flight most of that latency
+ * hides.  Same results and errors as k calls of mptc_arith_decode. */
+int mptc_arith_decode_multi(int k, const uint8_t *const *code, const size_t *nbytes, uint8_t *const *sym, const size_t *n);
 
 /* The 34-byte stream header (reader: codec.cpp:1172-1184). */
 typedef struct mptc_stream_header {

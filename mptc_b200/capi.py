@@ -354,7 +354,7 @@ class Context:
 
 # ---- host codec (include/mptc_codec.h) -----------------------------------------------------------
 CODEC_EXPORTS = ["mptc_arith_encode", "mptc_frame_payload", "mptc_encode_stream", "mptc_assemble_stream",
-                 "mptc_arith_decode", "mptc_stream_info", "mptc_decode_stream"]
+                 "mptc_arith_decode", "mptc_arith_decode_multi", "mptc_stream_info", "mptc_decode_stream"]
 
 
 class StreamHeader(C.Structure):
@@ -387,6 +387,7 @@ def _codec():
         L.mptc_assemble_stream.argtypes = [ci, ci, ci, C.POINTER(Params), vp, vp, vp, vp, ci, vp, sz, C.POINTER(sz),
                                            C.POINTER(StreamStats)]
         L.mptc_arith_decode.argtypes = [vp, sz, vp, sz]
+        L.mptc_arith_decode_multi.argtypes = [C.c_int, vp, vp, vp, vp]
         L.mptc_stream_info.argtypes = [vp, sz, C.POINTER(StreamHeader)]
         L.mptc_decode_stream.argtypes = [vp, vp, sz, ci, vp, vp, C.POINTER(DecodeStats)]
         L._codec_ready = True
@@ -401,6 +402,21 @@ def arith_decode(code: bytes, n: int) -> np.ndarray:
     if r != MPTC_OK:
         raise MptcError(f"mptc_arith_decode failed: {r}")
     return out
+
+
+def arith_decode_multi(codes, ns):
+    """Up to eight independent streams decoded in one interleaved loop (mptc_arith_decode_multi)."""
+    k = len(codes)
+    bufs = [np.frombuffer(c, dtype=np.uint8) for c in codes]
+    outs = [np.empty(n, dtype=np.uint8) for n in ns]
+    code_p = (C.c_void_p * k)(*[b.ctypes.data if b.size else None for b in bufs])
+    sym_p = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+    nbytes = (C.c_size_t * k)(*[b.size for b in bufs])
+    nn = (C.c_size_t * k)(*ns)
+    r = _codec().mptc_arith_decode_multi(k, code_p, nbytes, sym_p, nn)
+    if r != MPTC_OK:
+        raise MptcError(f"mptc_arith_decode_multi failed: {r}")
+    return outs
 
 
 def stream_info(stream: bytes) -> StreamHeader:

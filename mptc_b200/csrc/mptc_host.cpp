@@ -5,6 +5,9 @@
 #include "../../include/mptc_codec.h"
 #include "mptc_host.h"
 
+#include <emmintrin.h>
+
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
@@ -12,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <type_traits>
 #include <thread>
 
 namespace mptc {
@@ -209,10 +213,11 @@ namespace {
 constexpr unsigned kTableShift = 8;                            // 128 buckets over the 15-bit range (1024 buckets
                                                                // + branch-free steps measured 28 % slower: rebuilds)
 constexpr unsigned kTableSize = (1u << kLengthShift) >> kTableShift;
+constexpr unsigned kSearchWidth = 8;                           // cumulative frequencies compared per vector step
 }  // namespace
 
 RangeDecoder::RangeDecoder(unsigned symbols)
-    : n_(symbols < 257 ? 257 : symbols), dist_(n_ + 1), count_(n_), start_(kTableSize) {}
+    : n_(symbols < 257 ? 257 : symbols), dist_(n_ + 1 + kSearchWidth, 0x7FFFFFFFu), count_(n_), start_(kTableSize) {}
 
 void RangeDecoder::reset_model() {     // Adaptive_Data_Model::reset (arithmetic_codec.cpp:818-829)
   total_ = 0;
@@ -268,11 +273,14 @@ inline void RangeDecoder::begin(State &d, const uint8_t *code, size_t nbytes) {
   d.until = until_;
 }
 
-// Arithmetic_Codec::decode(Adaptive_Data_Model &) (arithmetic_codec.cpp:391-444)
-// (Measured and dropped: replacing the 32-bit division by a float-reciprocal estimate that only picks
-// the start bucket, with the exact comparison made on the products dist[s] * len -- 57 -> 42 Msym/s
-// single-stream on the build container's Xeon: its divider is not the bottleneck, the longer
-// dependent chain of conversions is slower.)
+// Arithmetic_Codec::decode(Adaptive_Data_Model &) (arithmetic_codec.cpp:391-444), without data-dependent
+// branches in the common case: the symbol search compares eight cumulative frequencies at once (SSE2; they
+// ascend strictly, so the first one above the target ends the search), the renormalisation shifts in zero,
+// one or two bytes at once (the interval is at least 2^9 wide after a step, so never three).  The branchy
+// form -- `while (dist[s + 1] <= dv) ++s;` and a byte-wise renormalisation loop -- mispredicted about twice
+// per symbol, and a misprediction throws away the work of all interleaved streams.
+// (Measured and dropped earlier: replacing the 32-bit division by a float-reciprocal estimate, 57 -> 42 Msym/s.)
+#ifdef MPTC_DECODER_BRANCHY
 inline uint8_t RangeDecoder::step(State &d) {
   const uint32_t *dist = dist_.data();
   const uint32_t len = d.length >> kLengthShift;
@@ -296,6 +304,54 @@ inline uint8_t RangeDecoder::step(State &d) {
   }
   return (uint8_t)s;
 }
+#else
+inline uint8_t RangeDecoder::step(State &d) {
+  const uint32_t *dist = dist_.data();
+  const uint32_t len = d.length >> kLengthShift;
+  uint32_t dv = d.value / len;
+  if (dv >= (1u << kLengthShift)) dv = (1u << kLengthShift) - 1;   // only on corrupt input
+  uint32_t s = start_[dv >> kTableShift];
+  {
+    const __m128i v = _mm_set1_epi32((int)dv);                     // all values < 2^31: signed compares are fine
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(dist + s + 1));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(dist + s + 5));
+    const unsigned above = (unsigned)_mm_movemask_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(a, v))) |
+                           ((unsigned)_mm_movemask_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(b, v))) << 4);
+    if (above) {
+      s += (uint32_t)__builtin_ctz(above);
+    } else {                                                       // more than eight symbols inside one bucket: rare
+      s += kSearchWidth;
+      while (dist[s + 1] <= dv) ++s;
+    }
+  }
+  const uint32_t x = dist[s] * len;
+  const uint32_t y = s + 1 == n_ ? d.length : dist[s + 1] * len;   // last symbol: y = old length
+  uint32_t value = d.value - x, length = y - x;
+  if (d.end - d.p >= 4 && length >= (1u << 8)) {                   // renorm_dec_interval, 0 - 2 bytes at once
+    const unsigned nb = (unsigned)__builtin_clz(length) >> 3;      // length >= 2^24 -> 0, >= 2^16 -> 1, >= 2^8 -> 2
+    uint32_t in;
+    memcpy(&in, d.p, 4);
+    in = __builtin_bswap32(in);
+    value = (uint32_t)(((((uint64_t)value) << 32) | in) >> (32 - 8 * nb));
+    length <<= 8 * nb;
+    d.p += nb;
+  } else {
+    while (length < kMinLength) {
+      value = (value << 8) | d.next();
+      length <<= 8;
+    }
+  }
+  d.value = value;
+  d.length = length;
+  d.ok &= s < 256;
+  ++count_[s];
+  if (--d.until == 0) {
+    update_model();
+    d.until = until_;
+  }
+  return (uint8_t)s;
+}
+#endif
 
 bool RangeDecoder::decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n) {
   State d;
@@ -316,18 +372,18 @@ bool RangeDecoder::decode_multi(RangeDecoder *const *dec, const StreamIO *io, in
     shortest = io[q].n < shortest ? io[q].n : shortest;
   }
   size_t i = 0;
-  if (k == 4)
+  auto run = [&](auto kc) {               // the common prefix of all streams, K chains in flight
+    constexpr int K = decltype(kc)::value;
     for (; i < shortest; ++i) {
-      io[0].sym[i] = dec[0]->step(st[0]);
-      io[1].sym[i] = dec[1]->step(st[1]);
-      io[2].sym[i] = dec[2]->step(st[2]);
-      io[3].sym[i] = dec[3]->step(st[3]);
+      uint8_t out[K];
+      for (int q = 0; q < K; ++q) out[q] = dec[q]->step(st[q]);
+      for (int q = 0; q < K; ++q) io[q].sym[i] = out[q];
     }
-  else if (k == 2)
-    for (; i < shortest; ++i) {
-      io[0].sym[i] = dec[0]->step(st[0]);
-      io[1].sym[i] = dec[1]->step(st[1]);
-    }
+  };
+  if (k == 8) run(std::integral_constant<int, 8>());
+  else if (k == 4) run(std::integral_constant<int, 4>());
+  else if (k == 3) run(std::integral_constant<int, 3>());
+  else if (k == 2) run(std::integral_constant<int, 2>());
   for (; i < longest; ++i)
     for (int q = 0; q < k; ++q)
       if (i < io[q].n) io[q].sym[i] = dec[q]->step(st[q]);
@@ -692,6 +748,23 @@ int mptc_arith_decode(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n
   });
 }
 
+int mptc_arith_decode_multi(int k, const uint8_t *const *code, const size_t *nbytes, uint8_t *const *sym, const size_t *n) {
+  return guarded([&]() -> int {
+  if (k < 1 || k > RangeDecoder::kMaxInterleave || !code || !nbytes || !sym || !n) return MPTC_E_ARG;
+  for (int q = 0; q < k; ++q)
+    if ((!code[q] && nbytes[q]) || (!sym[q] && n[q])) return MPTC_E_ARG;
+  RangeDecoder pool[RangeDecoder::kMaxInterleave];
+  RangeDecoder *d[RangeDecoder::kMaxInterleave];
+  RangeDecoder::StreamIO io[RangeDecoder::kMaxInterleave];
+  for (int q = 0; q < k; ++q) {
+    d[q] = &pool[q];
+    io[q] = RangeDecoder::StreamIO{code[q], nbytes[q], sym[q], n[q]};
+  }
+  const bool ok = k == 1 ? d[0]->decode_all(io[0].code, io[0].nbytes, io[0].sym, io[0].n) : RangeDecoder::decode_multi(d, io, k);
+  return ok ? MPTC_OK : MPTC_E_DATA;
+  });
+}
+
 int mptc_stream_info(const uint8_t *stream, size_t bytes, mptc_stream_header *hdr) {
   if (!stream || !hdr) return MPTC_E_ARG;
   if (bytes < 34) return MPTC_E_DATA;
@@ -793,34 +866,58 @@ int mptc_decode_stream(mptc_gpu_ctx *ctx, const uint8_t *stream, size_t bytes, i
   }
   std::vector<std::atomic<int>> left(H.n_groups);
   for (int g = 0; g < H.n_groups; ++g) left[g].store(1 + 5 * gop);
-  // tasks = records decoded by one thread in an interleaved loop: per frame the two Co|Cg and the
-  // two Y planes, the motion streams of two frames of a group, a palette alone (four at a time
-  // was measured and is no faster: the loop is bound by instruction throughput, not latency)
-  struct Task { int r[4]; int k; };
+  // tasks = records decoded by one thread in one interleaved loop (RangeDecoder::decode_multi), streams of equal
+  // length together: the motion streams of four frames of a group, the Y planes of two frames, the Co|Cg
+  // planes of two frames, a palette alone.  (With the branch-free decoder step four chains in flight are 30 %
+  // faster than two -- 148 against 114 Msym/s per thread on the GPU box's Xeon, profiles/micro/decoder_bench.py;
+  // the branchy step did not gain beyond two.)  Long tasks first: the threads take tasks in order.
+  struct Task { int r[RangeDecoder::kMaxInterleave]; int k; };
   std::vector<Task> tasks;
   tasks.reserve(recs.size());
+  auto add_task = [&](std::initializer_list<int> rs) {
+    Task t;
+    t.k = 0;
+    for (int r : rs) t.r[t.k++] = r;
+    for (int q = t.k; q < RangeDecoder::kMaxInterleave; ++q) t.r[q] = -1;
+    tasks.push_back(t);
+  };
   for (int g = 0; g < H.n_groups; ++g) {
     const int r0 = g * (1 + 5 * gop);
-    tasks.push_back({{r0, -1, -1, -1}, 1});                     // palette
-    for (int k = 0; k < gop; ++k) {
-      const int fr = r0 + 1 + 5 * k;
-      if ((k & 1) == 0) {                                       // motion of frames k, k+1
-        if (k + 1 < gop) tasks.push_back({{fr, fr + 5, -1, -1}, 2});
-        else tasks.push_back({{fr, -1, -1, -1}, 1});
+    auto fr = [&](int k) { return r0 + 1 + 5 * k; };           // records of frame k: motion, Y1, Co|Cg 1, Y2, Co|Cg 2
+    add_task({r0});                                             // palette
+    for (int k = 0; k < gop; k += 4) {                          // motion of frames k .. k+3
+      const int m = gop - k < 4 ? gop - k : 4;
+      if (m == 4) add_task({fr(k), fr(k + 1), fr(k + 2), fr(k + 3)});
+      else if (m == 3) add_task({fr(k), fr(k + 1), fr(k + 2)});
+      else if (m == 2) add_task({fr(k), fr(k + 1)});
+      else add_task({fr(k)});
+    }
+    for (int k = 0; k < gop; k += 2) {
+      if (k + 1 < gop) {
+        add_task({fr(k) + 2, fr(k) + 4, fr(k + 1) + 2, fr(k + 1) + 4});   // Co|Cg 1, 2 of two frames (equal lengths)
+        add_task({fr(k) + 1, fr(k) + 3, fr(k + 1) + 1, fr(k + 1) + 3});   // Y 1, 2 of two frames
+      } else {
+        add_task({fr(k) + 2, fr(k) + 4});
+        add_task({fr(k) + 1, fr(k) + 3});
       }
-      tasks.push_back({{fr + 2, fr + 4, -1, -1}, 2});           // Co|Cg 1, Co|Cg 2 (equal lengths)
-      tasks.push_back({{fr + 1, fr + 3, -1, -1}, 2});           // Y 1, Y 2
     }
   }
+  std::stable_sort(tasks.begin(), tasks.end(), [&](const Task &a, const Task &b) {
+    size_t na = 0, nb_ = 0;
+    for (int q = 0; q < a.k; ++q) na += recs[a.r[q]].n;
+    for (int q = 0; q < b.k; ++q) nb_ += recs[b.r[q]].n;
+    return na > nb_;
+  });
   std::atomic<int> next(0), corrupt(0);
   const int n_tasks = (int)tasks.size();
   auto worker = [&]() {
     try {
-      RangeDecoder pool4[4];
-      RangeDecoder *d[4] = {&pool4[0], &pool4[1], &pool4[2], &pool4[3]};
+      RangeDecoder pool[RangeDecoder::kMaxInterleave];
+      RangeDecoder *d[RangeDecoder::kMaxInterleave];
+      for (int q = 0; q < RangeDecoder::kMaxInterleave; ++q) d[q] = &pool[q];
       for (int i = next.fetch_add(1); i < n_tasks; i = next.fetch_add(1)) {
         const Task &t = tasks[i];
-        RangeDecoder::StreamIO io[4];
+        RangeDecoder::StreamIO io[RangeDecoder::kMaxInterleave];
         for (int q = 0; q < t.k; ++q) io[q] = {recs[t.r[q]].code, recs[t.r[q]].nbytes, recs[t.r[q]].dst, recs[t.r[q]].n};
         const bool ok = t.k == 1 ? d[0]->decode_all(io[0].code, io[0].nbytes, io[0].sym, io[0].n)
                                  : RangeDecoder::decode_multi(d, io, t.k);

@@ -58,7 +58,7 @@ class RangeDecoder {
   bool decode_all(const uint8_t *code, size_t nbytes, uint8_t *sym, size_t n);
   // Up to kMaxInterleave independent streams decoded in one interleaved loop (each with its own
   // model / decoder).
-  static constexpr int kMaxInterleave = 4;
+  static constexpr int kMaxInterleave = 8;
   struct StreamIO { const uint8_t *code; size_t nbytes; uint8_t *sym; size_t n; };
   static bool decode_multi(RangeDecoder *const *dec, const StreamIO *io, int k);
   static bool decode_pair(RangeDecoder &ma, const uint8_t *ca, size_t ba, uint8_t *sa, size_t na,

@@ -95,6 +95,43 @@ def test_arith_decode_matches_oracle_and_round_trips():
         assert np.array_equal(got, port.arith_decode(code, n))
 
 
+def test_arith_decode_extreme_distributions():
+    """The decoder's vector symbol search and its multi-byte renormalisation at their corners: a single repeated
+    symbol (intervals stay wide: zero-byte renormalisations), all 256 symbols equally rare inside one start bucket
+    (more than eight candidates per bucket: the scalar continuation), symbols 0 and 255, and short streams whose
+    code ends inside the four-byte look-ahead."""
+    rng = np.random.default_rng(9)
+    cases = [np.full(70000, 200, np.uint8), np.zeros(3000, np.uint8), np.full(3000, 255, np.uint8),
+             rng.integers(0, 256, 120000, dtype=np.uint8), np.tile(np.arange(256, dtype=np.uint8), 300),
+             np.where(rng.random(90000) < 0.999, 7, rng.integers(0, 256, 90000)).astype(np.uint8),
+             np.array([3], np.uint8), np.array([255, 0, 255], np.uint8)]
+    for s in cases:
+        code = capi.arith_encode(s)
+        assert np.array_equal(capi.arith_decode(code, s.size), s)
+        assert np.array_equal(port.arith_decode(code, s.size), s)
+
+
+def test_arith_decode_multi_equals_single_streams():
+    """mptc_arith_decode_multi: 1..8 interleaved streams, equal and ragged lengths (incl. empty), give what
+    mptc_arith_decode gives stream by stream; a truncated member fails the call."""
+    rng = np.random.default_rng(8)
+    for k in range(1, 9):
+        ns = [int(rng.integers(0, 40000)) for _ in range(k)] if k % 2 else [30000] * k
+        syms = [np.clip(rng.normal(128, rng.uniform(1, 60), n), 0, 255).astype(np.uint8) for n in ns]
+        codes = [capi.arith_encode(s) for s in syms]
+        outs = capi.arith_decode_multi(codes, ns)
+        for o, s, c in zip(outs, syms, codes):
+            assert np.array_equal(o, s)
+            assert np.array_equal(o, capi.arith_decode(c, s.size))
+    syms = [rng.integers(0, 256, 5000, dtype=np.uint8) for _ in range(4)]
+    codes = [capi.arith_encode(s) for s in syms]
+    codes[2] = codes[2][: len(codes[2]) // 2]
+    with pytest.raises(capi.MptcError):
+        capi.arith_decode_multi(codes, [5000] * 4)
+    with pytest.raises(capi.MptcError):
+        capi.arith_decode_multi(codes * 3, [5000] * 12)     # more than 8 streams
+
+
 def test_arith_decode_rejects_truncated_code():
     s = np.random.default_rng(7).integers(0, 256, 5000, dtype=np.uint8)
     code = capi.arith_encode(s)
