@@ -45,3 +45,10 @@ for _ in range(6):
     ctx.seq_encode(0, N, SA, THR, GOP)
     best = min(best, ctx.last_encode_ms("total"))
 print(f"resident (no copies)                                                    {best:7.2f} ms")
+# per-stage sums (over lanes and launches, overlapped) of the resident step and of the end-to-end step
+stages = ("total", "fit", "inter", "intra", "compact", "planes")
+ctx.seq_encode(0, N, SA, THR, GOP)
+print("resident   ", {k: round(ctx.last_encode_ms(k), 2) for k in stages})
+out = {k: v.array for k, v in pins.items()}
+ctx.encode_sequence(pin.array, SA, THR, GOP, out=out)
+print("end to end ", {k: round(ctx.last_encode_ms(k), 2) for k in stages})
