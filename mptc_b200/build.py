@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MPTC_LIB") or os.path.join(HERE, "libmptc_b200.so")   # MPTC_LIB: A/B builds (profiling)
 
 SOURCES = ["mptc_kernels.cu", "mptc_inter.cu", "mptc_inter_wide.cu", "mptc_intra_rows.cu", "mptc_sparse.cu", "mptc_pixel.cu", "mptc_decode.cu", "mptc_capi.cu", "mptc_host.cpp"]
-HEADERS = ["mptc_kernels.h", "mptc_device.cuh", "mptc_uniform_eval.cuh", "mptc_host.h", os.path.join("..", "..", "include", "mptc_gpu.h"),
+HEADERS = ["mptc_kernels.h", "mptc_device.cuh", "mptc_uniform_eval.cuh", "mptc_inter_tile.cuh", "mptc_host.h", os.path.join("..", "..", "include", "mptc_gpu.h"),
            os.path.join("..", "..", "include", "mptc_codec.h")]
 
 NVCC_FLAGS = [
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 # Sources that determine each search kernel's machine code: profiles/ncu_counters.json is stamped with
 # their hash (profiles/ncu_summary.py --json) and bench.py drops the ncu block when it no longer matches.
 KERNEL_SOURCES = {
-    "inter": ["mptc_inter_wide.cu", "mptc_inter.cu", "mptc_uniform_eval.cuh", "mptc_device.cuh", "mptc_kernels.h"],
+    "inter": ["mptc_inter_wide.cu", "mptc_inter.cu", "mptc_inter_tile.cuh", "mptc_uniform_eval.cuh", "mptc_device.cuh", "mptc_kernels.h"],
     "intra": ["mptc_intra_rows.cu", "mptc_uniform_eval.cuh", "mptc_device.cuh", "mptc_kernels.h"],
 }
 
