@@ -492,9 +492,22 @@ static bool launch_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int 
   return true;
 }
 
+template <typename E>
+static bool wide_fits_twice(int sa) {
+  int dev = 0, max_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  return 2 * (wide_layout<E>(sa).bytes + 1024 + 64) <= (size_t)max_sm;
+}
+
 bool launch_inter_search_wide(const SeqView &v, int k_in_gop, int n_gops, int sa, int thr, bool two_per_sm_only, cudaStream_t s) {
   static const bool no_int8 = getenv("MPTC_K2_NO_INT8") != nullptr;   // A/B measurements
-  if (thr < Table<int8_t>::kMax && !no_int8 && launch_wide<int8_t>(v, k_in_gop, n_gops, sa, thr, two_per_sm_only, s)) return true;
+  // The window decides, not the table type: where the 224-word int8 layout no longer fits twice on an SM (search
+  // areas above ~20) the 128-word int16 one still would, but nearly every tile of such a window overflows 128
+  // words and is handed to the 8x4 tile search -- search area 32 measured 15.4 (threshold 50, falling through
+  // from int8 to int16) and 24.4 (threshold 200) instead of 12.6 ms per GOP with round 1's kernel alone.
+  if (two_per_sm_only && !wide_fits_twice<int8_t>(sa)) return false;
+  if (thr < Table<int8_t>::kMax && !no_int8) return launch_wide<int8_t>(v, k_in_gop, n_gops, sa, thr, two_per_sm_only, s);
   if (thr < Table<int16_t>::kMax) return launch_wide<int16_t>(v, k_in_gop, n_gops, sa, thr, two_per_sm_only, s);
   return false;
 }
