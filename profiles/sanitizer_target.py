@@ -28,6 +28,9 @@ def check(ctx, frames, sa, thr, gop, tag):
 ctx = capi.Context(0)
 check(ctx, make_sequence(320, 128, 4, seed=3), 16, 50, 2, "320x128 sa16")
 check(ctx, make_sequence(512, 64, 3, seed=4), 4, 20, 3, "512x64 sa4 (rows of 4 groups)")
+check(ctx, make_sequence(320, 128, 3, seed=8), 16, 300, 3, "320x128 sa16 thr300 (K2: int16 table)")
+check(ctx, make_sequence(200, 72, 3, seed=9), 16, 40000, 3, "200x72 sa16 thr40000 (K2: round-1 tiling, int32 table; ragged tiles)")
+check(ctx, make_sequence(320, 128, 2, seed=10), 24, 50, 2, "320x128 sa24 (K2: window too large for the wide kernel)")
 rng = np.random.default_rng(5)
 noise = rng.integers(0, 256, size=(3, 96, 256, 3), dtype=np.uint8)
 check(ctx, noise, 16, 0, 3, "noise thr0 (chunked + direct paths)")
